@@ -1,0 +1,257 @@
+// HBM-bound row kernels of the backbone: LayerNorm, row statistics, fused preprocess + im2col.
+//
+//   dfd_layernorm_bf16  one warp per token row, 16-byte loads, fp32 two-pass statistics
+//                       (HF:modeling_siglip.py:348,357,618 — nn.LayerNorm(eps=1e-6) under autocast runs in fp32)
+//   dfd_rowstats_bf16   (Σx, Σx²) per row for the LN-folded GEMM epilogue
+//   dfd_patchify        u8 NHWC / f32 NCHW pixels → normalised bf16 patch matrix, optional nearest /
+//                       bilinear resample (inference_ai_human_images.py:200-204; train_fusion_head_only.py:67-74,103-104;
+//                       cifake_binary_classifier.py:716-717; HF:modeling_siglip.py:124-130,178)
+#include "dfd_common.cuh"
+
+#include <atomic>
+
+namespace dfd {
+
+extern std::atomic<int64_t> g_launches;
+
+namespace {
+
+constexpr int kRowThreads = 256;  // 8 warps = 8 rows per CTA
+constexpr int kMaxVec = 8;        // rows up to 8*32*8 = 2048 elements stay in registers
+
+__global__ void __launch_bounds__(kRowThreads)
+layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y,
+                      int64_t ldy, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      int M, int D, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (kRowThreads / 32) + warp;
+  if (row >= M) return;
+  const int nvec = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)row * ldx);
+  uint4 v[kMaxVec];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      v[i] = __ldg(xr + c);
+      const float2 a = unpack_bf16x2(v[i].x), b = unpack_bf16x2(v[i].y), c2 = unpack_bf16x2(v[i].z),
+                   d = unpack_bf16x2(v[i].w);
+      sum += ((a.x + a.y) + (b.x + b.y)) + ((c2.x + c2.y) + (d.x + d.y));
+    }
+  }
+  const float mean = warp_sum(sum) / (float)D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16x2(w[j]);
+        const float d0 = a.x - mean, d1 = a.y - mean;
+        sq += d0 * d0 + d1 * d1;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + (int64_t)row * ldy);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c + 1);
+      const float2 a = unpack_bf16x2(v[i].x), b = unpack_bf16x2(v[i].y), c2 = unpack_bf16x2(v[i].z),
+                   d = unpack_bf16x2(v[i].w);
+      uint4 o;
+      o.x = pack_bf16x2((a.x - mean) * rstd * g0.x + b0.x, (a.y - mean) * rstd * g0.y + b0.y);
+      o.y = pack_bf16x2((b.x - mean) * rstd * g0.z + b0.z, (b.y - mean) * rstd * g0.w + b0.w);
+      o.z = pack_bf16x2((c2.x - mean) * rstd * g1.x + b1.x, (c2.y - mean) * rstd * g1.y + b1.y);
+      o.w = pack_bf16x2((d.x - mean) * rstd * g1.z + b1.z, (d.y - mean) * rstd * g1.w + b1.w);
+      yr[c] = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kRowThreads)
+rowstats_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* __restrict__ stats, int M,
+                     int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (kRowThreads / 32) + warp;
+  if (row >= M) return;
+  const int nvec = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)row * ldx);
+  float s = 0.f, q = 0.f;
+  for (int c = lane; c < nvec; c += 32) {
+    const uint4 v = __ldg(xr + c);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = unpack_bf16x2(w[j]);
+      s += a.x + a.y;
+      q += a.x * a.x + a.y * a.y;
+    }
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) {
+    stats[2 * (int64_t)row] = s;
+    stats[2 * (int64_t)row + 1] = q;
+  }
+}
+
+// ---- preprocess + im2col -----------------------------------------------------------------------
+struct PatchArgs {
+  const void* pixels;
+  int fmt;  // 0 u8 NHWC, 1 f32 NCHW
+  int B, Hin, Win, S, P, G, K, mode;
+  float sy, sx;  // Hin/S, Win/S (fp32, as ATen computes them)
+  __nv_bfloat16* A;
+  int64_t lda;
+};
+
+__device__ __forceinline__ float fetch_pixel(const PatchArgs& a, int b, int c, int y, int x) {
+  if (a.fmt == 0) {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(a.pixels);
+    const float u = (float)__ldg(p + (((int64_t)b * a.Hin + y) * a.Win + x) * 3 + c);
+    // ToTensor (/255) then Normalize(mean .5, std .5), both in fp32 like torchvision
+    return (u / 255.0f - 0.5f) / 0.5f;
+  }
+  const float* p = reinterpret_cast<const float*>(a.pixels);
+  return __ldg(p + (((int64_t)b * 3 + c) * a.Hin + y) * a.Win + x);
+}
+
+__device__ __forceinline__ float sample_pixel(const PatchArgs& a, int b, int c, int y, int x) {
+  if (a.mode == 0) return fetch_pixel(a, b, c, y, x);
+  if (a.mode == 1) {
+    // ATen nearest: src = min(floor(dst * scale), in - 1), scale = in / out in fp32
+    const int ys = min((int)floorf((float)y * a.sy), a.Hin - 1);
+    const int xs = min((int)floorf((float)x * a.sx), a.Win - 1);
+    return fetch_pixel(a, b, c, ys, xs);
+  }
+  // ATen bilinear, align_corners=False: src = max(scale * (dst + .5) - .5, 0)
+  const float fy = fmaxf(a.sy * ((float)y + 0.5f) - 0.5f, 0.f);
+  const float fx = fmaxf(a.sx * ((float)x + 0.5f) - 0.5f, 0.f);
+  const int y0 = min((int)fy, a.Hin - 1), x0 = min((int)fx, a.Win - 1);
+  const int y1 = min(y0 + 1, a.Hin - 1), x1 = min(x0 + 1, a.Win - 1);
+  const float ly = fy - (float)y0, lx = fx - (float)x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  return hy * (hx * fetch_pixel(a, b, c, y0, x0) + lx * fetch_pixel(a, b, c, y0, x1)) +
+         ly * (hx * fetch_pixel(a, b, c, y1, x0) + lx * fetch_pixel(a, b, c, y1, x1));
+}
+
+// one thread = 8 consecutive columns of one patch row (one 16-byte store)
+__global__ void __launch_bounds__(256) patchify_kernel(PatchArgs a) {
+  const int vec_per_row = (int)(a.lda >> 3);
+  const int64_t total = (int64_t)a.B * a.G * a.G * vec_per_row;
+  const int PP = a.P * a.P;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int vcol = (int)(idx % vec_per_row);
+    const int64_t prow = idx / vec_per_row;
+    const int gx = (int)(prow % a.G);
+    const int gy = (int)((prow / a.G) % a.G);
+    const int b = (int)(prow / ((int64_t)a.G * a.G));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = vcol * 8 + j;
+      if (k < a.K) {
+        const int c = k / PP;
+        const int r = k - c * PP;
+        const int ky = r / a.P, kx = r - ky * a.P;
+        v[j] = sample_pixel(a, b, c, gy * a.P + ky, gx * a.P + kx);
+      } else {
+        v[j] = 0.f;  // K padding
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(a.A + prow * a.lda + (int64_t)vcol * 8) = o;
+  }
+}
+
+}  // namespace
+
+int layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,
+                   const float* beta, int M, int D, float eps, cudaStream_t st) {
+  DFD_REQUIRE(x && y && gamma && beta, DFD_ERR_BAD_ARG, "layernorm: null pointer");
+  DFD_REQUIRE(M > 0 && D > 0, DFD_ERR_SHAPE, "layernorm: M and D must be positive");
+  DFD_REQUIRE(D % 8 == 0 && D <= kMaxVec * 256, DFD_ERR_SHAPE,
+              "layernorm: D must be a multiple of 8 and <= %d (D=%d)", kMaxVec * 256, D);
+  DFD_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= D && ldy >= D, DFD_ERR_SHAPE,
+              "layernorm: leading dimensions must be multiples of 8 and >= D");
+  const int rows_per_cta = kRowThreads / 32;
+  layernorm_bf16_kernel<<<(M + rows_per_cta - 1) / rows_per_cta, kRowThreads, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, gamma,
+      beta, M, D, eps);
+  DFD_LAUNCH_CHECK();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return DFD_OK;
+}
+
+int rowstats_bf16(const void* x, int64_t ldx, float* stats, int M, int D, cudaStream_t st) {
+  DFD_REQUIRE(x && stats, DFD_ERR_BAD_ARG, "rowstats: null pointer");
+  DFD_REQUIRE(M > 0 && D > 0 && D % 8 == 0 && ldx % 8 == 0 && ldx >= D, DFD_ERR_SHAPE,
+              "rowstats: bad shape (M=%d D=%d ldx=%lld)", M, D, (long long)ldx);
+  const int rows_per_cta = kRowThreads / 32;
+  rowstats_bf16_kernel<<<(M + rows_per_cta - 1) / rows_per_cta, kRowThreads, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, stats, M, D);
+  DFD_LAUNCH_CHECK();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return DFD_OK;
+}
+
+int patchify(const void* pixels, int pix_format, int B, int Hin, int Win, int S, int P, int resize_mode,
+             void* A, int64_t lda, cudaStream_t st) {
+  DFD_REQUIRE(pixels && A, DFD_ERR_BAD_ARG, "patchify: null pointer");
+  DFD_REQUIRE(pix_format == 0 || pix_format == 1, DFD_ERR_BAD_ARG, "patchify: pix_format must be 0 or 1");
+  DFD_REQUIRE(resize_mode >= 0 && resize_mode <= 2, DFD_ERR_BAD_ARG, "patchify: resize_mode must be 0..2");
+  DFD_REQUIRE(B > 0 && Hin > 0 && Win > 0 && S > 0 && P > 0 && P <= S, DFD_ERR_SHAPE,
+              "patchify: bad shape");
+  DFD_REQUIRE(resize_mode != 0 || (Hin == S && Win == S), DFD_ERR_SHAPE,
+              "patchify: resize_mode 0 needs %dx%d input, got %dx%d", S, S, Hin, Win);
+  const int K = 3 * P * P;
+  DFD_REQUIRE(lda % 8 == 0 && lda >= K, DFD_ERR_SHAPE, "patchify: lda must be a multiple of 8 and >= 3*P*P");
+  PatchArgs a;
+  a.pixels = pixels;
+  a.fmt = pix_format;
+  a.B = B; a.Hin = Hin; a.Win = Win; a.S = S; a.P = P; a.G = S / P; a.K = K;
+  a.mode = (Hin == S && Win == S) ? 0 : resize_mode;
+  a.sy = (float)Hin / (float)S;
+  a.sx = (float)Win / (float)S;
+  a.A = reinterpret_cast<__nv_bfloat16*>(A);
+  a.lda = lda;
+  const int64_t total = (int64_t)B * a.G * a.G * (lda >> 3);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
+  patchify_kernel<<<(int)blocks, 256, 0, st>>>(a);
+  DFD_LAUNCH_CHECK();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return DFD_OK;
+}
+
+}  // namespace dfd
+
+extern "C" DFD_API int dfd_layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy,
+                                          const float* gamma, const float* beta, int M, int D,
+                                          float eps, void* stream) {
+  return dfd::layernorm_bf16(x, ldx, y, ldy, gamma, beta, M, D, eps,
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" DFD_API int dfd_rowstats_bf16(const void* x, int64_t ldx, float* stats, int M, int D,
+                                         void* stream) {
+  return dfd::rowstats_bf16(x, ldx, stats, M, D, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" DFD_API int dfd_patchify(const void* pixels, int pix_format, int B, int Hin, int Win, int S,
+                                    int P, int resize_mode, void* A, int64_t lda, void* stream) {
+  return dfd::patchify(pixels, pix_format, B, Hin, Win, S, P, resize_mode, A, lda,
+                       reinterpret_cast<cudaStream_t>(stream));
+}

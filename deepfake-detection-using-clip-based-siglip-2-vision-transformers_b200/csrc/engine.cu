@@ -1,0 +1,462 @@
+// dfd_engine: owns the repacked SigLIP vision-tower weights and the activation workspace of one
+// (device, model config) and strings the kernels into the backbone forward:
+//
+//   pixels ─patchify→ patches ─GEMM(+bias+pos)→ x
+//   L × { LN → GEMM qkv → attention → GEMM out(+residual) → LN → GEMM fc1(+gelu_tanh) → GEMM fc2(+residual) }
+//   post-LN → [last_hidden] → GEMM kv → MAP attention → GEMM out → LN → GEMM fc1(+gelu) → GEMM fc2(+residual) → pooled
+//
+// = HF SiglipVisionModel.forward (HF:modeling_siglip.py:175-186,340-362,586-654), the model the reference
+// instantiates at Siglip2sidafrozen.py:753 and calls at :787; identical math to open_clip's
+// encode_image (inference_ai_human_images.py:148).  Everything is enqueue-only on the caller's stream.
+#include "dfd_common.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace dfd {
+
+extern std::atomic<int64_t> g_launches;
+
+namespace {
+
+// dst[r, c] (dst_dtype, leading dim dst_ld) = src[r, c] (src_dtype, dense [rows, cols]); columns
+// cols..dst_cols-1 of each destination row are zero filled (K padding of the patch-embedding weight).
+__global__ void convert_rows_kernel(const void* __restrict__ src, int src_bf16, int64_t rows, int64_t cols,
+                                    void* __restrict__ dst, int dst_bf16, int64_t dst_ld, int64_t dst_cols) {
+  const int64_t total = rows * dst_cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / dst_cols, c = i % dst_cols;
+    float v = 0.f;
+    if (c < cols) {
+      v = src_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[r * cols + c])
+                   : reinterpret_cast<const float*>(src)[r * cols + c];
+    }
+    if (dst_bf16) reinterpret_cast<__nv_bfloat16*>(dst)[r * dst_ld + c] = __float2bfloat16(v);
+    else reinterpret_cast<float*>(dst)[r * dst_ld + c] = v;
+  }
+}
+
+// q[j] = bq[j] + sum_k probe[k] * Wq[j, k]   (one warp per output)
+__global__ void probe_query_kernel(const float* __restrict__ probe, const __nv_bfloat16* __restrict__ Wq,
+                                   const float* __restrict__ bq, float* __restrict__ q, int D) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= D) return;
+  float acc = 0.f;
+  for (int k = lane; k < D; k += 32) acc += probe[k] * __bfloat162float(Wq[(int64_t)j * D + k]);
+  acc = warp_sum(acc);
+  if (lane == 0) q[j] = acc + bq[j];
+}
+
+struct Layer {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  __nv_bfloat16 *w_qkv, *w_o, *w_fc1, *w_fc2;
+  float *b_qkv, *b_o, *b_fc1, *b_fc2;
+};
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+}  // namespace dfd
+
+struct dfd_engine {
+  dfd_config cfg;
+  int device, max_batch;
+  int S, P, G, N, D, I, L, H, hd, Kpe, Kpad;
+  bool finalized;
+  // weights
+  uint8_t* wslab;
+  int64_t wbytes;
+  __nv_bfloat16* w_pe;
+  float *b_pe, *pos;
+  std::vector<dfd::Layer> layers;
+  float *post_g, *post_b;
+  float *probe, *q_probe;
+  __nv_bfloat16 *w_in, *w_mo, *w_mfc1, *w_mfc2;
+  float *b_in, *b_mo, *hln_g, *hln_b, *b_mfc1, *b_mfc2;
+  std::vector<std::string> missing;  // names still to be set
+  // workspace
+  uint8_t* aslab;
+  int64_t abytes;
+  __nv_bfloat16 *patches, *x, *h, *qkv, *att, *mlp, *ao, *r, *h2, *m2;
+  void* staging;
+  int64_t staging_bytes;
+};
+
+namespace dfd {
+namespace {
+
+struct Carver {
+  uint8_t* base;
+  int64_t off;
+  template <typename T>
+  T* take(int64_t n) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += align_up(n * (int64_t)sizeof(T), 256);
+    return p;
+  }
+};
+
+void carve_weights(dfd_engine* e, uint8_t* base, int64_t* total) {
+  Carver c{base, 0};
+  const int64_t D = e->D, I = e->I, N = e->N;
+  e->w_pe = c.take<__nv_bfloat16>(D * e->Kpad);
+  e->b_pe = c.take<float>(D);
+  e->pos = c.take<float>(N * D);
+  e->layers.resize(e->L);
+  for (auto& l : e->layers) {
+    l.ln1_g = c.take<float>(D); l.ln1_b = c.take<float>(D);
+    l.ln2_g = c.take<float>(D); l.ln2_b = c.take<float>(D);
+    l.w_qkv = c.take<__nv_bfloat16>(3 * D * D); l.b_qkv = c.take<float>(3 * D);
+    l.w_o = c.take<__nv_bfloat16>(D * D); l.b_o = c.take<float>(D);
+    l.w_fc1 = c.take<__nv_bfloat16>(I * D); l.b_fc1 = c.take<float>(I);
+    l.w_fc2 = c.take<__nv_bfloat16>(D * I); l.b_fc2 = c.take<float>(D);
+  }
+  e->post_g = c.take<float>(D); e->post_b = c.take<float>(D);
+  e->probe = c.take<float>(D); e->q_probe = c.take<float>(D);
+  e->w_in = c.take<__nv_bfloat16>(3 * D * D); e->b_in = c.take<float>(3 * D);
+  e->w_mo = c.take<__nv_bfloat16>(D * D); e->b_mo = c.take<float>(D);
+  e->hln_g = c.take<float>(D); e->hln_b = c.take<float>(D);
+  e->w_mfc1 = c.take<__nv_bfloat16>(I * D); e->b_mfc1 = c.take<float>(I);
+  e->w_mfc2 = c.take<__nv_bfloat16>(D * I); e->b_mfc2 = c.take<float>(D);
+  *total = c.off;
+}
+
+void carve_acts(dfd_engine* e, uint8_t* base, int64_t* total) {
+  Carver c{base, 0};
+  const int64_t B = e->max_batch, M = B * e->N, D = e->D, I = e->I;
+  e->patches = c.take<__nv_bfloat16>(M * e->Kpad);
+  e->x = c.take<__nv_bfloat16>(M * D);
+  e->h = c.take<__nv_bfloat16>(M * D);
+  e->qkv = c.take<__nv_bfloat16>(M * 3 * D);
+  e->att = c.take<__nv_bfloat16>(M * D);
+  e->mlp = c.take<__nv_bfloat16>(M * I);
+  e->ao = c.take<__nv_bfloat16>(B * D);
+  e->r = c.take<__nv_bfloat16>(B * D);
+  e->h2 = c.take<__nv_bfloat16>(B * D);
+  e->m2 = c.take<__nv_bfloat16>(B * I);
+  *total = c.off;
+}
+
+struct Slot {
+  void* dst;
+  int dst_bf16;
+  int64_t rows, cols, dst_ld, dst_cols;
+};
+
+// name -> destination.  Returns false if the name is not part of the vision tower.
+bool resolve(dfd_engine* e, const std::string& name, Slot* s) {
+  const int64_t D = e->D, I = e->I, N = e->N;
+  auto mk = [&](void* dst, int bf, int64_t rows, int64_t cols) {
+    *s = Slot{dst, bf, rows, cols, cols, cols};
+    return true;
+  };
+  if (name == "embeddings.patch_embedding.weight") {
+    *s = Slot{e->w_pe, 1, D, e->Kpe, e->Kpad, e->Kpad};
+    return true;
+  }
+  if (name == "embeddings.patch_embedding.bias") return mk(e->b_pe, 0, 1, D);
+  if (name == "embeddings.position_embedding.weight") return mk(e->pos, 0, N, D);
+  if (name == "post_layernorm.weight") return mk(e->post_g, 0, 1, D);
+  if (name == "post_layernorm.bias") return mk(e->post_b, 0, 1, D);
+  if (name == "head.probe") return mk(e->probe, 0, 1, D);
+  if (name == "head.attention.in_proj_weight") return mk(e->w_in, 1, 3 * D, D);
+  if (name == "head.attention.in_proj_bias") return mk(e->b_in, 0, 1, 3 * D);
+  if (name == "head.attention.out_proj.weight") return mk(e->w_mo, 1, D, D);
+  if (name == "head.attention.out_proj.bias") return mk(e->b_mo, 0, 1, D);
+  if (name == "head.layernorm.weight") return mk(e->hln_g, 0, 1, D);
+  if (name == "head.layernorm.bias") return mk(e->hln_b, 0, 1, D);
+  if (name == "head.mlp.fc1.weight") return mk(e->w_mfc1, 1, I, D);
+  if (name == "head.mlp.fc1.bias") return mk(e->b_mfc1, 0, 1, I);
+  if (name == "head.mlp.fc2.weight") return mk(e->w_mfc2, 1, D, I);
+  if (name == "head.mlp.fc2.bias") return mk(e->b_mfc2, 0, 1, D);
+  const char* pre = "encoder.layers.";
+  if (name.compare(0, strlen(pre), pre) != 0) return false;
+  size_t pos = strlen(pre);
+  size_t dot = name.find('.', pos);
+  if (dot == std::string::npos) return false;
+  int li = -1;
+  try { li = std::stoi(name.substr(pos, dot - pos)); } catch (...) { return false; }
+  if (li < 0 || li >= e->L) return false;
+  Layer& l = e->layers[li];
+  const std::string t = name.substr(dot + 1);
+  if (t == "layer_norm1.weight") return mk(l.ln1_g, 0, 1, D);
+  if (t == "layer_norm1.bias") return mk(l.ln1_b, 0, 1, D);
+  if (t == "layer_norm2.weight") return mk(l.ln2_g, 0, 1, D);
+  if (t == "layer_norm2.bias") return mk(l.ln2_b, 0, 1, D);
+  if (t == "self_attn.q_proj.weight") return mk(l.w_qkv, 1, D, D);
+  if (t == "self_attn.k_proj.weight") return mk(l.w_qkv + D * D, 1, D, D);
+  if (t == "self_attn.v_proj.weight") return mk(l.w_qkv + 2 * D * D, 1, D, D);
+  if (t == "self_attn.q_proj.bias") return mk(l.b_qkv, 0, 1, D);
+  if (t == "self_attn.k_proj.bias") return mk(l.b_qkv + D, 0, 1, D);
+  if (t == "self_attn.v_proj.bias") return mk(l.b_qkv + 2 * D, 0, 1, D);
+  if (t == "self_attn.qkv.weight") return mk(l.w_qkv, 1, 3 * D, D);  // timm fused layout (q, k, v)
+  if (t == "self_attn.qkv.bias") return mk(l.b_qkv, 0, 1, 3 * D);
+  if (t == "self_attn.out_proj.weight") return mk(l.w_o, 1, D, D);
+  if (t == "self_attn.out_proj.bias") return mk(l.b_o, 0, 1, D);
+  if (t == "mlp.fc1.weight") return mk(l.w_fc1, 1, I, D);
+  if (t == "mlp.fc1.bias") return mk(l.b_fc1, 0, 1, I);
+  if (t == "mlp.fc2.weight") return mk(l.w_fc2, 1, D, I);
+  if (t == "mlp.fc2.bias") return mk(l.b_fc2, 0, 1, D);
+  return false;
+}
+
+void list_required(dfd_engine* e) {
+  auto& m = e->missing;
+  m = {"embeddings.patch_embedding.weight", "embeddings.patch_embedding.bias",
+       "embeddings.position_embedding.weight", "post_layernorm.weight", "post_layernorm.bias", "head.probe",
+       "head.attention.in_proj_weight", "head.attention.in_proj_bias", "head.attention.out_proj.weight",
+       "head.attention.out_proj.bias", "head.layernorm.weight", "head.layernorm.bias", "head.mlp.fc1.weight",
+       "head.mlp.fc1.bias", "head.mlp.fc2.weight", "head.mlp.fc2.bias"};
+  const char* per[] = {"layer_norm1.weight", "layer_norm1.bias", "layer_norm2.weight", "layer_norm2.bias",
+                       "self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight",
+                       "self_attn.q_proj.bias", "self_attn.k_proj.bias", "self_attn.v_proj.bias",
+                       "self_attn.out_proj.weight", "self_attn.out_proj.bias", "mlp.fc1.weight", "mlp.fc1.bias",
+                       "mlp.fc2.weight", "mlp.fc2.bias"};
+  for (int i = 0; i < e->L; ++i)
+    for (const char* p : per) m.push_back("encoder.layers." + std::to_string(i) + "." + p);
+}
+
+void mark_set(dfd_engine* e, const std::string& name) {
+  auto erase = [&](const std::string& n) {
+    for (size_t i = 0; i < e->missing.size(); ++i)
+      if (e->missing[i] == n) { e->missing.erase(e->missing.begin() + i); return; }
+  };
+  const size_t p = name.find("self_attn.qkv.");
+  if (p != std::string::npos) {  // fused tensor satisfies the three split names
+    const std::string head = name.substr(0, p), tail = name.substr(p + strlen("self_attn.qkv."));
+    erase(head + "self_attn.q_proj." + tail);
+    erase(head + "self_attn.k_proj." + tail);
+    erase(head + "self_attn.v_proj." + tail);
+  } else {
+    erase(name);
+  }
+}
+
+struct DeviceGuard {
+  int prev;
+  bool ok;
+  explicit DeviceGuard(int dev) : prev(-1), ok(false) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+}  // namespace dfd
+
+using namespace dfd;
+
+extern "C" DFD_API int dfd_engine_create(const dfd_config* cfg, int device, int max_batch, dfd_engine** out) {
+  DFD_REQUIRE(cfg && out, DFD_ERR_BAD_ARG, "engine_create: null pointer");
+  *out = nullptr;
+  DFD_REQUIRE(max_batch > 0, DFD_ERR_BAD_ARG, "engine_create: max_batch must be positive");
+  DFD_REQUIRE(cfg->patch > 0 && cfg->image_size >= cfg->patch && cfg->hidden > 0 && cfg->inter > 0 &&
+                  cfg->layers > 0 && cfg->heads > 0,
+              DFD_ERR_BAD_ARG, "engine_create: bad config");
+  DFD_REQUIRE(cfg->hidden % cfg->heads == 0, DFD_ERR_SHAPE, "engine_create: hidden %% heads != 0");
+  const int hd = cfg->hidden / cfg->heads;
+  DFD_REQUIRE(hd == 64 || hd == 72, DFD_ERR_UNSUPPORTED, "engine_create: head dim %d unsupported (64, 72)", hd);
+  DFD_REQUIRE(cfg->hidden % 8 == 0 && cfg->inter % 8 == 0, DFD_ERR_SHAPE,
+              "engine_create: hidden and inter must be multiples of 8");
+  DFD_REQUIRE(cfg->gelu_tanh == 1, DFD_ERR_UNSUPPORTED, "engine_create: only gelu_pytorch_tanh backbones");
+  DFD_REQUIRE(cfg->fuse_ln == 0, DFD_ERR_UNIMPLEMENTED, "engine_create: fuse_ln=1 not implemented yet");
+  int ndev = 0;
+  DFD_CUDA(cudaGetDeviceCount(&ndev));
+  DFD_REQUIRE(device >= 0 && device < ndev, DFD_ERR_NO_DEVICE, "engine_create: device %d of %d", device, ndev);
+  cudaDeviceProp prop;
+  DFD_CUDA(cudaGetDeviceProperties(&prop, device));
+  DFD_REQUIRE(prop.major == 10, DFD_ERR_UNSUPPORTED,
+              "engine_create: device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
+  DeviceGuard guard(device);
+  DFD_REQUIRE(guard.ok, DFD_ERR_CUDA, "engine_create: cudaSetDevice(%d) failed", device);
+
+  dfd_engine* e = new dfd_engine();
+  e->cfg = *cfg;
+  e->device = device;
+  e->max_batch = max_batch;
+  e->S = cfg->image_size; e->P = cfg->patch; e->G = e->S / e->P; e->N = e->G * e->G;
+  e->D = cfg->hidden; e->I = cfg->inter; e->L = cfg->layers; e->H = cfg->heads; e->hd = hd;
+  e->Kpe = 3 * e->P * e->P;
+  e->Kpad = (int)align_up(e->Kpe, 64);
+  e->finalized = false;
+  e->wslab = e->aslab = nullptr;
+  e->staging = nullptr;
+  e->staging_bytes = 0;
+  carve_weights(e, nullptr, &e->wbytes);
+  carve_acts(e, nullptr, &e->abytes);
+  cudaError_t err = cudaMalloc(&e->wslab, e->wbytes);
+  if (err == cudaSuccess) err = cudaMalloc(&e->aslab, e->abytes);
+  if (err != cudaSuccess) {
+    if (e->wslab) cudaFree(e->wslab);
+    delete e;
+    return cuda_fail(err, "cudaMalloc(engine slabs)", __FILE__, __LINE__);
+  }
+  carve_weights(e, e->wslab, &e->wbytes);
+  carve_acts(e, e->aslab, &e->abytes);
+  cudaMemset(e->wslab, 0, e->wbytes);
+  list_required(e);
+  *out = e;
+  return DFD_OK;
+}
+
+extern "C" DFD_API int dfd_engine_destroy(dfd_engine* e) {
+  if (!e) return DFD_OK;
+  DeviceGuard guard(e->device);
+  cudaDeviceSynchronize();
+  if (e->wslab) cudaFree(e->wslab);
+  if (e->aslab) cudaFree(e->aslab);
+  if (e->staging) cudaFree(e->staging);
+  delete e;
+  return DFD_OK;
+}
+
+extern "C" DFD_API int64_t dfd_engine_workspace_bytes(const dfd_engine* e) {
+  return e ? e->wbytes + e->abytes : 0;
+}
+
+extern "C" DFD_API int dfd_engine_set_tensor(dfd_engine* e, const char* name, const void* data, int dtype,
+                                             int ndim, const int64_t* shape, int on_host) {
+  DFD_REQUIRE(e && name && data && shape, DFD_ERR_BAD_ARG, "set_tensor: null pointer");
+  DFD_REQUIRE(dtype == 0 || dtype == 1, DFD_ERR_BAD_ARG, "set_tensor: dtype must be 0 (f32) or 1 (bf16)");
+  DFD_REQUIRE(ndim >= 0 && ndim <= 8, DFD_ERR_BAD_ARG, "set_tensor: bad ndim");
+  Slot s;
+  DFD_REQUIRE(resolve(e, name, &s), DFD_ERR_BAD_ARG, "set_tensor: unknown tensor name '%s'", name);
+  int64_t numel = 1;
+  for (int i = 0; i < ndim; ++i) numel *= shape[i];
+  DFD_REQUIRE(numel == s.rows * s.cols, DFD_ERR_SHAPE, "set_tensor: '%s' has %lld elements, expected %lld", name,
+              (long long)numel, (long long)(s.rows * s.cols));
+  DeviceGuard guard(e->device);
+  DFD_REQUIRE(guard.ok, DFD_ERR_CUDA, "set_tensor: cudaSetDevice failed");
+  const void* src = data;
+  if (on_host) {
+    const int64_t bytes = numel * (dtype ? 2 : 4);
+    if (bytes > e->staging_bytes) {
+      if (e->staging) { cudaDeviceSynchronize(); cudaFree(e->staging); e->staging = nullptr; }
+      DFD_CUDA(cudaMalloc(&e->staging, bytes));
+      e->staging_bytes = bytes;
+    }
+    DFD_CUDA(cudaMemcpy(e->staging, data, bytes, cudaMemcpyHostToDevice));
+    src = e->staging;
+  }
+  const int64_t total = s.rows * s.dst_cols;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  convert_rows_kernel<<<blocks, 256>>>(src, dtype, s.rows, s.cols, s.dst, s.dst_bf16, s.dst_ld, s.dst_cols);
+  DFD_LAUNCH_CHECK();
+  DFD_CUDA(cudaDeviceSynchronize());  // weight loading is not a hot path; keeps staging reuse simple
+  mark_set(e, name);
+  e->finalized = false;
+  return DFD_OK;
+}
+
+extern "C" DFD_API int dfd_engine_finalize(dfd_engine* e) {
+  DFD_REQUIRE(e, DFD_ERR_BAD_ARG, "finalize: null engine");
+  if (!e->missing.empty()) {
+    set_last_error("finalize: %zu tensors not set, first: %s", e->missing.size(), e->missing[0].c_str());
+    return DFD_ERR_STATE;
+  }
+  DeviceGuard guard(e->device);
+  DFD_REQUIRE(guard.ok, DFD_ERR_CUDA, "finalize: cudaSetDevice failed");
+  // the MAP query is batch independent: q = probe · W_qᵀ + b_q  (first D rows of in_proj)
+  probe_query_kernel<<<(e->D + 7) / 8, 256>>>(e->probe, e->w_in, e->b_in, e->q_probe, e->D);
+  DFD_LAUNCH_CHECK();
+  DFD_CUDA(cudaDeviceSynchronize());
+  e->finalized = true;
+  return DFD_OK;
+}
+
+#define DFD_TRY(expr)            \
+  do {                           \
+    const int _rc = (expr);      \
+    if (_rc != DFD_OK) return _rc; \
+  } while (0)
+
+extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int pix_format, int B, int Hin,
+                                          int Win, int resize_mode, void* pooled, void* last_hidden,
+                                          void* stream) {
+  DFD_REQUIRE(e && pixels && pooled, DFD_ERR_BAD_ARG, "forward: null pointer");
+  DFD_REQUIRE(e->finalized, DFD_ERR_STATE, "forward: engine not finalized");
+  DFD_REQUIRE(B > 0 && B <= e->max_batch, DFD_ERR_SHAPE, "forward: batch %d outside 1..%d", B, e->max_batch);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int N = e->N, D = e->D, I = e->I, H = e->H, hd = e->hd;
+  const int M = B * N;
+  const float eps = e->cfg.ln_eps;
+  const float scale = 1.0f / sqrtf((float)hd);
+
+  DFD_TRY(patchify(pixels, pix_format, B, Hin, Win, e->S, e->P, resize_mode, e->patches, e->Kpad, st));
+  {
+    dfd_gemm_epilogue ep{};
+    ep.bias = e->b_pe;
+    ep.pos = e->pos;
+    ep.pos_rows = N;
+    DFD_TRY(gemm_bf16_dispatch(e->patches, e->Kpad, e->w_pe, e->Kpad, e->x, D, M, D, e->Kpad, &ep, 0, st));
+  }
+  for (int li = 0; li < e->L; ++li) {
+    const Layer& l = e->layers[li];
+    DFD_TRY(layernorm_bf16(e->x, D, e->h, D, l.ln1_g, l.ln1_b, M, D, eps, st));
+    {
+      dfd_gemm_epilogue ep{};
+      ep.bias = l.b_qkv;
+      DFD_TRY(gemm_bf16_dispatch(e->h, D, l.w_qkv, D, e->qkv, 3 * D, M, 3 * D, D, &ep, 0, st));
+    }
+    DFD_TRY(attention_bf16(e->qkv, 3 * D, e->att, D, B, N, H, hd, scale, st));
+    {
+      dfd_gemm_epilogue ep{};
+      ep.bias = l.b_o;
+      ep.residual = e->x;
+      ep.ldr = D;
+      DFD_TRY(gemm_bf16_dispatch(e->att, D, l.w_o, D, e->x, D, M, D, D, &ep, 0, st));
+    }
+    DFD_TRY(layernorm_bf16(e->x, D, e->h, D, l.ln2_g, l.ln2_b, M, D, eps, st));
+    {
+      dfd_gemm_epilogue ep{};
+      ep.bias = l.b_fc1;
+      ep.act = 1;
+      DFD_TRY(gemm_bf16_dispatch(e->h, D, l.w_fc1, D, e->mlp, I, M, I, D, &ep, 0, st));
+    }
+    {
+      dfd_gemm_epilogue ep{};
+      ep.bias = l.b_fc2;
+      ep.residual = e->x;
+      ep.ldr = D;
+      DFD_TRY(gemm_bf16_dispatch(e->mlp, I, l.w_fc2, I, e->x, D, M, D, I, &ep, 0, st));
+    }
+  }
+  __nv_bfloat16* xp = last_hidden ? reinterpret_cast<__nv_bfloat16*>(last_hidden) : e->h;
+  DFD_TRY(layernorm_bf16(e->x, D, xp, D, e->post_g, e->post_b, M, D, eps, st));
+  {  // K | V projection of every token (rows D..3D of in_proj)
+    dfd_gemm_epilogue ep{};
+    ep.bias = e->b_in + D;
+    DFD_TRY(gemm_bf16_dispatch(xp, D, e->w_in + (int64_t)D * D, D, e->qkv, 2 * D, M, 2 * D, D, &ep, 0, st));
+  }
+  DFD_TRY(map_attention_bf16(e->qkv, 2 * D, e->q_probe, e->ao, D, B, N, H, hd, scale, st));
+  {
+    dfd_gemm_epilogue ep{};
+    ep.bias = e->b_mo;
+    DFD_TRY(gemm_bf16_dispatch(e->ao, D, e->w_mo, D, e->r, D, B, D, D, &ep, 0, st));
+  }
+  DFD_TRY(layernorm_bf16(e->r, D, e->h2, D, e->hln_g, e->hln_b, B, D, eps, st));
+  {
+    dfd_gemm_epilogue ep{};
+    ep.bias = e->b_mfc1;
+    ep.act = 1;
+    DFD_TRY(gemm_bf16_dispatch(e->h2, D, e->w_mfc1, D, e->m2, I, B, I, D, &ep, 0, st));
+  }
+  {
+    dfd_gemm_epilogue ep{};
+    ep.bias = e->b_mfc2;
+    ep.residual = e->r;
+    ep.ldr = D;
+    DFD_TRY(gemm_bf16_dispatch(e->m2, I, e->w_mfc2, I, pooled, D, B, D, I, &ep, 0, st));
+  }
+  return DFD_OK;
+}

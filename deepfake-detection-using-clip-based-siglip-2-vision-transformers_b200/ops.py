@@ -1,0 +1,273 @@
+"""Torch-tensor wrappers over the op-level C ABI of libdfd.so (include/dfd.h).
+
+PyTorch is used here only for device memory and streams; every function enqueues hand-written
+sm_100a kernels on the current CUDA stream and returns torch tensors.  There is no CPU fallback:
+non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import GemmEpilogue, HeadWeights, ScoreWeights, Scores, check, current_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dfd ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = 0, pos=None, residual=None,
+              ln_rowstats=None, ln_colsum=None, ln_dim: int = 0, ln_eps: float = 1e-6, stats_out=None,
+              out: Optional[torch.Tensor] = None, tile_n: int = 0) -> torch.Tensor:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K].T); bf16 in/out, fp32 accumulate in TMEM (dfd_gemm_bf16)."""
+    _need_cuda(a, w, bias, pos, residual, out)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    epi = GemmEpilogue()
+    epi.bias = _p(bias)
+    epi.act = act
+    epi.pos = _p(pos)
+    epi.pos_rows = 0 if pos is None else pos.shape[0]
+    epi.residual = _p(residual)
+    epi.ldr = 0 if residual is None else residual.stride(0)
+    epi.ln_rowstats = _p(ln_rowstats)
+    epi.ln_colsum = _p(ln_colsum)
+    epi.ln_dim = ln_dim
+    epi.ln_eps = ln_eps
+    epi.stats_out = _p(stats_out)
+    lib = _lib.load()
+    if tile_n:
+        rc = lib.dfd_gemm_bf16_tile(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
+                                    out.stride(0), M, N, K, C.byref(epi), tile_n, current_stream())
+    else:
+        rc = lib.dfd_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
+                               out.stride(0), M, N, K, C.byref(epi), current_stream())
+    check(rc)
+    return out
+
+
+def layernorm_bf16(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    _need_cuda(x, gamma, beta)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    y = torch.empty_like(x)
+    check(_lib.load().dfd_layernorm_bf16(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), gamma.data_ptr(),
+                                         beta.data_ptr(), x.shape[0], x.shape[1], eps, current_stream()))
+    return y
+
+
+def rowstats_bf16(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    st = torch.empty((x.shape[0], 2), dtype=torch.float32, device=x.device)
+    check(_lib.load().dfd_rowstats_bf16(x.data_ptr(), x.stride(0), st.data_ptr(), x.shape[0], x.shape[1],
+                                        current_stream()))
+    return st
+
+
+def attention_bf16(qkv: torch.Tensor, B: int, N: int, H: int, hd: int, scale: Optional[float] = None) -> torch.Tensor:
+    """qkv [B*N, 3*H*hd] (q | k | v) -> [B*N, H*hd]; non-causal softmax(q k^T scale) v."""
+    _need_cuda(qkv)
+    assert qkv.dtype == torch.bfloat16 and qkv.shape == (B * N, 3 * H * hd) and qkv.stride(1) == 1
+    out = torch.empty((B * N, H * hd), dtype=torch.bfloat16, device=qkv.device)
+    scale = (1.0 / math.sqrt(hd)) if scale is None else scale
+    check(_lib.load().dfd_attention_bf16(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), B, N, H, hd,
+                                         scale, current_stream()))
+    return out
+
+
+def map_attention_bf16(kv: torch.Tensor, q: torch.Tensor, B: int, N: int, H: int, hd: int,
+                       scale: Optional[float] = None) -> torch.Tensor:
+    _need_cuda(kv, q)
+    assert kv.dtype == torch.bfloat16 and kv.shape == (B * N, 2 * H * hd) and kv.stride(1) == 1
+    assert q.dtype == torch.float32 and q.numel() == H * hd
+    out = torch.empty((B, H * hd), dtype=torch.bfloat16, device=kv.device)
+    scale = (1.0 / math.sqrt(hd)) if scale is None else scale
+    check(_lib.load().dfd_map_attention_bf16(kv.data_ptr(), kv.stride(0), q.data_ptr(), out.data_ptr(),
+                                             out.stride(0), B, N, H, hd, scale, current_stream()))
+    return out
+
+
+RESIZE_NONE, RESIZE_NEAREST, RESIZE_BILINEAR = 0, 1, 2
+
+
+def patchify(pixels: torch.Tensor, S: int, P: int, resize_mode: int = RESIZE_NONE, lda: Optional[int] = None) -> torch.Tensor:
+    """u8 NHWC [B,H,W,3] or f32 NCHW [B,3,H,W] -> bf16 patch matrix [B*G*G, lda] (column order c,ky,kx)."""
+    _need_cuda(pixels)
+    pixels = pixels.contiguous()
+    if pixels.dtype == torch.uint8:
+        fmt, (B, Hin, Win, ch) = 0, pixels.shape
+    elif pixels.dtype == torch.float32:
+        fmt, (B, ch, Hin, Win) = 1, pixels.shape
+    else:
+        raise TypeError("patchify: pixels must be uint8 NHWC or float32 NCHW")
+    assert ch == 3
+    K = 3 * P * P
+    lda = lda or (K + 63) // 64 * 64
+    G = S // P
+    A = torch.empty((B * G * G, lda), dtype=torch.bfloat16, device=pixels.device)
+    check(_lib.load().dfd_patchify(pixels.data_ptr(), fmt, B, Hin, Win, S, P, resize_mode, A.data_ptr(), lda,
+                                   current_stream()))
+    return A
+
+
+def _f32(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+class HeadParams:
+    """Device copy of a classifier head (H-A: kind 1, H-B: kind 2, none: kind 0) for dfd_head_fwd."""
+
+    def __init__(self, kind: int, dim: int, norm_eps: float, tensors: dict, device, ln_eps: float = 1e-5):
+        self.kind, self.dim = kind, dim
+        self._keep = {k: _f32(v, device) for k, v in tensors.items()}
+        w = HeadWeights()
+        w.kind, w.dim, w.norm_eps, w.ln_eps = kind, dim, norm_eps, ln_eps
+        for k, v in self._keep.items():
+            setattr(w, k, v.data_ptr())
+        self.struct = w
+
+
+def head_fwd(head: HeadParams, pooled: torch.Tensor, prototypes: Optional[torch.Tensor] = None,
+             want_features: bool = False):
+    """pooled bf16 [B,D] -> (features f32 [B,D] | None, z_sig f32 [B] | None, p_proto f32 [B] | None)."""
+    _need_cuda(pooled, prototypes)
+    assert pooled.dtype == torch.bfloat16 and pooled.dim() == 2 and pooled.stride(1) == 1
+    B, D = pooled.shape
+    assert D == head.dim
+    dev = pooled.device
+    feats = torch.empty((B, D), dtype=torch.float32, device=dev) if want_features else None
+    z = torch.empty((B,), dtype=torch.float32, device=dev) if head.kind != 0 else None
+    pp = None
+    if prototypes is not None:
+        assert prototypes.dtype == torch.float32 and prototypes.shape == (2, D) and prototypes.is_contiguous()
+        pp = torch.empty((B,), dtype=torch.float32, device=dev)
+    check(_lib.load().dfd_head_fwd(C.byref(head.struct), pooled.data_ptr(), pooled.stride(0), B, _p(prototypes),
+                                   _p(feats), _p(z), _p(pp), current_stream()))
+    return feats, z, pp
+
+
+def freq_features(gray256: torch.Tensor, luts, eps: float = 1e-8, zscore: bool = False,
+                  scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """gray256 f32 [B,256,256] in [0,1] -> 24-d features f32 [B,24] (dfd_freq_features)."""
+    _need_cuda(gray256)
+    assert gray256.dtype == torch.float32 and gray256.shape[1:] == (256, 256) and gray256.is_contiguous()
+    B = gray256.shape[0]
+    lib = _lib.load()
+    need = lib.dfd_freq_scratch_bytes(B)
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty((need,), dtype=torch.uint8, device=gray256.device)
+    band, rbin, sector = luts
+    feats = torch.empty((B, 24), dtype=torch.float32, device=gray256.device)
+    check(lib.dfd_freq_features(gray256.data_ptr(), B, band.data_ptr(), rbin.data_ptr(), sector.data_ptr(), eps,
+                                int(zscore), scratch.data_ptr(), feats.data_ptr(), current_stream()))
+    return feats
+
+
+class ScoreParams:
+    """Device copy of FreqMLP + fusion + CORAL parameters for dfd_score_epilogue (gen 1 or 2)."""
+
+    def __init__(self, gen: int, device, *, freq_state: Optional[dict] = None, fusion_state: Optional[dict] = None,
+                 coral_cuts_logit=(0.0, 0.0, 0.0, 0.0), coral_temp: float = 1.0, freq_temp: float = 1.25):
+        self.gen = gen
+        self._keep = []
+        w = ScoreWeights()
+        w.gen = gen
+        w.freq_temp = freq_temp
+
+        def put(t):
+            d = _f32(t, device)
+            self._keep.append(d)
+            return d.data_ptr()
+
+        if freq_state is not None:
+            if gen == 1:
+                w.g1_ln_w, w.g1_ln_b = put(freq_state["net.0.weight"]), put(freq_state["net.0.bias"])
+                w.g1_w1, w.g1_b1 = put(freq_state["net.1.weight"]), put(freq_state["net.1.bias"])
+                w.g1_w2, w.g1_b2 = put(freq_state["net.3.weight"]), put(freq_state["net.3.bias"])
+            else:
+                w.g2_mean, w.g2_std = put(freq_state["normer.mean"]), put(freq_state["normer.std"])
+                w.g2_alpha, w.g2_beta = put(freq_state["contrast.alpha"]), put(freq_state["contrast.beta"])
+                w.g2_gates = put(freq_state["band.gates"])
+                for b in range(2):
+                    names = ("norm.weight", "norm.bias", "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")
+                    for i, n in enumerate(names):
+                        w.g2_blk[b][i] = put(freq_state[f"blocks.{b}.{n}"])
+                w.g2_head_w, w.g2_head_b = put(freq_state["head.weight"]), put(freq_state["head.bias"])
+                w.g2_temp = float(freq_state["temp.T"])
+        if fusion_state is not None:
+            if gen == 1:
+                fw = fusion_state["fc.weight"].detach().float().reshape(-1).tolist()
+                w.g1_fc_w[0], w.g1_fc_w[1] = fw[0], fw[1]
+                w.g1_fc_b = float(fusion_state["fc.bias"].detach().float().reshape(-1)[0])
+            else:
+                w.f2_w0, w.f2_b0 = put(fusion_state["mlp.0.weight"]), put(fusion_state["mlp.0.bias"])
+                w.f2_w1, w.f2_b1 = put(fusion_state["mlp.2.weight"]), put(fusion_state["mlp.2.bias"])
+                w.f2_temp = float(fusion_state["temp.T"])
+        for i in range(4):
+            w.coral_cuts[i] = float(coral_cuts_logit[i])
+        w.coral_temp = float(coral_temp)
+        self.struct = w
+
+
+SCORE_FIELDS = ("z_freq", "z", "z_scaled", "p_raw", "risk_probs", "p_coral", "entropy", "p_blend", "risk_idx")
+
+
+def score_epilogue(params: ScoreParams, z_sig: torch.Tensor, feats: Optional[torch.Tensor] = None,
+                   z_freq: Optional[torch.Tensor] = None) -> dict:
+    """One warp per sample: FreqMLP -> fusion -> temperature -> CORAL.  Returns a dict of SoA tensors."""
+    _need_cuda(z_sig, feats, z_freq)
+    assert z_sig.dtype == torch.float32 and z_sig.is_contiguous()
+    B = z_sig.numel()
+    dev = z_sig.device
+    if feats is not None:
+        assert feats.dtype == torch.float32 and feats.shape == (B, 24) and feats.is_contiguous()
+    if z_freq is not None:
+        assert z_freq.dtype == torch.float32 and z_freq.numel() == B and z_freq.is_contiguous()
+    out = {k: torch.empty((B,), dtype=torch.float32, device=dev) for k in SCORE_FIELDS}
+    out["risk_probs"] = torch.empty((B, 5), dtype=torch.float32, device=dev)
+    out["risk_idx"] = torch.empty((B,), dtype=torch.int32, device=dev)
+    s = Scores()
+    for k in SCORE_FIELDS:
+        setattr(s, k, out[k].data_ptr())
+    check(_lib.load().dfd_score_epilogue(C.byref(params.struct), z_sig.data_ptr(), _p(feats), _p(z_freq), B,
+                                         C.byref(s), current_stream()))
+    out["z_sig"] = z_sig
+    return out
+
+
+FUSION_PARAM_ORDER = ("mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias", "temp.T")
+
+
+def fusion_fwd_bwd(params195: torch.Tensor, z_freq: torch.Tensor, z_sig: torch.Tensor, y: torch.Tensor,
+                   inv_global_batch: Optional[float] = None, want_logits: bool = False):
+    """AdaptiveFusionHead forward + backward of mean BCE-with-logits. Returns (loss[1], grads[195], logits|None);
+    loss and grads are this rank's partial sums (allreduce-sum them across ranks)."""
+    _need_cuda(params195, z_freq, z_sig, y)
+    for t in (params195, z_freq, z_sig, y):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert params195.numel() == 195
+    B = z_freq.numel()
+    dev = z_freq.device
+    loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+    grads = torch.zeros((195,), dtype=torch.float32, device=dev)
+    logits = torch.empty((B,), dtype=torch.float32, device=dev) if want_logits else None
+    inv = (1.0 / B) if inv_global_batch is None else inv_global_batch
+    check(_lib.load().dfd_fusion_fwd_bwd(params195.data_ptr(), z_freq.data_ptr(), z_sig.data_ptr(), y.data_ptr(), B,
+                                         inv, loss.data_ptr(), grads.data_ptr(), _p(logits), current_stream()))
+    return loss, grads, logits

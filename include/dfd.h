@@ -1,0 +1,223 @@
+/*
+ * dfd.h — C ABI of libdfd.so, the B200 (sm_100a) implementation of the deepfake-detection hot path
+ * (SigLIP-2 ViT forward + FreqMLP spectrum features + fusion head + temperature/CORAL scoring).
+ *
+ * The reference (joesound212985/Deepfake-Detection-using-CLIP-Based-SigLIP-2-Vision-Transformers)
+ * has no FFI of its own: its seam is Python duck typing of nn.Modules.  Each entry
+ * point below therefore cites the reference Python call it replaces (file:line under /root/reference,
+ * or HF: = transformers/models/siglip/modeling_siglip.py which the reference calls at
+ * Siglip2sidafrozen.py:753,787).  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - every call is enqueue-only on `stream` (a cudaStream_t passed as void*), never synchronises,
+ *     except the *_host entry points (which copy, run and synchronise) and dfd_engine_create/destroy;
+ *   - return value: 0 = ok, negative = error (enum below); dfd_last_error() gives the text
+ *     (thread-local).  No exceptions or aborts cross the ABI.  There is NO CPU fallback: without a
+ *     CUDA device every compute entry point returns DFD_ERR_NO_DEVICE / DFD_ERR_CUDA.
+ *   - bf16 tensors are row-major with an explicit leading dimension in ELEMENTS.
+ */
+#ifndef DFD_H_
+#define DFD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define DFD_API
+#else
+#define DFD_API __attribute__((visibility("default")))
+#endif
+
+enum {
+  DFD_OK = 0,
+  DFD_ERR_BAD_ARG = -1,
+  DFD_ERR_SHAPE = -2,
+  DFD_ERR_UNSUPPORTED = -3,
+  DFD_ERR_CUDA = -4,
+  DFD_ERR_NO_DEVICE = -5,
+  DFD_ERR_UNIMPLEMENTED = -6,
+  DFD_ERR_STATE = -7
+};
+
+DFD_API const char* dfd_last_error(void);
+DFD_API int dfd_version(void);
+/* Number of kernels launched by this library in the calling process since load (bench "gpu_launches"). */
+DFD_API int64_t dfd_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Op level (each is one kernel family; the engine below strings them together)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Epilogue of the tcgen05 GEMM.  out = epi(A·Wᵀ):
+ *   v = acc                                   (fp32, TMEM)
+ *   if (ln_colsum) v = rstd_m·(v − mean_m·ln_colsum[n])      — LayerNorm folded through the GEMM:
+ *                     mean/rstd from ln_rowstats[m] = (Σx, Σx²) over ln_dim columns, eps ln_eps
+ *   if (bias)     v += bias[n]
+ *   if (act == 1) v = gelu_tanh(v)             HF:modeling_siglip.py:323-327 (gelu_pytorch_tanh)
+ *   if (pos)      v += pos[(m % pos_rows)·N + n]   HF:modeling_siglip.py:179-185 (position embedding)
+ *   if (residual) v += residual[m·ldr + n]     HF:modeling_siglip.py:354,359 (residual adds)
+ *   C[m·ldc + n] = bf16(v);  if (stats_out) stats_out[m] += (Σ_n bf16(v), Σ_n bf16(v)²)  (atomics)
+ */
+typedef struct dfd_gemm_epilogue {
+  const float* bias;         /* [N] fp32 or NULL */
+  int act;                   /* 0 none, 1 gelu_tanh */
+  const float* pos;          /* [pos_rows, N] fp32 or NULL */
+  int pos_rows;
+  const void* residual;      /* bf16 [M, ldr] or NULL; may alias C */
+  int64_t ldr;
+  const float* ln_rowstats;  /* [M,2] fp32 (Σx, Σx²) or NULL */
+  const float* ln_colsum;    /* [N] fp32 */
+  int ln_dim;
+  float ln_eps;
+  float* stats_out;          /* [M,2] fp32, accumulated atomically, or NULL */
+} dfd_gemm_epilogue;
+
+/* C[M,N] (bf16) = epi(A[M,K] (bf16, lda) · W[N,K]ᵀ (bf16, ldw)), fp32 accumulate in TMEM.
+ * Replaces nn.Linear / nn.Conv2d-as-GEMM under bf16 autocast: HF:modeling_siglip.py:285-287 (q/k/v),
+ * :308 (out_proj), :324,326 (fc1/fc2), :178 (patch embedding).  Requires K%8==0, N%8==0, 16-byte
+ * aligned pointers and leading dimensions that are multiples of 8 elements. */
+DFD_API int dfd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C,
+                          int64_t ldc, int M, int N, int K, const dfd_gemm_epilogue* epi,
+                          void* stream);
+
+/* y[M,D] (bf16) = LayerNorm(x[M,D] (bf16)) · gamma + beta, fp32 statistics, eps as given.
+ * HF:modeling_siglip.py:348,357 (layer_norm1/2), :618 (post_layernorm). */
+DFD_API int dfd_layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,
+                               const float* beta, int M, int D, float eps, void* stream);
+/* stats[M,2] = (Σx, Σx²) of bf16 rows (feeds the LN-folded GEMM epilogue when the producer was not a GEMM). */
+DFD_API int dfd_rowstats_bf16(const void* x, int64_t ldx, float* stats, int M, int D, void* stream);
+
+/* Non-causal multi-head attention over packed qkv[B·N, 3·H·hd] (bf16; q | k | v column blocks, head h at
+ * columns h·hd) -> out[B·N, H·hd] (bf16).  softmax(q·kᵀ·scale) in fp32.
+ * HF:modeling_siglip.py:229-249,293-306 (SDPA, is_causal=False). hd in {64,72}. */
+DFD_API int dfd_attention_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N,
+                               int H, int hd, float scale, void* stream);
+
+/* Fused preprocess + im2col: pixels -> bf16 patch matrix A[B·G·G, Kpad] with column order (c, ky, kx)
+ * (= conv weight [D,3,P,P] flattened), value (u8/255 − 0.5)/0.5 (ToTensor + Normalize(.5,.5):
+ * inference_ai_human_images.py:200-204; train_fusion_head_only.py:67-74), optional resize of the
+ * source to S×S first (resize_mode: 0 none (Hin==S), 1 nearest — train_fusion_head_only.py:103-104,
+ * 2 bilinear align_corners=False — cifake_binary_classifier.py:716-717).  Only pixels
+ * [0, G·P) of each axis are read (conv padding='valid': HF:modeling_siglip.py:124-130).
+ * pix_format: 0 = u8 NHWC [B,Hin,Win,3]; 1 = f32 NCHW [B,3,Hin,Win] already normalised. */
+DFD_API int dfd_patchify(const void* pixels, int pix_format, int B, int Hin, int Win, int S, int P,
+                         int resize_mode, void* A, int64_t lda, void* stream);
+
+/* MAP pooling head, single learned query per head (HF:modeling_siglip.py:639-654):
+ * attn[b, h·hd..] = softmax_n(q[h]·k[b,n,h]·scale) · v[b,n,h]  with kv[B·N, 2·H·hd] (k | v), q fp32 [H·hd]
+ * (the projected probe, batch independent).  out bf16 [B, H·hd]. */
+DFD_API int dfd_map_attention_bf16(const void* kv, int64_t ldkv, const float* q, void* out,
+                                   int64_t ldo, int B, int N, int H, int hd, float scale,
+                                   void* stream);
+
+/* Classifier head on pooled embeddings (fp32 weights, fp32 math):
+ *   f = pooled / (‖pooled‖₂ + norm_eps)                       inference_ai_human_images.py:149; +1e-6: train_fusion_head_only.py:106
+ *   kind 1 (H-A): LN → Linear(D,D/2) → GELU(erf) → Linear(D/2,1)            inference_ai_human_images.py:131-138
+ *   kind 2 (H-B): f·sigmoid(W2·relu(W1·f)) → LN → Linear → GELU → Linear → GELU → Linear(·,1)   train_fusion_head_only.py:84-99,107-108
+ *   prototypes (optional [2,D] real,fake): p_proto = softmax([−‖f−p_r‖, −‖f−p_f‖])[1]        inference_ai_human_images.py:288-295
+ * Weights are passed as a flat table of device pointers (see dfd_head_weights). */
+typedef struct dfd_head_weights {
+  int kind;                 /* 0 = none (only normalise / prototypes), 1 = H-A, 2 = H-B */
+  int dim;                  /* D */
+  float norm_eps;           /* added to the L2 norm (0 or 1e-6) */
+  float ln_eps;             /* classifier LayerNorm eps (1e-5) */
+  const float *se_w1, *se_b1, *se_w2, *se_b2;          /* [D/16,D],[D/16],[D,D/16],[D] (kind 2) */
+  const float *ln_g, *ln_b;                             /* [D] */
+  const float *w1, *b1;                                 /* [D/2,D],[D/2] */
+  const float *w2, *b2;                                 /* kind1: [1,D/2],[1]; kind2: [D/4,D/2],[D/4] */
+  const float *w3, *b3;                                 /* kind2: [1,D/4],[1] */
+} dfd_head_weights;
+DFD_API int dfd_head_fwd(const dfd_head_weights* w, const void* pooled_bf16, int64_t ldp, int B,
+                         const float* prototypes, float* feat_out /*[B,D] normalised, or NULL*/,
+                         float* z_sig /*[B] or NULL*/, float* p_proto /*[B] or NULL*/, void* stream);
+
+/* 24-d frequency feature vector per gray 256×256 fp32 image in [0,1]
+ * (train_fusion_head_only.py:150-226 = FreqMLP trainer.py:91-177; app copy deepfake-detector-v2/app.py:752-846):
+ * 2-D FFT magnitude band energies, log-spectrum slope, sector anisotropy, phase entropy, 2-level Haar
+ * energies, 3 SRM stencil moments.  lut = host-precomputed per-pixel LUTs of the 256² grid uploaded with
+ * dfd_freq_set_luts (band id, log-radius bin, sector id), built by the host with the reference's own torch
+ * ops.  eps: 1e-8 (trainers/app v2) or 1e-6 (appv3.py:570).  zscore!=0 applies the app's per-vector
+ * z-scoring (app.py:840-846).  scratch: B·256·129·8 bytes. */
+DFD_API int dfd_freq_features(const float* gray256, int B, const uint8_t* lut_band,
+                              const int8_t* lut_rbin, const int8_t* lut_sector, float eps, int zscore,
+                              void* scratch, float* feats /*[B,24]*/, void* stream);
+DFD_API int64_t dfd_freq_scratch_bytes(int B);
+
+/* Score epilogue: FreqMLP + fusion + temperature + CORAL, one warp per sample.
+ *  gen 1 (shipped siglip/ safetensors files; deepfake-detector-v2/app.py:601-628,691-709,1355-1396):
+ *     z_freq = FreqMLP_G1(feats)  (SafeLayerNorm eps 1e-5 → Linear(24,64) → GELU(erf) → Linear(64,1); eval noise omitted)
+ *     z = fc·[σ(z_sig), σ(z_freq/freq_temp)] + b
+ *  gen 2 (train_fusion_head_only.py:230-317):
+ *     z_freq = FreqMLP_G2(feats) ; z = AdaptiveFusionHead(z_freq, z_sig)
+ *  then z_scaled = z / max(coral_temp,1e-3); p_raw = σ(z_scaled); CORAL probs/argmax/μ/var/entropy/blend.
+ * If feats==NULL, z_freq_in[B] is used directly.  All outputs are SoA fp32 (risk_idx int32), any may be NULL. */
+typedef struct dfd_score_weights {
+  int gen;                      /* 1 or 2 */
+  /* G1 FreqMLP */
+  const float *g1_ln_w, *g1_ln_b, *g1_w1, *g1_b1, *g1_w2, *g1_b2;
+  /* G1 fusion */
+  float g1_fc_w[2], g1_fc_b, freq_temp;
+  /* G2 FreqMLP: normer.mean/std, contrast.alpha/beta, band.gates[4], blocks{0,1}.{norm.w,norm.b,fc1.w,fc1.b,fc2.w,fc2.b}, head.w, head.b, temp.T */
+  const float *g2_mean, *g2_std, *g2_alpha, *g2_beta, *g2_gates;
+  const float *g2_blk[2][6];
+  const float *g2_head_w, *g2_head_b;
+  float g2_temp;
+  /* G2 fusion: mlp.0.{w[32,3],b[32]}, mlp.2.{w[2,32],b[2]}, temp.T */
+  const float *f2_w0, *f2_b0, *f2_w1, *f2_b1;
+  float f2_temp;
+  /* CORAL */
+  float coral_cuts[4];          /* logit-space cutpoints */
+  float coral_temp;
+} dfd_score_weights;
+typedef struct dfd_scores {
+  float *z_freq, *z, *z_scaled, *p_raw, *risk_probs /*[B,5]*/, *p_coral, *entropy, *p_blend;
+  int32_t* risk_idx;
+} dfd_scores;
+DFD_API int dfd_score_epilogue(const dfd_score_weights* w, const float* z_sig, const float* feats,
+                               const float* z_freq_in, int B, const dfd_scores* out, void* stream);
+
+/* AdaptiveFusionHead forward + backward for head-only training (train_fusion_head_only.py:303-317,423-425):
+ * loss = mean BCEWithLogits(head(z_freq,z_sig), y) over the GLOBAL batch (inv_global_batch = 1/B_global);
+ * grads[195] (order mlp.0.weight[32,3], mlp.0.bias[32], mlp.2.weight[2,32], mlp.2.bias[2], temp.T) and
+ * loss_sum[1] are ACCUMULATED (caller zeroes), so ranks allreduce(sum) them afterwards. logits[B] optional. */
+DFD_API int dfd_fusion_fwd_bwd(const float* params195, const float* z_freq, const float* z_sig,
+                               const float* y, int B, float inv_global_batch, float* loss_sum,
+                               float* grads195, float* logits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Engine level (owns packed weights + workspaces; one per (device, model config))
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dfd_engine dfd_engine;
+typedef struct dfd_config {
+  int image_size, patch, hidden, inter, layers, heads; /* tokens = (image_size/patch)^2, hd = hidden/heads */
+  int gelu_tanh;   /* 1 = HF gelu_pytorch_tanh (default) */
+  float ln_eps;    /* 1e-6 */
+  int fuse_ln;     /* 1 = LayerNorm folded into the QKV / fc1 / MAP-kv GEMM epilogues (row stats from the
+                      producing GEMM); 0 = stand-alone LayerNorm kernels */
+} dfd_config;
+
+DFD_API int dfd_engine_create(const dfd_config* cfg, int device, int max_batch, dfd_engine** out);
+DFD_API int dfd_engine_destroy(dfd_engine* e);
+/* Copy + repack one tensor (device or host pointer; dtype 0=f32, 1=bf16) under its canonical HF name,
+ * e.g. "embeddings.patch_embedding.weight", "encoder.layers.3.self_attn.q_proj.bias",
+ * "head.attention.in_proj_weight" (Siglip2sidafrozen.py:753 state dict). */
+DFD_API int dfd_engine_set_tensor(dfd_engine* e, const char* name, const void* data, int dtype,
+                                  int ndim, const int64_t* shape, int on_host);
+/* Call once after all tensors are set: folds LN affine into weights (fuse_ln), projects the probe. */
+DFD_API int dfd_engine_finalize(dfd_engine* e);
+/* pixels -> pooled[B,D] (bf16) (+ optional last_hidden[B·N,D] bf16 = post_layernorm output).
+ * HF SiglipVisionModel.forward (HF:modeling_siglip.py:586-625) == open_clip encode_image
+ * (inference_ai_human_images.py:148). */
+DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int pix_format, int B, int Hin,
+                               int Win, int resize_mode, void* pooled, void* last_hidden,
+                               void* stream);
+DFD_API int64_t dfd_engine_workspace_bytes(const dfd_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFD_H_ */

@@ -1,0 +1,260 @@
+"""Generates tests/golden/*.npz — run in the build container only (needs /root/reference and `transformers`).
+
+    python oracle/make_golden.py
+
+Backbone vectors come from the real `transformers.SiglipVisionModel` (the class the reference instantiates at
+Siglip2sidafrozen.py:753) loaded with oracle.siglip_ref.init_state_dict weights.  Scoring vectors come from the
+reference's OWN function/class bodies, extracted by `ast` from the source text under /root/reference and
+exec'd (the scripts cannot be imported: open_clip / pywt / gradio are not installed, coral.py does not parse)
+with a Haar shim standing in for `pywt.dwt2(x, 'db1')`.  Nothing from /root/reference is copied into the repo;
+only numeric outputs are stored.
+"""
+from __future__ import annotations
+
+import ast
+import io
+import json
+import math
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import scoring_ref as S  # noqa: E402
+from oracle import siglip_ref as R  # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+# ---- reference extraction ---------------------------------------------------------------------------
+def extract(path: str, names, namespace: dict, line_range=None):
+    src = open(path, encoding="utf-8").read()
+    if line_range is not None:  # coral.py has a SyntaxError in its module docstring: parse a slice only
+        lines = src.splitlines()
+        src = "\n".join(lines[line_range[0] - 1 : line_range[1]])
+    tree = ast.parse(src)
+    picked = []
+    for node in tree.body:
+        nm = None
+        if isinstance(node, (ast.FunctionDef, ast.ClassDef)):
+            nm = node.name
+        elif isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Name):
+            nm = node.targets[0].id
+        if nm in names:
+            picked.append(node)
+    found = {getattr(n, "name", None) or n.targets[0].id for n in picked}
+    missing = set(names) - found
+    assert not missing, f"{path}: not found {missing}"
+    mod = ast.Module(body=picked, type_ignores=[])
+    exec(compile(mod, path, "exec"), namespace)
+    return namespace
+
+
+def pywt_shim():
+    m = types.ModuleType("pywt")
+
+    def dwt2(x, wavelet):
+        assert wavelet == "db1"
+        cA, cH, cV, cD = S.haar2(np.asarray(x, dtype=np.float32))
+        return cA, (cH, cV, cD)
+
+    m.dwt2 = dwt2
+    return m
+
+
+def base_namespace():
+    import cv2
+    from PIL import Image, ImageOps
+    from typing import List, Sequence
+
+    return {"torch": torch, "nn": nn, "F": F, "np": np, "math": math, "cv2": cv2, "Image": Image,
+            "ImageOps": ImageOps, "pywt": pywt_shim(), "List": List, "Sequence": Sequence}
+
+
+def test_images():
+    """Four RGB u8 images with natural-ish spectra (gradients + texture + edges + noise), various sizes."""
+    rng = np.random.default_rng(7)
+    out = []
+    for (h, w) in ((224, 224), (200, 300), (64, 64), (384, 384)):
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+        img = np.zeros((h, w, 3))
+        for c in range(3):
+            f1, f2 = rng.uniform(0.01, 0.2, 2)
+            img[..., c] = (0.5 + 0.25 * np.sin(f1 * xx + c) * np.cos(f2 * yy) + 0.15 * ((xx // 16 + yy // 16) % 2)
+                           + 0.1 * rng.standard_normal((h, w)) + 0.2 * (xx / w - 0.5))
+        out.append(np.clip(img * 255.0, 0, 255).astype(np.uint8))
+    return out
+
+
+def make_scoring():
+    from PIL import Image
+
+    tr = extract(f"{REF}/train_fusion_head_only.py",
+                 {"EPS", "SRM_K", "_pil_to_gray256_clahe", "fft_features", "srm_features", "extract_freq_vector",
+                  "FeatureNormalizer", "ContrastScaler", "TemperatureScaler", "BandGating", "ResidualMLPBlock",
+                  "FreqMLP", "AdaptiveFusionHead"}, base_namespace())
+    app = base_namespace()
+    app.update({"DETECT_USE_CLAHE": False, "CORAL_CUTS": json.load(open(f"{REF}/siglip/coral_cutpoints.json"))})
+    extract(f"{REF}/deepfake-detector-v2/app.py",
+            {"EPS", "SRM_K", "_pil_to_gray256", "fft_features", "srm_features", "extract_freq_vector", "SafeLayerNorm",
+             "FreqMLP", "_logit", "CoralCalibrator"}, app)
+    coral_ns = extract(f"{REF}/coral.py", {"fit_coral_cutpoints"}, base_namespace(), line_range=(296, 325))
+
+    g = {}
+    imgs = test_images()
+    grays_clahe, grays_plain = [], []
+    for im in imgs:
+        pil = Image.fromarray(im, "RGB")
+        grays_clahe.append(tr["_pil_to_gray256_clahe"](pil).numpy())
+        grays_plain.append(app["_pil_to_gray256"](pil).numpy())
+    gray = np.stack(grays_clahe + grays_plain)  # [8,256,256] float32, values k/255
+    g["gray_u8"] = np.round(gray * 255.0).astype(np.uint8)
+    assert np.array_equal(g["gray_u8"].astype(np.float32) / 255.0, gray)
+    g["rgb_shapes"] = np.array([im.shape[:2] for im in imgs], dtype=np.int32)
+
+    # features: trainer variant (raw) and app variant (z-scored), computed by the reference bodies on the
+    # stored gray256 (their gray256 producer is swapped for a lookup; it is pinned separately above)
+    raw, zs = [], []
+    for i in range(gray.shape[0]):
+        x = torch.from_numpy(gray[i].copy())
+        tr["_pil_to_gray256_clahe"] = lambda pil, _x=x: _x.clone()
+        app["_pil_to_gray256"] = lambda pil, _x=x: _x.clone()
+        raw.append(tr["extract_freq_vector"](None).numpy())
+        zs.append(app["extract_freq_vector"](None).numpy())
+    g["feats_raw"] = np.stack(raw).astype(np.float32)
+    g["feats_zscore"] = np.stack(zs).astype(np.float32)
+
+    # FreqMLP G1 with the shipped weights (eval-time noise disabled by running in train mode: no dropout/BN)
+    from safetensors.torch import load_file
+
+    g1 = app["FreqMLP"]()
+    g1.load_state_dict(load_file(f"{REF}/siglip/freq_mlp.safetensors"), strict=True)
+    g1.train()
+    with torch.no_grad():
+        g["zfreq_g1"] = g1(torch.from_numpy(g["feats_zscore"])).numpy()
+    # FreqMLP G2 with seeded weights
+    g2 = tr["FreqMLP"]()
+    g2.load_state_dict(S.init_freq_mlp_g2(2), strict=True)
+    g2.eval()
+    with torch.no_grad():
+        g["zfreq_g2"] = g2(torch.from_numpy(g["feats_raw"])).numpy()
+
+    # fusion heads
+    rng = np.random.default_rng(11)
+    zsig = rng.normal(0, 3, 64).astype(np.float32)
+    zfreq = rng.normal(0, 3, 64).astype(np.float32)
+    g["fuse_zsig"], g["fuse_zfreq"] = zsig, zfreq
+    fus1 = load_file(f"{REF}/siglip/fusion_head.safetensors")
+    lin = nn.Linear(2, 1)
+    lin.load_state_dict({"weight": fus1["fc.weight"], "bias": fus1["fc.bias"]})
+    with torch.no_grad():
+        p_sig = torch.sigmoid(torch.from_numpy(zsig))
+        p_freq = torch.sigmoid(torch.from_numpy(zfreq / 1.25))
+        g["fuse_g1_z"] = lin(torch.stack([p_sig, p_freq], 1)).squeeze(1).numpy()
+    fh = tr["AdaptiveFusionHead"]()
+    fh.load_state_dict(S.init_fusion_g2(3), strict=True)
+    with torch.no_grad():
+        g["fuse_g2_z"] = fh(torch.from_numpy(zfreq), torch.from_numpy(zsig)).numpy()
+    # reference training step = reference forward + BCEWithLogits + backward under enable_grad
+    yb = (rng.random(64) > 0.5).astype(np.float32)
+    g["fuse_y"] = yb
+    with torch.enable_grad():
+        fh.train()
+        fh.zero_grad()
+        loss = nn.BCEWithLogitsLoss()(fh(torch.from_numpy(zfreq), torch.from_numpy(zsig)), torch.from_numpy(yb))
+        loss.backward()
+        g["fuse_g2_loss"] = np.float32(loss.item())
+        g["fuse_g2_grads"] = torch.cat([p.grad.reshape(-1) for p in fh.parameters()]).numpy()
+        assert [n for n, _ in fh.named_parameters()] == ["mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias", "temp.T"]
+
+    # CORAL: the reference calibrator on a sweep of z_scaled
+    cal = app["CoralCalibrator"]()
+    g["coral_cut_logits"] = cal.c.numpy()
+    zsw = np.linspace(-8, 10, 721).astype(np.float32)
+    idx, probs = [], []
+    for z in zsw:
+        i, p = cal.predict(torch.tensor(float(z)))
+        idx.append(i)
+        probs.append(p.numpy())
+    g["coral_z"], g["coral_idx"], g["coral_probs"] = zsw, np.array(idx, np.int32), np.stack(probs)
+    # script-style fitting on a seeded logit vector
+    lg = torch.from_numpy(rng.normal(0, 2, 1001).astype(np.float32))
+    g["fit_logits"] = lg.numpy()
+    g["fit_cuts_script"] = np.array(coral_ns["fit_coral_cutpoints"](lg, torch.zeros(1001)), dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "scoring_golden.npz"), **g)
+    print("scoring_golden.npz:", {k: v.shape for k, v in g.items()})
+
+
+def make_heads():
+    """Classifier heads as the reference defines them (inference_ai_human_images.py:131-138;
+    train_fusion_head_only.py:84-99), fed seeded pooled embeddings."""
+    g = {}
+    for D in (128, 1152):
+        pooled = torch.randn(6, D, generator=torch.Generator().manual_seed(5)) * 2.0
+        g[f"pooled_{D}"] = pooled.numpy()
+        a = nn.Sequential(nn.LayerNorm(D), nn.Dropout(0.3), nn.Linear(D, D // 2), nn.GELU(), nn.Dropout(0.2),
+                          nn.Linear(D // 2, 1)).eval()
+        sd = R.init_head("A", D, 1)
+        a.load_state_dict({k.replace("classifier.", ""): v for k, v in sd.items()})
+        se = nn.Sequential(nn.Linear(D, D // 16), nn.ReLU(), nn.Linear(D // 16, D), nn.Sigmoid()).eval()
+        b = nn.Sequential(nn.LayerNorm(D), nn.Dropout(0.3), nn.Linear(D, D // 2), nn.GELU(), nn.Dropout(0.2),
+                          nn.Linear(D // 2, D // 4), nn.GELU(), nn.Linear(D // 4, 1)).eval()
+        sdb = R.init_head("B", D, 1)
+        se.load_state_dict({k.replace("se.", ""): v for k, v in sdb.items() if k.startswith("se.")})
+        b.load_state_dict({k.replace("classifier.", ""): v for k, v in sdb.items() if k.startswith("classifier.")})
+        with torch.no_grad():
+            f = pooled / pooled.norm(dim=-1, keepdim=True)
+            g[f"zA_{D}"] = a(f).squeeze(-1).numpy()
+            f2 = pooled / (pooled.norm(dim=-1, keepdim=True) + 1e-6)
+            g[f"zB_{D}"] = b(f2 * se(f2)).squeeze(-1).numpy()
+            protos = torch.randn(2, D, generator=torch.Generator().manual_seed(6))
+            protos = protos / protos.norm(dim=-1, keepdim=True)
+            g[f"protos_{D}"] = protos.numpy()
+            dr, df = torch.cdist(f, protos[0:1]), torch.cdist(f, protos[1:2])
+            g[f"pproto_{D}"] = torch.softmax(torch.cat([-dr, -df], 1), 1)[:, 1].numpy()
+    np.savez_compressed(os.path.join(OUT, "heads_golden.npz"), **g)
+    print("heads_golden.npz:", {k: v.shape for k, v in g.items()})
+
+
+def make_backbone():
+    from transformers import SiglipVisionConfig, SiglipVisionModel
+
+    g = {}
+    cases = [("tiny-hd64", 3), ("tiny-hd72", 2), ("small-hd72", 2), ("siglip2-base-patch16-224", 2),
+             ("siglip2-so400m-patch14-384", 1)]
+    for name, B in cases:
+        c = R.CONFIGS[name]
+        sd = R.init_state_dict(c, 0)
+        hc = SiglipVisionConfig(hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
+                                num_hidden_layers=c.num_hidden_layers, num_attention_heads=c.num_attention_heads,
+                                image_size=c.image_size, patch_size=c.patch_size)
+        m = SiglipVisionModel(hc).eval()
+        m.load_state_dict({"vision_model." + k: v for k, v in sd.items()}, strict=True)
+        x = R.preprocess_u8(R.synthetic_images(B, c.image_size, 0))
+        with torch.no_grad():
+            o = m(pixel_values=x, output_hidden_states=True)
+        g[name + "/pooled"] = o.pooler_output.numpy()
+        g[name + "/last_hidden_sub"] = o.last_hidden_state[:, ::7, ::5].numpy()
+        g[name + "/hidden1_sub"] = o.hidden_states[1][:, ::7, ::5].numpy()
+        g[name + "/weight_checksum"] = np.float64(sum(float(v.double().sum()) for v in sd.values()))
+        print(name, "pooled", o.pooler_output.shape, "|pooled|max", float(o.pooler_output.abs().max()))
+    np.savez_compressed(os.path.join(OUT, "backbone_golden.npz"), **g)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    which = sys.argv[1:] or ["scoring", "heads", "backbone"]
+    if "scoring" in which:
+        make_scoring()
+    if "heads" in which:
+        make_heads()
+    if "backbone" in which:
+        make_backbone()

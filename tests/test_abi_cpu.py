@@ -1,0 +1,166 @@
+"""CPU tests (no GPU): the C-ABI library builds, loads and exports every symbol include/dfd.h declares, the
+ctypes structs mirror the C structs, argument validation works without a device, and compute entry points
+FAIL LOUDLY (no CPU fallback) when there is no GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from dfd import _lib
+
+    if not _lib.LIB_PATH.exists():
+        import __graft_entry__ as g
+
+        g.build()
+    return _lib.load()
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "dfd.h")).read()
+    return sorted(set(re.findall(r"DFD_API\s+[\w\s\*]+?\b(dfd_\w+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(lib):
+    from dfd import _lib
+
+    names = _declared_symbols()
+    assert len(names) >= 20
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (dfd_\w+)", out))
+    for n in names:
+        assert n in exported, f"{n} declared in include/dfd.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert exported - set(_lib.SIGNATURES) == set(), "exported symbol without a binding"
+
+
+def test_struct_layouts_match_c(tmp_path):
+    """sizeof() of every struct crossing the ABI, as the C compiler sees it, equals the ctypes mirror."""
+    from dfd import _lib
+
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "dfd.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+                   "sizeof(dfd_gemm_epilogue),sizeof(dfd_head_weights),sizeof(dfd_score_weights),sizeof(dfd_scores),"
+                   "sizeof(dfd_config));return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    assert sizes == [C.sizeof(_lib.GemmEpilogue), C.sizeof(_lib.HeadWeights), C.sizeof(_lib.ScoreWeights),
+                     C.sizeof(_lib.Scores), C.sizeof(_lib.EngineConfig)]
+
+
+def test_version_and_error_text(lib):
+    assert lib.dfd_version() >= 100
+    assert lib.dfd_launch_count() >= 0
+    rc = lib.dfd_gemm_bf16(None, 0, None, 0, None, 0, 1, 1, 1, None, None)
+    assert rc == -1 and b"null" in lib.dfd_last_error()
+    assert lib.dfd_freq_scratch_bytes(3) == 3 * (256 * 129 * 8 + 256)
+    assert lib.dfd_freq_scratch_bytes(0) == 0
+    assert lib.dfd_engine_destroy(None) == 0 and lib.dfd_engine_workspace_bytes(None) == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device behaviour")
+def test_no_cpu_fallback_without_device(lib):
+    from dfd import _lib, engine
+
+    cfg = _lib.EngineConfig(64, 16, 128, 256, 2, 2, 1, 1e-6, 0)
+    h = C.c_void_p()
+    rc = lib.dfd_engine_create(C.byref(cfg), 0, 4, C.byref(h))
+    assert rc in (-4, -5) and not h.value, lib.dfd_last_error()
+    with pytest.raises(RuntimeError):
+        engine.SiglipEngine(engine.ARCHS["tiny-hd64"], 0, 4)
+    # a GEMM with plausible (host) pointers must not compute anything on the CPU: it reports the missing driver
+    buf = (C.c_uint16 * (128 * 64))()
+    rc = lib.dfd_gemm_bf16(C.addressof(buf), 64, C.addressof(buf), 64, C.addressof(buf), 64, 128, 64, 64, None, None)
+    assert rc in (-4, -5), lib.dfd_last_error()
+
+
+def test_engine_config_validation(lib):
+    from dfd import _lib
+
+    h = C.c_void_p()
+    bad = _lib.EngineConfig(64, 16, 130, 256, 2, 2, 1, 1e-6, 0)  # head dim 65
+    assert lib.dfd_engine_create(C.byref(bad), 0, 4, C.byref(h)) == -3
+    bad = _lib.EngineConfig(64, 16, 128, 256, 2, 3, 1, 1e-6, 0)  # hidden % heads
+    assert lib.dfd_engine_create(C.byref(bad), 0, 4, C.byref(h)) == -2
+    assert lib.dfd_engine_create(None, 0, 4, C.byref(h)) == -1
+
+
+def test_state_dict_canonicalisation_hf_and_timm():
+    """HF split q/k/v and timm fused qkv / attn_pool layouts land on the same canonical names."""
+    from dfd import engine
+    from oracle import siglip_ref as R
+
+    c = R.CONFIGS["tiny-hd64"]
+    sd = R.init_state_dict(c, 0)
+    hf = {"vision_model." + k: v for k, v in sd.items()}
+    canon = engine.canonicalize_state_dict(hf)
+    assert set(canon) == set(sd)
+    D = c.hidden_size
+    timm = {"backbone.visual.trunk.patch_embed.proj.weight": sd["embeddings.patch_embedding.weight"],
+            "backbone.visual.trunk.patch_embed.proj.bias": sd["embeddings.patch_embedding.bias"],
+            "backbone.visual.trunk.pos_embed": sd["embeddings.position_embedding.weight"][None],
+            "backbone.visual.trunk.norm.weight": sd["post_layernorm.weight"],
+            "backbone.visual.trunk.norm.bias": sd["post_layernorm.bias"],
+            "backbone.visual.trunk.attn_pool.latent": sd["head.probe"],
+            "backbone.visual.trunk.attn_pool.q.weight": sd["head.attention.in_proj_weight"][:D],
+            "backbone.visual.trunk.attn_pool.q.bias": sd["head.attention.in_proj_bias"][:D],
+            "backbone.visual.trunk.attn_pool.kv.weight": sd["head.attention.in_proj_weight"][D:],
+            "backbone.visual.trunk.attn_pool.kv.bias": sd["head.attention.in_proj_bias"][D:],
+            "backbone.visual.trunk.attn_pool.proj.weight": sd["head.attention.out_proj.weight"],
+            "backbone.visual.trunk.attn_pool.proj.bias": sd["head.attention.out_proj.bias"],
+            "backbone.visual.trunk.attn_pool.norm.weight": sd["head.layernorm.weight"],
+            "backbone.visual.trunk.attn_pool.norm.bias": sd["head.layernorm.bias"],
+            "backbone.text.transformer.whatever": torch.zeros(3), "backbone.logit_scale": torch.zeros(())}
+    for nm in ("fc1", "fc2"):
+        for wb in ("weight", "bias"):
+            timm[f"backbone.visual.trunk.attn_pool.mlp.{nm}.{wb}"] = sd[f"head.mlp.{nm}.{wb}"]
+    for i in range(c.num_hidden_layers):
+        p, t = f"encoder.layers.{i}.", f"backbone.visual.trunk.blocks.{i}."
+        for wb in ("weight", "bias"):
+            timm[t + "attn.qkv." + wb] = torch.cat([sd[p + f"self_attn.{n}_proj.{wb}"] for n in "qkv"], 0)
+            timm[t + "attn.proj." + wb] = sd[p + "self_attn.out_proj." + wb]
+            for a, b in (("norm1", "layer_norm1"), ("norm2", "layer_norm2"), ("mlp.fc1", "mlp.fc1"), ("mlp.fc2", "mlp.fc2")):
+                timm[t + a + "." + wb] = sd[p + b + "." + wb]
+    ct = engine.canonicalize_state_dict(timm)
+    assert "head.attention.in_proj_weight" in ct and torch.equal(ct["head.attention.in_proj_weight"], sd["head.attention.in_proj_weight"])
+    assert torch.equal(ct["encoder.layers.1.self_attn.qkv.weight"][D:2 * D], sd["encoder.layers.1.self_attn.k_proj.weight"])
+    assert not any("text" in k or "logit_scale" in k for k in ct)
+    a = engine.arch_from_state_dict(hf)
+    assert (a.image_size, a.patch_size, a.hidden_size, a.intermediate_size, a.num_hidden_layers, a.num_attention_heads) == (64, 16, 128, 256, 2, 2)
+    assert abs(engine.ARCHS["google/siglip2-so400m-patch14-384"].flops_per_image() / 1e9 - 670.346) < 1e-3
+
+
+def test_freq_luts_equal_oracle_tables():
+    import numpy as np
+
+    from dfd import scoring
+    from oracle import scoring_ref as S
+
+    band, rbin, sector = scoring.build_freq_luts("cpu")
+    b, r, s = S.grid_tables()
+    assert np.array_equal(band.numpy(), b) and np.array_equal(rbin.numpy(), r) and np.array_equal(sector.numpy(), s)
+
+
+def test_coral_loader_formats(tmp_path, shipped):
+    import json
+
+    from dfd import scoring
+
+    c, t = scoring.load_coral(os.path.join(shipped["dir"], "coral_cutpoints.json"), os.path.join(shipped["dir"], "coral_temp.json"))
+    assert abs(c[0] + 1.14372) < 1e-5 and abs(t - 0.9956228137016296) < 1e-12
+    (tmp_path / "c.json").write_text(json.dumps([-2.0, -0.5, 0.5, 1.5]))
+    (tmp_path / "t.json").write_text("1.7")
+    c, t = scoring.load_coral(str(tmp_path / "c.json"), str(tmp_path / "t.json"))
+    assert c == [-2.0, -0.5, 0.5, 1.5] and t == 1.7
+    (tmp_path / "t2.json").write_text(json.dumps({"temp": 0.8}))
+    assert scoring.load_coral(None, str(tmp_path / "t2.json"))[1] == 0.8
+    assert abs(scoring.load_coral(None, None)[0][0] - scoring._logit(0.32)) < 1e-12
+    assert scoring.fit_coral_cutpoints_shipped(shipped["bins"]) == {k: float(shipped["cuts"][k]) for k in ("q25", "q50", "q75", "max")}

@@ -1,0 +1,440 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes -> libdfd.so).
+
+Floating-point kernels are compared against a plain fp32 torch restatement of the same op on the same
+(bf16-rounded) inputs; tolerances are written next to each check.  Scoring kernels are compared against
+oracle/scoring_ref.py and the reference-generated golden vectors (tests/golden/).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+def _gelu_tanh(x):
+    return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * x ** 3)))
+
+
+# ---------------------------------------------------------------------------------------------------
+# GEMM
+# ---------------------------------------------------------------------------------------------------
+GEMM_SHAPES = [
+    # M, N, K                 what it is
+    (256, 256, 128),          # smallest whole tiles
+    (128, 128, 64),           # one tile, one k-block
+    (1000, 768, 768),         # ragged M
+    (392, 2304, 768),         # base qkv slice
+    (300, 4304, 1152),        # so400m fc1: N not a multiple of any tile
+    (300, 1152, 4304),        # so400m fc2: K not a multiple of 64 (TMA zero fill along K)
+    (7, 1152, 640),           # tiny M (MAP head GEMMs, batch 7), padded patch K
+    (1, 768, 768),            # single row
+    (3000, 3456, 1152),       # so400m qkv, many tiles per CTA -> pipeline wrap-around and both accumulators
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("tile_n", [0, 128, 192, 256])
+def test_gemm_plain(M, N, K, tile_n):
+    from dfd import ops
+
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = _bf(torch.randn(M, K, generator=g)).to(DEV)
+    w = _bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    out = ops.gemm_bf16(a, w, tile_n=tile_n)
+    ref = a.float() @ w.float().t()
+    torch.cuda.synchronize()
+    # bf16 output rounding: 2^-9 relative; fp32 accumulation over K: negligible
+    err = (out.float() - ref).abs()
+    tol = 2.0 ** -8 * ref.abs() + 1e-3
+    assert bool((err <= tol).all()), f"max err {err.max().item()} at {err.argmax().item()}"
+
+
+@pytest.mark.parametrize("M,N,K", [(520, 768, 768), (300, 4304, 1152), (1458, 1152, 640)])
+def test_gemm_epilogues(M, N, K):
+    from dfd import ops
+
+    g = torch.Generator(device="cpu").manual_seed(5)
+    a = _bf(torch.randn(M, K, generator=g)).to(DEV)
+    w = _bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = _bf(torch.randn(M, N, generator=g)).to(DEV)
+    pos_rows = 729 if M % 729 == 0 else 13
+    pos = torch.randn(pos_rows, N, generator=g).to(DEV)
+    acc = a.float() @ w.float().t()
+
+    def close(out, ref, what):
+        err = (out.float() - ref).abs()
+        tol = 2.0 ** -8 * ref.abs() + 2e-3
+        assert bool((err <= tol).all()), f"{what}: max err {err.max().item()}"
+
+    close(ops.gemm_bf16(a, w, bias=bias), acc + bias, "bias")
+    close(ops.gemm_bf16(a, w, bias=bias, act=1), _gelu_tanh(acc + bias), "bias+gelu_tanh")
+    close(ops.gemm_bf16(a, w, bias=bias, residual=res), acc + bias + res.float(), "bias+residual")
+    rows = torch.arange(M, device=DEV) % pos_rows
+    close(ops.gemm_bf16(a, w, bias=bias, pos=pos), acc + bias + pos[rows], "bias+pos")
+    # in-place residual (C aliases residual), as the engine uses it
+    x = res.clone()
+    ops.gemm_bf16(a, w, bias=bias, residual=x, out=x)
+    close(x, acc + bias + res.float(), "in-place residual")
+    # row statistics of the bf16 output
+    st = torch.zeros(M, 2, device=DEV)
+    o = ops.gemm_bf16(a, w, bias=bias, stats_out=st)
+    torch.cuda.synchronize()
+    of = o.float()
+    assert torch.allclose(st[:, 0], of.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[:, 1], (of * of).sum(1), rtol=1e-4, atol=1e-2)
+
+
+def test_gemm_ln_fold():
+    """LayerNorm folded through the GEMM: LN(x)·(γ⊙W)ᵀ = rstd·(x·W'ᵀ − mean·colsum(W'))."""
+    from dfd import ops
+
+    M, D, N = 777, 1152, 384
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = _bf(torch.randn(M, D, generator=g) * 2.0 + 0.3).to(DEV)
+    gamma = (1.0 + 0.1 * torch.randn(D, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(D, generator=g)).to(DEV)
+    w = (torch.randn(N, D, generator=g) / math.sqrt(D)).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    wf = _bf(w * gamma[None])
+    colsum = wf.float().sum(1)
+    bias2 = b + w @ beta
+    st = ops.rowstats_bf16(x)
+    out = ops.gemm_bf16(x, wf, bias=bias2, ln_rowstats=st, ln_colsum=colsum, ln_dim=D, ln_eps=1e-6)
+    ref = torch.nn.functional.layer_norm(x.float(), (D,), gamma, beta, 1e-6) @ w.t() + b
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 0.06, err  # two bf16 roundings (W' and the output) on O(1) values
+
+
+def test_gemm_bad_args():
+    from dfd import _lib, ops
+
+    a = torch.zeros(8, 12, dtype=torch.bfloat16, device=DEV)  # K % 8 != 0
+    w = torch.zeros(8, 12, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(_lib.DfdError) as e:
+        ops.gemm_bf16(a, w)
+    assert e.value.code == -2
+
+
+# ---------------------------------------------------------------------------------------------------
+# LayerNorm / rowstats / patchify
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,D", [(1, 128), (37, 768), (1000, 1152), (513, 144), (64, 2048)])
+def test_layernorm(M, D):
+    from dfd import ops
+
+    g = torch.Generator(device="cpu").manual_seed(D)
+    x = _bf(torch.randn(M, D, generator=g) * 3 + 1).to(DEV)
+    gamma = (1 + 0.2 * torch.randn(D, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(D, generator=g)).to(DEV)
+    y = ops.layernorm_bf16(x, gamma, beta, 1e-6)
+    ref = torch.nn.functional.layer_norm(x.float(), (D,), gamma, beta, 1e-6)
+    torch.cuda.synchronize()
+    err = (y.float() - ref).abs()
+    assert bool((err <= 2.0 ** -8 * ref.abs() + 1e-5).all()), err.max().item()
+    st = ops.rowstats_bf16(x)
+    assert torch.allclose(st[:, 0], x.float().sum(1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(st[:, 1], (x.float() ** 2).sum(1), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("S,P", [(224, 16), (384, 14), (60, 14)])
+def test_patchify_u8(S, P):
+    from dfd import ops
+    from oracle import siglip_ref as R
+
+    img = R.synthetic_images(3, S, seed=1)
+    A = ops.patchify(img.to(DEV), S, P)
+    x = R.preprocess_u8(img)
+    G = S // P
+    ref = x[:, :, : G * P, : G * P].reshape(3, 3, G, P, G, P).permute(0, 2, 4, 1, 3, 5).reshape(3 * G * G, 3 * P * P)
+    torch.cuda.synchronize()
+    K = 3 * P * P
+    assert A.shape[1] % 64 == 0 and A.shape[1] >= K
+    assert torch.equal(A[:, :K].cpu(), ref.to(torch.bfloat16)), "normalised patches must be bit-exact in bf16"
+    assert float(A[:, K:].abs().max()) == 0.0 if A.shape[1] > K else True
+
+
+@pytest.mark.parametrize("mode,name", [(1, "nearest"), (2, "bilinear")])
+@pytest.mark.parametrize("Hin,S,P", [(32, 224, 16), (100, 60, 14), (300, 224, 16)])
+def test_patchify_resize(mode, name, Hin, S, P):
+    from dfd import ops
+    from oracle import siglip_ref as R
+
+    img = R.synthetic_images(2, Hin, seed=2)
+    x = R.preprocess_u8(img)
+    ref_img = R.resize_input(x, S, name)
+    G = S // P
+    ref = ref_img[:, :, : G * P, : G * P].reshape(2, 3, G, P, G, P).permute(0, 2, 4, 1, 3, 5).reshape(2 * G * G, -1)
+    K = 3 * P * P
+    for src in (img.to(DEV), x.to(DEV)):  # u8 NHWC and f32 NCHW inputs
+        A = ops.patchify(src, S, P, resize_mode=mode)
+        torch.cuda.synchronize()
+        err = (A[:, :K].float().cpu() - ref).abs().max().item()
+        assert err <= 2.0 ** -8 * 1.0 + 1e-6, err  # values in [-1,1], bf16 output
+
+
+# ---------------------------------------------------------------------------------------------------
+# attention
+# ---------------------------------------------------------------------------------------------------
+def _ref_attention(qkv, B, N, H, hd):
+    D = H * hd
+    q, k, v = (qkv.float()[:, i * D:(i + 1) * D].reshape(B, N, H, hd).transpose(1, 2) for i in range(3))
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * N, D)
+
+
+@pytest.mark.parametrize("B,N,H,hd", [(2, 196, 12, 64), (1, 729, 16, 72), (3, 16, 2, 64), (2, 16, 2, 72),
+                                      (2, 225, 4, 72), (1, 1024, 2, 72), (2, 64, 1, 64), (1, 129, 3, 64), (1, 1, 2, 72)])
+def test_attention(B, N, H, hd):
+    from dfd import ops
+
+    g = torch.Generator(device="cpu").manual_seed(N + hd)
+    qkv = _bf(torch.randn(B * N, 3 * H * hd, generator=g) * 1.5).to(DEV)
+    out = ops.attention_bf16(qkv, B, N, H, hd)
+    ref = _ref_attention(qkv, B, N, H, hd)
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    # P is rounded to bf16 before PV (as in flash attention) and the output is bf16: ~2^-8 of |v| ~ 1.5·4
+    assert err < 0.04, err
+    assert torch.isfinite(out.float()).all()
+
+
+@pytest.mark.parametrize("B,N,H,hd", [(3, 196, 12, 64), (2, 729, 16, 72), (5, 16, 2, 72), (1, 1024, 16, 72)])
+def test_map_attention(B, N, H, hd):
+    from dfd import ops
+
+    D = H * hd
+    g = torch.Generator(device="cpu").manual_seed(N)
+    kv = _bf(torch.randn(B * N, 2 * D, generator=g)).to(DEV)
+    q = torch.randn(D, generator=g).to(DEV)
+    out = ops.map_attention_bf16(kv, q, B, N, H, hd)
+    k = kv.float()[:, :D].reshape(B, N, H, hd)
+    v = kv.float()[:, D:].reshape(B, N, H, hd)
+    s = torch.einsum("bnhd,hd->bhn", k, q.reshape(H, hd)) / math.sqrt(hd)
+    ref = torch.einsum("bhn,bnhd->bhd", torch.softmax(s, -1), v).reshape(B, D)
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 0.02, err
+
+
+# ---------------------------------------------------------------------------------------------------
+# classifier heads (golden vectors come from torch modules built exactly as the reference defines them)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D", [128, 1152])
+def test_heads(D, golden_heads):
+    from dfd import ops
+    from oracle import siglip_ref as R
+
+    pooled = torch.from_numpy(golden_heads[f"pooled_{D}"])
+    pb = pooled.to(torch.bfloat16).to(DEV)
+    pr = pb.float().cpu()  # what the kernel actually sees
+    protos = torch.from_numpy(golden_heads[f"protos_{D}"]).to(DEV)
+    for kind, eps in (("A", 0.0), ("B", 1e-6)):
+        sd = R.init_head(kind, D, 1)
+        t = {"ln_g": sd["classifier.0.weight"], "ln_b": sd["classifier.0.bias"], "w1": sd["classifier.2.weight"],
+             "b1": sd["classifier.2.bias"], "w2": sd["classifier.5.weight"], "b2": sd["classifier.5.bias"]}
+        if kind == "B":
+            t.update({"se_w1": sd["se.0.weight"], "se_b1": sd["se.0.bias"], "se_w2": sd["se.2.weight"],
+                      "se_b2": sd["se.2.bias"], "w3": sd["classifier.7.weight"], "b3": sd["classifier.7.bias"]})
+        head = ops.HeadParams(1 if kind == "A" else 2, D, eps, t, DEV)
+        feats, z, pp = ops.head_fwd(head, pb, prototypes=protos, want_features=True)
+        torch.cuda.synchronize()
+        z_ref = R.classifier_head(sd, kind, pr, eps)
+        assert torch.allclose(z.cpu(), z_ref, atol=2e-5, rtol=1e-5), (z.cpu() - z_ref).abs().max()
+        # golden from the fp32 pooled: differs only by the bf16 rounding of the input (logit gate 1e-2)
+        assert np.abs(z.cpu().numpy() - golden_heads[f"z{kind}_{D}"]).max() < 1e-2
+        f_ref = R.l2_normalize(pr, eps)
+        assert torch.allclose(feats.cpu(), f_ref, atol=1e-6)
+        if kind == "A":
+            p_ref = R.prototype_prob(f_ref, protos[0].cpu(), protos[1].cpu())
+            assert torch.allclose(pp.cpu(), p_ref, atol=1e-5)
+            assert np.abs(pp.cpu().numpy() - golden_heads[f"pproto_{D}"]).max() < 2e-3
+    # kind 0: normalise only
+    head0 = ops.HeadParams(0, D, 0.0, {}, DEV)
+    feats, z, pp = ops.head_fwd(head0, pb, want_features=True)
+    assert z is None and pp is None and torch.allclose(feats.cpu(), R.l2_normalize(pr, 0.0), atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------
+# frequency features
+# ---------------------------------------------------------------------------------------------------
+def _feat_close(v, ref, gray):
+    from oracle import scoring_ref as S
+
+    scale = np.maximum(np.abs(ref.astype(np.float64)), np.maximum(S.feature_scales(gray), 1e-12))
+    return np.abs(v.astype(np.float64) - ref) / scale
+
+
+def test_freq_features_golden(golden_scoring):
+    """FreqMLP features within 1e-4 relative (BASELINE.json) of the reference's own extract_freq_vector."""
+    from dfd import ops, scoring
+
+    gray = golden_scoring["gray_u8"].astype(np.float32) / 255.0
+    luts = scoring.build_freq_luts(DEV)
+    x = torch.from_numpy(gray).to(DEV)
+    raw = ops.freq_features(x, luts, eps=1e-8, zscore=False).cpu().numpy()
+    zs = ops.freq_features(x, luts, eps=1e-8, zscore=True).cpu().numpy()
+    for i in range(gray.shape[0]):
+        rel = _feat_close(raw[i], golden_scoring["feats_raw"][i], gray[i])
+        assert rel.max() < 1e-4, (i, int(rel.argmax()), rel.max(), raw[i], golden_scoring["feats_raw"][i])
+        assert np.abs(zs[i] - golden_scoring["feats_zscore"][i]).max() < 1e-4
+
+
+def test_freq_features_oracle_edge_cases():
+    """Constant, impulse, single-frequency and random images against oracle/scoring_ref.py."""
+    from dfd import ops, scoring
+    from oracle import scoring_ref as S
+
+    rng = np.random.default_rng(3)
+    yy, xx = np.mgrid[0:256, 0:256]
+    imgs = [np.zeros((256, 256), np.float32), np.full((256, 256), 0.5, np.float32),
+            (rng.integers(0, 256, (256, 256)) / 255.0).astype(np.float32),
+            (0.5 + 0.5 * np.cos(2 * np.pi * (8 * xx + 3 * yy) / 256)).astype(np.float32)]
+    imp = np.zeros((256, 256), np.float32)
+    imp[17, 200] = 1.0
+    imgs.append(imp)
+    x = torch.from_numpy(np.stack(imgs)).to(DEV)
+    out = ops.freq_features(x, scoring.build_freq_luts(DEV)).cpu().numpy()
+    assert np.isfinite(out).all()
+    for i, im in enumerate(imgs):
+        ref = S.extract_freq_vector(im)
+        if i in (2,):  # generic image: the full gate
+            assert _feat_close(out[i], ref, im).max() < 1e-4
+        else:
+            # degenerate spectra (exact zeros / a single line): phase of numerically-zero bins is arbitrary in any
+            # FFT, so entropy (6), slope (4) and kurtosis of ~0 variance are excluded; the energy features must agree
+            # (absolute floor 2e-5: an fp32 FFT's noise floor is ~1e-5 of the total spectral energy)
+            for j in (0, 1, 2, 7, 8, 9, 10, 11, 12, 13, 14, 16, 19, 22):
+                assert abs(out[i][j] - ref[j]) <= 1e-4 * abs(ref[j]) + 2e-5, (i, j, out[i][j], ref[j])
+
+
+def test_freq_features_batch_consistency():
+    """Large batch == per-image results (no cross-image leakage through scratch), bitwise for the energy
+    features whose accumulation order is fixed."""
+    from dfd import ops, scoring
+
+    rng = np.random.default_rng(5)
+    g = torch.from_numpy((rng.integers(0, 256, (67, 256, 256)) / 255.0).astype(np.float32)).to(DEV)
+    luts = scoring.build_freq_luts(DEV)
+    full = ops.freq_features(g, luts)
+    for i in (0, 13, 66):
+        one = ops.freq_features(g[i:i + 1].contiguous(), luts)
+        assert torch.allclose(full[i], one[0], rtol=2e-5, atol=1e-7)
+        assert torch.equal(full[i, 7:15], one[0, 7:15])
+
+
+# ---------------------------------------------------------------------------------------------------
+# score epilogue
+# ---------------------------------------------------------------------------------------------------
+def test_score_epilogue_g1_shipped(golden_scoring, shipped):
+    """The shipped siglip/ artefacts end to end: FreqMLP G1 -> Linear(2,1) on probabilities -> temp -> CORAL."""
+    from dfd import scoring
+    from oracle import scoring_ref as S
+
+    st = scoring.ScoringStack.from_dir(shipped["dir"], DEV)
+    assert st.gen == 1
+    feats = torch.from_numpy(golden_scoring["feats_zscore"]).to(DEV)
+    z_sig = torch.linspace(-3, 3, feats.shape[0]).to(DEV)
+    out = st(z_sig, feats=feats)
+    torch.cuda.synchronize()
+    zf = out["z_freq"].cpu().numpy()
+    assert np.abs(zf - golden_scoring["zfreq_g1"]).max() < 2e-5
+    z_ref = S.fusion_g1(shipped["fusion"], z_sig.cpu().numpy(), golden_scoring["zfreq_g1"])
+    assert np.abs(out["z"].cpu().numpy() - z_ref).max() < 1e-5
+    cl = S.coral_cut_logits(shipped["cuts"])
+    d = S.detect_scores(z_ref, cl, shipped["temp"]["temperature"])
+    for k in ("z_scaled", "p_raw", "p_coral", "entropy", "p_blend"):
+        assert np.abs(out[k].cpu().numpy() - d[k]).max() < 1e-5, k
+    assert np.abs(out["risk_probs"].cpu().numpy() - d["risk_probs"]).max() < 1e-6
+    assert np.array_equal(out["risk_idx"].cpu().numpy(), d["risk_idx"])
+    # survey known answers: z_sig in {-3,0,3} with z_freq=-6.5968 -> risk_idx 3
+    zs3 = torch.tensor([-3.0, 0.0, 3.0], device=DEV)
+    o3 = st(zs3, z_freq=torch.full((3,), -6.5968, device=DEV))
+    assert np.allclose(o3["z_scaled"].cpu().numpy(), [0.21511, 0.54866, 0.88220], atol=2e-5)
+    assert o3["risk_idx"].cpu().tolist() == [3, 3, 3]
+
+
+def test_score_epilogue_g2(golden_scoring):
+    from dfd import scoring
+    from oracle import scoring_ref as S
+
+    fs, hs = S.init_freq_mlp_g2(2), S.init_fusion_g2(3)
+    cuts = [-1.0, -0.2, 0.3, 1.5]
+    st = scoring.ScoringStack(DEV, fs, hs, cuts, 1.0)
+    assert st.gen == 2
+    feats = torch.from_numpy(golden_scoring["feats_raw"]).to(DEV)
+    out = st(torch.zeros(feats.shape[0], device=DEV), feats=feats)
+    assert np.abs(out["z_freq"].cpu().numpy() - golden_scoring["zfreq_g2"]).max() < 2e-5
+    zs = torch.from_numpy(golden_scoring["fuse_zsig"]).to(DEV)
+    zf = torch.from_numpy(golden_scoring["fuse_zfreq"]).to(DEV)
+    out = st(zs, z_freq=zf)
+    z = out["z"].cpu().numpy()
+    assert np.abs(z - golden_scoring["fuse_g2_z"]).max() < 2e-5
+    d = S.detect_scores(golden_scoring["fuse_g2_z"], np.array(cuts, np.float32), 1.0)
+    tp = S.coral_transition_points(np.array(cuts, np.float32))
+    near = np.abs(d["z_scaled"][:, None] - tp[None]).min(1) < 1e-2
+    idx = out["risk_idx"].cpu().numpy()
+    assert np.array_equal(idx[~near], d["risk_idx"][~near])
+    assert len(set(idx.tolist())) >= 3  # these cuts reach several bins
+
+
+def test_coral_sweep_against_reference(golden_scoring, shipped):
+    """CORAL bin = argmax of sigmoid differences, identical to the reference's CoralCalibrator.predict on a
+    z sweep, except within 1e-2 of an argmax transition point."""
+    from dfd import scoring
+    from oracle import scoring_ref as S
+
+    cal = scoring.CoralCalibrator(shipped["cuts"], device=DEV)
+    assert np.allclose(cal.c.numpy(), golden_scoring["coral_cut_logits"], atol=1e-6)
+    z = torch.from_numpy(golden_scoring["coral_z"]).to(DEV)
+    idx, probs = cal.predict(z)
+    idx, probs = idx.cpu().numpy(), probs.cpu().numpy()
+    tp = S.coral_transition_points(golden_scoring["coral_cut_logits"])
+    near = np.abs(golden_scoring["coral_z"][:, None] - tp[None]).min(1) < 1e-2
+    assert np.array_equal(idx[~near], golden_scoring["coral_idx"][~near])
+    assert np.abs(probs - golden_scoring["coral_probs"]).max() < 2e-6
+    assert set(np.unique(idx)) == {0, 3, 4}
+    i1, p1 = cal.predict(torch.tensor(0.5))
+    assert i1 == 3 and p1.shape == (5,)
+
+
+# ---------------------------------------------------------------------------------------------------
+# fusion head training step
+# ---------------------------------------------------------------------------------------------------
+def test_fusion_fwd_bwd(golden_scoring):
+    from dfd import ops
+    from oracle import scoring_ref as S
+
+    sd = S.init_fusion_g2(3)
+    flat = torch.cat([sd[k].reshape(-1).float() for k in ops.FUSION_PARAM_ORDER]).to(DEV)
+    zf = torch.from_numpy(golden_scoring["fuse_zfreq"]).to(DEV)
+    zs = torch.from_numpy(golden_scoring["fuse_zsig"]).to(DEV)
+    y = torch.from_numpy(golden_scoring["fuse_y"]).to(DEV)
+    loss, grads, logits = ops.fusion_fwd_bwd(flat, zf, zs, y, want_logits=True)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - float(golden_scoring["fuse_g2_loss"])) < 1e-5
+    gr = golden_scoring["fuse_g2_grads"]
+    assert np.abs(grads.cpu().numpy() - gr).max() < 1e-5 * max(1.0, np.abs(gr).max())
+    assert np.abs(logits.cpu().numpy() - golden_scoring["fuse_g2_z"]).max() < 2e-5
+    # linearity over shards: two half-batches with inv_global_batch = 1/B sum to the full-batch result
+    l1, g1, _ = ops.fusion_fwd_bwd(flat, zf[:40].contiguous(), zs[:40].contiguous(), y[:40].contiguous(), 1.0 / 64)
+    l2, g2, _ = ops.fusion_fwd_bwd(flat, zf[40:].contiguous(), zs[40:].contiguous(), y[40:].contiguous(), 1.0 / 64)
+    assert torch.allclose(l1 + l2, loss, atol=1e-6) and torch.allclose(g1 + g2, grads, atol=1e-6)
+    # large ragged batch vs float64 autograd oracle
+    rng = np.random.default_rng(1)
+    n = 10007
+    zf2, zs2 = rng.normal(0, 3, n).astype(np.float32), rng.normal(0, 3, n).astype(np.float32)
+    y2 = (rng.random(n) > 0.5).astype(np.float32)
+    lo, go, _ = S.fusion_loss_and_grads(sd, zf2, zs2, y2)
+    l3, g3, _ = ops.fusion_fwd_bwd(flat, torch.from_numpy(zf2).to(DEV), torch.from_numpy(zs2).to(DEV),
+                                   torch.from_numpy(y2).to(DEV))
+    assert abs(l3.item() - lo) < 1e-4 and np.abs(g3.cpu().numpy() - go).max() < 1e-4
