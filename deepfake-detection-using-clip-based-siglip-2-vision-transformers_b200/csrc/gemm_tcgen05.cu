@@ -20,7 +20,10 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;                       // two groups of 4 warps (one warp per TMEM lane quadrant)
+constexpr int kGemmThreads = (2 + kEpiWarps) * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kChunkN = 64;                         // epilogue / TMA-store granularity along N
+constexpr int kStageCBytes = BM * kChunkN * 2;      // 16 KB staging tile per epilogue group
 
 struct EpiArgs {
   const float* bias;
@@ -36,29 +39,49 @@ struct EpiArgs {
   float* stats_out;
 };
 
-template <int BN>
+// CG = CTAs per MMA (1, or 2 = cta_group::2: a 256 x BN tile shared by an SM pair, each CTA staging its own
+// 128 rows of A and HALF of the B tile, which roughly halves shared-memory traffic per MMA)
+template <int BN, int CG>
 struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (BN / CG) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
+  static constexpr int kStages = (227 * 1024 - 2 * kStageCBytes - 256 - 1024) / kStageBytes > 8
+                                     ? 8
+                                     : (227 * 1024 - 2 * kStageCBytes - 256 - 1024) / kStageBytes;
   static constexpr int kTileBytes = kStages * kStageBytes;
+  static constexpr int kCBytes = 2 * kStageCBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kTotal = kTileBytes + kBarBytes + 1024;  // +1024 alignment slack
+  static constexpr int kTotal = kTileBytes + kCBytes + kBarBytes + 1024;  // +1024 alignment slack
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN>
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+// gelu_pytorch_tanh with the single-MUFU tanh (abs error ~5e-4 of a value that is rounded to bf16 anyway)
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * x * fmaf(k1 * x, x, 1.0f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;\n" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+
+template <int BN, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
-                         const __grid_constant__ CUtensorMap tmB, __nv_bfloat16* C,
-                         int64_t ldc, int M, int N, int K, EpiArgs epi) {
-  using S = GemmSmem<BN>;
+                         const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmC, int M, int N, int K, EpiArgs epi) {
+  using S = GemmSmem<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kTileBytes);
+  uint8_t* smem_c = smem + S::kTileBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kTileBytes + S::kCBytes);
   uint64_t* empty_bar = full_bar + S::kStages;
   uint64_t* tfull_bar = empty_bar + S::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -67,14 +90,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_m = (M + BM - 1) / BM;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const int num_m = (M + BM * CG - 1) / (BM * CG);
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + BK - 1) / BK;
+  const int first_tile = blockIdx.x / CG;
+  const int tile_step = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
 #pragma unroll
     for (int s = 0; s < S::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -83,13 +111,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], kEpiWarps * CG);
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<S::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_pair<S::kTmemCols>(tmem_slot);
+    else tmem_alloc<S::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // peer barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -98,29 +130,38 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * BM;
-        const int n0 = (tile % num_n) * BN;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        // N fastest: CTAs working at the same time share A row blocks through L2; the weights (<= 10 MB)
+        // stay L2 resident for the whole GEMM
+        const int m0 = (tile / num_n) * (BM * CG) + (int)cta_rank * BM;
+        const int n0 = (tile % num_n) * BN + (int)cta_rank * (BN / CG) * (CG - 1);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
-          mbar_expect_tx(&full_bar[stage], S::kStageBytes);
-          tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m0);
-          tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
+          if (CG == 2) {
+            // the leader's barrier collects the bytes of both CTAs
+            if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+            tma_load_2d_pair(&tmA, &full_bar[stage], sa, kb * BK, m0);
+            tma_load_2d_pair(&tmB, &full_bar[stage], sb, kb * BK, n0);
+          } else {
+            mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+            tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m0);
+            tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
+          }
           if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    if (lane == 0 && is_leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -133,25 +174,43 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128-byte swizzle row: +2 in 16-byte units
-            umma_bf16_ss(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
-                         idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2)
+              umma_bf16_ss_pair(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                                idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16_ss(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                           idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+          // frees this smem stage (in both CTAs) when the MMAs retire
+          if (CG == 2) umma_commit_pair(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (CG == 2) umma_commit_pair(&tfull_bar[acc]);
+        else umma_commit(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
     // ------------------------------- epilogue -----------------------------------
+    // 8 warps = 2 groups; group g takes the 64-column chunks c ≡ g (mod 2) of every tile.  A chunk goes
+    // TMEM -> registers -> fused math -> bf16 -> 128B-swizzled staging tile -> one TMA store.
+    const int ew = warp - 2;
+    const int grp = ew >> 2;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;
+    const bool leader = ((ew & 3) == 0) && (lane == 0);
+    uint8_t* stage_c = smem_c + grp * kStageCBytes;
+    const uint32_t stage_row = smem_u32(stage_c) + static_cast<uint32_t>(row_in_tile * 128);
+    const int sw = row_in_tile & 7;
+    constexpr int kChunks = BN / kChunkN;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / num_n) * BM;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const int m0 = (tile / num_n) * (BM * CG) + (int)cta_rank * BM;
       const int n0 = (tile % num_n) * BN;
-      const int row = m0 + quad * 32 + lane;
+      const int row = m0 + row_in_tile;
       const bool row_ok = row < M;
 
       float ln_mean = 0.f, ln_rstd = 1.f;
@@ -162,95 +221,139 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         ln_rstd = rsqrtf(var + epi.ln_eps);
       }
       const float* pos_row =
-          epi.pos != nullptr ? epi.pos + (int64_t)(row % epi.pos_rows) * N : nullptr;
+          epi.pos != nullptr ? epi.pos + (int64_t)(row_ok ? (row % epi.pos_rows) : 0) * N : nullptr;
       const __nv_bfloat16* res_row =
-          epi.residual != nullptr ? epi.residual + (int64_t)row * epi.ldr : nullptr;
-      __nv_bfloat16* c_row = C + (int64_t)row * ldc;
+          (epi.residual != nullptr && row_ok) ? epi.residual + (int64_t)row * epi.ldr : nullptr;
       float st_sum = 0.f, st_sq = 0.f;
+
+      // residual of this group's first chunk is fetched before the accumulator is ready
+      uint4 res[8];
+      auto load_res = [&](int c) {
+        const int c0 = n0 + c * kChunkN;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          res[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (res_row != nullptr && c < kChunks && c0 + j * 8 < N)
+            res[j] = *reinterpret_cast<const uint4*>(res_row + c0 + j * 8);
+        }
+      };
+      load_res(grp);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(acc * BN);
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        const int c0 = n0 + ch * 32;
-        if (c0 >= N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(ch * 32), r);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int c = c0 + g * 8;
-            if (c < N) {
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-              if (epi.ln_colsum != nullptr) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(epi.ln_colsum + c));
-                const float4 s1 = __ldg(reinterpret_cast<const float4*>(epi.ln_colsum + c + 4));
-                const float cs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = ln_rstd * (v[j] - ln_mean * cs[j]);
-              }
-              if (epi.bias != nullptr) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + c));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + c + 4));
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-              if (epi.act == 1) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = gelu_tanh(v[j]);
-              }
-              if (pos_row != nullptr) {
-                const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos_row + c));
-                const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos_row + c + 4));
-                v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
-                v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
-              }
-              if (res_row != nullptr) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(res_row + c);
-                const float2 a0 = unpack_bf16x2(rr.x), a1 = unpack_bf16x2(rr.y),
-                             a2 = unpack_bf16x2(rr.z), a3 = unpack_bf16x2(rr.w);
-                v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
-                v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
-              }
-              uint4 o;
-              o.x = pack_bf16x2(v[0], v[1]);
-              o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]);
-              o.w = pack_bf16x2(v[6], v[7]);
-              if (epi.stats_out != nullptr) {
-                const float2 q0 = unpack_bf16x2(o.x), q1 = unpack_bf16x2(o.y),
-                             q2 = unpack_bf16x2(o.z), q3 = unpack_bf16x2(o.w);
-                st_sum += ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
-                st_sq += ((q0.x * q0.x + q0.y * q0.y) + (q1.x * q1.x + q1.y * q1.y)) +
-                         ((q2.x * q2.x + q2.y * q2.y) + (q3.x * q3.x + q3.y * q3.y));
-              }
-              *reinterpret_cast<uint4*>(c_row + c) = o;
-            }
-          }
+      // chunks of this tile that hold real columns (the N tail may leave a group without work)
+      const int nvalid = min(kChunks, (N - n0 + kChunkN - 1) / kChunkN);
+      if (grp >= nvalid) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(&tempty_bar[acc], 0);
+          else mbar_arrive(&tempty_bar[acc]);
         }
       }
-      // all TMEM reads of this accumulator stage are complete (wait::ld above)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+#pragma unroll 1
+      for (int c = grp; c < nvalid; c += 2) {
+        const int c0 = n0 + c * kChunkN;
+        uint32_t r[64];
+        tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * kChunkN), *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * kChunkN + 32),
+                           *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+        tmem_ld_wait();
+        if (c + 2 >= nvalid) {
+          // last chunk of this group for this tile: the accumulator stage can go back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(&tempty_bar[acc], 0);
+            else mbar_arrive(&tempty_bar[acc]);
+          }
+        }
+        uint4 o[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int cc = c0 + g * 8;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+          if (cc < N) {
+            if (epi.ln_colsum != nullptr) {
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(epi.ln_colsum + cc));
+              const float4 s1 = __ldg(reinterpret_cast<const float4*>(epi.ln_colsum + cc + 4));
+              const float cs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = ln_rstd * (v[j] - ln_mean * cs[j]);
+            }
+            if (epi.bias != nullptr) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + cc));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + cc + 4));
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (epi.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_fast(v[j]);
+            }
+            if (pos_row != nullptr) {
+              const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos_row + cc));
+              const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos_row + cc + 4));
+              v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
+              v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+            }
+            if (res_row != nullptr) {
+              const float2 a0 = unpack_bf16x2(res[g].x), a1 = unpack_bf16x2(res[g].y),
+                           a2 = unpack_bf16x2(res[g].z), a3 = unpack_bf16x2(res[g].w);
+              v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
+              v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
+            }
+          }
+          o[g].x = pack_bf16x2(v[0], v[1]);
+          o[g].y = pack_bf16x2(v[2], v[3]);
+          o[g].z = pack_bf16x2(v[4], v[5]);
+          o[g].w = pack_bf16x2(v[6], v[7]);
+          if (epi.stats_out != nullptr && cc < N) {
+            const float2 q0 = unpack_bf16x2(o[g].x), q1 = unpack_bf16x2(o[g].y),
+                         q2 = unpack_bf16x2(o[g].z), q3 = unpack_bf16x2(o[g].w);
+            st_sum += ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
+            st_sq += ((q0.x * q0.x + q0.y * q0.y) + (q1.x * q1.x + q1.y * q1.y)) +
+                     ((q2.x * q2.x + q2.y * q2.y) + (q3.x * q3.x + q3.y * q3.y));
+          }
+        }
+        load_res(c + 2);  // next chunk's residual travels while this one is stored
+        // staging tile free? (the previous TMA store of this group has finished reading it)
+        if (leader) tma_store_wait_read<0>();
+        named_bar_sync(1 + grp, 128);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint32_t addr = stage_row + static_cast<uint32_t>((g ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(o[g].x), "r"(o[g].y),
+                       "r"(o[g].z), "r"(o[g].w)
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + grp, 128);
+        if (leader) {
+          tma_store_2d(&tmC, stage_c, c0, m0);  // rows >= M and columns >= N are clipped by the TMA unit
+          tma_store_commit();
+        }
+      }
       if (epi.stats_out != nullptr && row_ok) {
         atomicAdd(epi.stats_out + 2 * (int64_t)row, st_sum);
         atomicAdd(epi.stats_out + 2 * (int64_t)row + 1, st_sq);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (leader) tma_store_wait<0>();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // no CTA of the pair leaves while the other may still touch it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<S::kTmemCols>(tmem_base);
+    if (CG == 2) tmem_dealloc_pair<S::kTmemCols>(tmem_base);
+    else tmem_dealloc<S::kTmemCols>(tmem_base);
   }
 }
 
@@ -281,7 +384,7 @@ PFN_encodeTiled get_encode_fn() {
 
 // bf16 row-major [rows, cols] with leading dimension ld (elements) -> 2-D tiled map, box = {64, box_rows}
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
-                      int box_rows) {
+                      int box_rows, bool store = false) {
   PFN_encodeTiled fn = get_encode_fn();
   DFD_REQUIRE(fn != nullptr, DFD_ERR_NO_DEVICE,
               "cuTensorMapEncodeTiled unavailable (no CUDA driver on this host)");
@@ -291,48 +394,64 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t 
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  store ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DFD_REQUIRE(r == CUDA_SUCCESS, DFD_ERR_CUDA,
               "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d", (int)r,
               (long long)rows, (long long)cols, (long long)ld, box_rows);
   return DFD_OK;
 }
 
-template <int BN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, __nv_bfloat16* C, int64_t ldc,
-                       int M, int N, int K, const EpiArgs& ea, cudaStream_t st) {
-  using S = GemmSmem<BN>;
+template <int BN, int CG>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N,
+                       int K, const EpiArgs& ea, cudaStream_t st) {
+  using S = GemmSmem<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    DFD_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>,
+    DFD_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CG>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
-  const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-  gemm_bf16_tcgen05_kernel<BN><<<grid, kGemmThreads, S::kTotal, st>>>(tmA, tmB, C, ldc, M, N, K, ea);
-  DFD_LAUNCH_CHECK();
+  const int num_tiles = ((M + BM * CG - 1) / (BM * CG)) * ((N + BN - 1) / BN);
+  const int max_units = kNumSMs / CG;
+  const int units = num_tiles < max_units ? num_tiles : max_units;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(units * CG);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DFD_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CG>, tmA, tmB, tmC, M, N, K, ea));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return DFD_OK;
 }
 
-// Tile-N choice: the widest tile that does not waste more than ~6 % of the MMA work on padding,
-// preferring tiles that give every SM work.
-static int pick_bn(int M, int N) {
+// Tile choice.  Large-M GEMMs run as CTA pairs (256 x BN tiles, cta_group::2); BN = 256 keeps the pair at the
+// shared-memory bandwidth limit, narrower tiles only pay off when they remove a mostly-empty N tail.
+static void pick_tile(int M, int N, int* bn_out, int* cg_out) {
+  const int cg = (M > BM * kNumSMs / 2) ? 2 : 1;
   const int cands[3] = {256, 192, 128};
+  const double penalty[3] = {1.0, 1.12, 1.35};
   int best = 128;
   double best_cost = 1e30;
-  const int num_m = (M + BM - 1) / BM;
+  const int num_m = (M + BM * cg - 1) / (BM * cg);
+  const int units = kNumSMs / cg;
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     const int num_n = (N + bn - 1) / bn;
     const long tiles = (long)num_m * num_n;
-    const long waves = (tiles + kNumSMs - 1) / kNumSMs;
-    // time ~ waves * (bn columns per tile) with a mild bonus for wider tiles (better operand reuse)
-    const double cost = (double)waves * bn * (bn == 256 ? 1.0 : (bn == 192 ? 1.03 : 1.10));
+    const long waves = (tiles + units - 1) / units;
+    const double cost = (double)waves * bn * penalty[i];
     if (cost < best_cost) { best_cost = cost; best = bn; }
   }
-  return best;
+  *bn_out = best;
+  *cg_out = cg;
 }
 
 int gemm_bf16_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
@@ -366,18 +485,35 @@ int gemm_bf16_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, v
     DFD_REQUIRE(ea.residual == nullptr || (ea.ldr % 8 == 0 && ea.ldr >= N), DFD_ERR_SHAPE,
                 "gemm: residual leading dimension invalid");
   }
-  const int bn = force_bn > 0 ? force_bn : pick_bn(M, N);
-  CUtensorMap tmA, tmB;
+  int bn = 0, cg = 1;
+  pick_tile(M, N, &bn, &cg);
+  if (force_bn > 0) {  // test hook: tile_n, +1000 forces single-CTA tiles, +2000 forces CTA pairs
+    bn = force_bn % 1000;
+    if (force_bn >= 2000) cg = 2;
+    else if (force_bn >= 1000) cg = 1;
+  }
+  DFD_REQUIRE(bn == 128 || bn == 192 || bn == 256, DFD_ERR_UNSUPPORTED, "gemm: unsupported tile N %d", bn);
+  CUtensorMap tmA, tmB, tmC;
   int rc = make_tmap_bf16_2d(&tmA, A, M, K, lda, BM);
   if (rc != DFD_OK) return rc;
-  rc = make_tmap_bf16_2d(&tmB, W, N, K, ldw, bn);
+  rc = make_tmap_bf16_2d(&tmB, W, N, K, ldw, bn / cg);
   if (rc != DFD_OK) return rc;
-  __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(C);
-  switch (bn) {
-    case 256: return launch_gemm<256>(tmA, tmB, Cb, ldc, M, N, K, ea, st);
-    case 192: return launch_gemm<192>(tmA, tmB, Cb, ldc, M, N, K, ea, st);
-    case 128: return launch_gemm<128>(tmA, tmB, Cb, ldc, M, N, K, ea, st);
-    default: break;
+  rc = make_tmap_bf16_2d(&tmC, C, M, N, ldc, BM, true);
+  if (rc != DFD_OK) return rc;
+  if (cg == 2) {
+    switch (bn) {
+      case 256: return launch_gemm<256, 2>(tmA, tmB, tmC, M, N, K, ea, st);
+      case 192: return launch_gemm<192, 2>(tmA, tmB, tmC, M, N, K, ea, st);
+      case 128: return launch_gemm<128, 2>(tmA, tmB, tmC, M, N, K, ea, st);
+      default: break;
+    }
+  } else {
+    switch (bn) {
+      case 256: return launch_gemm<256, 1>(tmA, tmB, tmC, M, N, K, ea, st);
+      case 192: return launch_gemm<192, 1>(tmA, tmB, tmC, M, N, K, ea, st);
+      case 128: return launch_gemm<128, 1>(tmA, tmB, tmC, M, N, K, ea, st);
+      default: break;
+    }
   }
   set_last_error("gemm: unsupported tile N %d", bn);
   return DFD_ERR_UNSUPPORTED;

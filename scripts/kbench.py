@@ -57,10 +57,10 @@ def gemms(B, arch):
         bias = torch.randn(n, device=DEV)
         out = torch.empty(m, n, dtype=torch.bfloat16, device=DEV)
         res = torch.randn(m, n, device=DEV).to(torch.bfloat16) if o.get("res") else None
-        for tn in (128, 192, 256, 0):
+        for tn in (1256, 2128, 2192, 2256, 0):
             med, best = timeit(lambda: ops.gemm_bf16(a, w, bias=bias, act=o.get("act", 0), residual=res, out=out, tile_n=tn))
             tf = 2.0 * m * n * k / med / 1e9
-            print(f"gemm {name:9s} M={m} N={n} K={k} tile={tn:3d}: {med:8.3f} ms  {tf:7.1f} TF/s "
+            print(f"gemm {name:9s} M={m} N={n} K={k} tile={tn:4d}: {med:8.3f} ms  {tf:7.1f} TF/s "
                   f"({tf / PEAKS['bf16_tflops'] * 100:4.1f}% of measured burst)  best {best:.3f}", flush=True)
         med, _ = timeit(lambda: torch.matmul(a, w.t(), out=out))
         print(f"   cuBLAS (torch.matmul, no epilogue) {med:8.3f} ms {2.0 * m * n * k / med / 1e9:7.1f} TF/s", flush=True)

@@ -41,7 +41,7 @@ GEMM_SHAPES = [
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-@pytest.mark.parametrize("tile_n", [0, 128, 192, 256])
+@pytest.mark.parametrize("tile_n", [0, 1128, 1192, 1256, 2128, 2192, 2256])  # auto, single-CTA, CTA-pair tiles
 def test_gemm_plain(M, N, K, tile_n):
     from dfd import ops
 
@@ -75,6 +75,8 @@ def test_gemm_epilogues(M, N, K):
         tol = 2.0 ** -8 * ref.abs() + 2e-3
         assert bool((err <= tol).all()), f"{what}: max err {err.max().item()}"
 
+    for tn in (1256, 2256, 2192):
+        close(ops.gemm_bf16(a, w, bias=bias, residual=res, tile_n=tn), acc + bias + res.float(), f"bias+residual tile {tn}")
     close(ops.gemm_bf16(a, w, bias=bias), acc + bias, "bias")
     close(ops.gemm_bf16(a, w, bias=bias, act=1), _gelu_tanh(acc + bias), "bias+gelu_tanh")
     close(ops.gemm_bf16(a, w, bias=bias, residual=res), acc + bias + res.float(), "bias+residual")
