@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of the detection hot path (SigLIP-2 so400m/14-384 backbone + classifier head + FreqMLP
+features + fusion/CORAL epilogue) on N B200s, data parallel.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (N>1: launched by torchrun)
+    python bench.py --impl reference [--gpus N] --steps K --warmup W  # the reference's CPU path on the host cores
+
+One "step" = one pass of the whole hot path over one batch of synthetic images per GPU (BASELINE.json
+configs[2]: so400m-patch14-384, 729 tokens, batch 512 per GPU, weak scaling).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "images/sec SigLIP-2 so400m/14-384 detect"
+WORKLOADS = {
+    "so400m-384": ("google/siglip2-so400m-patch14-384", 512),
+    "base-224": ("google/siglip2-base-patch16-224", 256),
+}
+
+
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks.update(json.load(f))
+        peaks["source"] = "measured"
+    except Exception:
+        pass
+    return peaks
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.t = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) >= 7:
+                self.rows.append(p)
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for p in self.rows:
+            try:
+                sm.append(float(p[0]))
+                mx = float(p[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arms (the only places bench.py touches oracle/): cpu_baseline of our arm, and --impl reference
+# ---------------------------------------------------------------------------------------------------------
+class CpuReference:
+    """The reference's CPU path for the hot path: backbone = the library call the reference makes
+    (transformers.SiglipVisionModel, Siglip2sidafrozen.py:753,787; fp32, all host threads) when importable, else
+    the oracle restatement; heads / frequency features / fusion / CORAL = the oracle port of the reference's
+    functions (train_fusion_head_only.py:142-317, app.py:1265-1396), one image at a time like its loops."""
+
+    def __init__(self, workload: str):
+        import torch
+
+        from oracle import scoring_ref as S
+        from oracle import siglip_ref as R
+
+        self.torch, self.S, self.R = torch, S, R
+        name = WORKLOADS[workload][0].split("/")[-1]
+        self.cfg = R.CONFIGS[name]
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        sd = R.init_state_dict(self.cfg, 0)
+        self.sd, self.hf, self.kind = sd, None, "port"
+        try:
+            from transformers import SiglipVisionConfig, SiglipVisionModel
+
+            c = self.cfg
+            m = SiglipVisionModel(SiglipVisionConfig(hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
+                                                     num_hidden_layers=c.num_hidden_layers,
+                                                     num_attention_heads=c.num_attention_heads,
+                                                     image_size=c.image_size, patch_size=c.patch_size)).eval()
+            m.load_state_dict({"vision_model." + k: v for k, v in sd.items()}, strict=True)
+            self.hf = m
+        except Exception:
+            self.hf = None
+        self.head = R.init_head("B", self.cfg.hidden_size, 1)
+        self.fm, self.fu = S.init_freq_mlp_g2(2), S.init_fusion_g2(3)
+        self.cuts = __import__("numpy").array([-1.0, -0.2, 0.3, 1.5], dtype="float32")
+
+    def run(self, n: int, seed: int = 0) -> float:
+        """Hot path over n synthetic images; returns seconds."""
+        import numpy as np
+
+        torch, S, R = self.torch, self.S, self.R
+        img = R.synthetic_images(n, self.cfg.image_size, seed)
+        t0 = time.perf_counter()
+        with torch.inference_mode():
+            x = R.preprocess_u8(img)
+            if self.hf is not None:
+                pooled = self.hf(pixel_values=x).pooler_output
+            else:
+                pooled = R.siglip_vision_forward(self.sd, self.cfg, x, "fp32")["pooler_output"]
+            z_sig = R.classifier_head(self.head, "B", pooled, 1e-6).numpy()
+        feats = np.stack([S.extract_freq_vector(S.gray256_from_rgb_u8(im.numpy(), True)) for im in img])
+        z = S.fusion_g2(self.fu, S.freq_mlp_g2(self.fm, feats), z_sig)
+        S.detect_scores(z, self.cuts, 1.0)
+        return time.perf_counter() - t0
+
+    def describe(self, n: int) -> str:
+        bb = "transformers.SiglipVisionModel fp32 (the reference's own backbone call)" if self.hf is not None \
+            else "oracle/siglip_ref.py fp32"
+        return (f"{n} synthetic {self.cfg.image_size}x{self.cfg.image_size} images per step: backbone {bb}, "
+                f"{self.cores} torch threads; heads+freq features+fusion+CORAL = oracle port, single thread per image")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ref = CpuReference(args.workload)
+    t1 = ref.run(1, seed=99)                       # probe (also first-touch warm-up)
+    n = max(1, min(16, int(4.0 / max(t1, 1e-3))))  # ~4 s per step
+    for _ in range(args.warmup):
+        ref.run(n, seed=1)
+    ts = [ref.run(n, seed=2 + i) for i in range(args.steps)]
+    total = sum(ts)
+    value = n * args.steps / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][0]} detect, CPU sample of {n} images/step"},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": ref.cores, "kind": ref.kind,
+                             "sample": ref.describe(n)},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+
+    from dfd import _lib, distributed, pipeline, scoring, weights
+    from dfd.engine import ARCHS
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the dfd hot path has no CPU fallback")
+    rank, world, local = distributed.init_from_env("nccl")
+    if world != args.gpus and world > 1:
+        print(f"bench.py: WORLD_SIZE={world} overrides --gpus {args.gpus}", file=sys.stderr)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    arch_name, default_batch = WORKLOADS[args.workload]
+    B = args.batch or default_batch
+    arch = ARCHS[arch_name]
+    peaks = load_peaks()
+    lib = _lib.load()
+
+    bsd = weights.random_vision_state_dict(arch, seed=0, device=dev)
+    st = scoring.ScoringStack(dev, weights.random_freq_mlp_g2(2), weights.random_fusion_g2(3), [-1.0, -0.2, 0.3, 1.5], 1.0)
+    pipe = pipeline.DetectionPipeline(arch, bsd, weights.random_classifier_head("B", arch.hidden_size, 1), st,
+                                      device=local, max_batch=min(B, args.max_batch))
+    del bsd
+    S = arch.image_size
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    images = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8, device=dev, generator=g)
+    gray = torch.randint(0, 256, (B, 256, 256), device=dev, generator=g).float() / 255.0
+
+    def step_device():
+        out = pipe.detect_device(images, gray)
+        return distributed.all_gather_records(pipe.pack(out))
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+
+    # ---- timed region 1: inputs resident in HBM ------------------------------------------------------
+    pipe.engine.profile(True)
+    fam_ms = {k: 0.0 for k in ("gemm", "attention", "layernorm", "other")}
+    fam_n = dict.fromkeys(fam_ms, 0)
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = lib.dfd_launch_count()
+    distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+        if pipe.engine.max_batch >= B:  # one engine forward per step: its per-launch events can be read back
+            for k, (ms, n) in pipe.engine.profile_read().items():
+                fam_ms[k] += ms
+                fam_n[k] += n
+    e1.record()
+    distributed.barrier()
+    torch.cuda.synchronize()
+    dt = distributed.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+    launches = (lib.dfd_launch_count() - launches0) // args.steps
+    clocks = sampler.stop() if sampler else None
+    pipe.engine.profile(False)
+    value = world * B * args.steps / dt
+
+    # ---- timed region 2: end to end through the public API, host buffers --------------------------------
+    h_img = torch.empty((B, S, S, 3), dtype=torch.uint8).pin_memory()
+    h_gray = torch.empty((B, 256, 256), dtype=torch.float32).pin_memory()
+    h_img.copy_(images)
+    h_gray.copy_(gray)
+
+    def step_host():
+        rec = pipe.detect(h_img, h_gray)          # H2D (pinned) + kernels + D2H of the packed score records
+        if world > 1:
+            distributed.all_gather_records(torch.from_numpy(rec).to(dev))
+        return rec
+
+    for _ in range(2):
+        step_host()
+    distributed.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        rec = step_host()
+    e1.record()
+    torch.cuda.synchronize()
+    distributed.barrier()
+    dt_e2e = distributed.max_over_ranks(max(e0.elapsed_time(e1) / 1e3, time.perf_counter() - t0), dev)
+    e2e_value = world * B * args.steps / dt_e2e
+    h2d = h_img.numel() + h_gray.numel() * 4
+    d2h = rec.size * 4
+
+    if rank != 0:
+        return
+    gemm_flops = pipe.engine.gemm_flops(B) * args.steps
+    roof = None
+    if fam_ms["gemm"] > 0:
+        ach = gemm_flops / (fam_ms["gemm"] / 1e3) / 1e12
+        peak = float(peaks["bf16_tflops_sustained"])
+        step_ms = dt / args.steps * 1e3
+        roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of the step)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                "launches_per_step": fam_n["gemm"] // args.steps,
+                "avg_launch_ms": fam_ms["gemm"] / max(fam_n["gemm"], 1),
+                "traffic": args.gemm_traffic,
+                "share_of_step": {k: fam_ms[k] / args.steps / step_ms for k in fam_ms}}
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {arch_name} detect (backbone+H-B head+freq features+G2 fusion+CORAL)",
+                   "per_gpu_batch": B, "global_batch": B * world, "tokens": arch.tokens, "parallelism": f"dp{world}",
+                   "l2": "per-step inputs (u8 images + gray256) and activations are >> the 126 MB L2; no flush needed",
+                   "weights": "random init (seeded), bf16"},
+        "tensor_pipe_frac_of_step": arch.flops_per_image() * value / world / 1e12 / float(peaks["bf16_tflops_sustained"]),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": dt_e2e / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        ref = CpuReference(args.workload)
+        t1 = ref.run(1, seed=99)
+        n = max(1, min(16, int(12.0 / max(t1, 1e-3))))
+        t = ref.run(n, seed=5)
+        line["cpu_baseline"] = {"value": n / t, "unit": "images/s", "cores": ref.cores, "kind": ref.kind,
+                                "sample": ref.describe(n) + f"; one timed pass of {t:.1f} s after a 1-image warm-up"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="so400m-384")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--max-batch", type=int, default=512, help="engine workspace batch (larger batches are chunked)")
+    ap.add_argument("--gemm-traffic", type=float, default=None,
+                    help="dram bytes per GEMM launch from an ncu --set full capture (profiles/), else null")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+    try:
+        import torch.distributed as dist
+
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

@@ -112,6 +112,8 @@ SIGNATURES = {
     "dfd_engine_finalize": (_I, [_P]),
     "dfd_engine_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "dfd_engine_workspace_bytes": (_L, [_P]),
+    "dfd_engine_profile": (_I, [_P, _I]),
+    "dfd_engine_profile_read": (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
 }
 
 _lib = None

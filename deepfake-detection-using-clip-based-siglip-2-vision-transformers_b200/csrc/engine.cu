@@ -85,6 +85,12 @@ struct dfd_engine {
   __nv_bfloat16 *patches, *x, *h, *qkv, *att, *mlp, *ao, *r, *h2, *m2;
   void* staging;
   int64_t staging_bytes;
+  // optional per-launch CUDA-event timing of the forward (bench.py roofline): family 0 GEMM, 1 attention,
+  // 2 LayerNorm, 3 other (patchify, MAP attention)
+  bool prof_on;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_fam;
+  int prof_n;
 };
 
 namespace dfd {
@@ -291,6 +297,8 @@ extern "C" DFD_API int dfd_engine_create(const dfd_config* cfg, int device, int 
   e->wslab = e->aslab = nullptr;
   e->staging = nullptr;
   e->staging_bytes = 0;
+  e->prof_on = false;
+  e->prof_n = 0;
   carve_weights(e, nullptr, &e->wbytes);
   carve_acts(e, nullptr, &e->abytes);
   cudaError_t err = cudaMalloc(&e->wslab, e->wbytes);
@@ -315,6 +323,7 @@ extern "C" DFD_API int dfd_engine_destroy(dfd_engine* e) {
   if (e->wslab) cudaFree(e->wslab);
   if (e->aslab) cudaFree(e->aslab);
   if (e->staging) cudaFree(e->staging);
+  for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
   delete e;
   return DFD_OK;
 }
@@ -380,6 +389,49 @@ extern "C" DFD_API int dfd_engine_finalize(dfd_engine* e) {
     if (_rc != DFD_OK) return _rc; \
   } while (0)
 
+// run one launch, bracketed by events when profiling is on
+#define DFD_OP(fam, expr)                                                                   \
+  do {                                                                                      \
+    const bool _p = e->prof_on && (size_t)(2 * e->prof_n + 2) <= e->prof_ev.size();          \
+    if (_p) DFD_CUDA(cudaEventRecord(e->prof_ev[2 * e->prof_n], st));                        \
+    DFD_TRY(expr);                                                                          \
+    if (_p) {                                                                               \
+      DFD_CUDA(cudaEventRecord(e->prof_ev[2 * e->prof_n + 1], st));                          \
+      e->prof_fam[e->prof_n++] = (fam);                                                     \
+    }                                                                                       \
+  } while (0)
+
+extern "C" DFD_API int dfd_engine_profile(dfd_engine* e, int enable) {
+  DFD_REQUIRE(e, DFD_ERR_BAD_ARG, "profile: null engine");
+  DeviceGuard guard(e->device);
+  if (enable && e->prof_ev.empty()) {
+    const int n = 16 + 8 * e->L;
+    e->prof_ev.resize(2 * n);
+    e->prof_fam.assign(n, 0);
+    for (auto& ev : e->prof_ev) DFD_CUDA(cudaEventCreate(&ev));
+  }
+  e->prof_on = enable != 0;
+  e->prof_n = 0;
+  return DFD_OK;
+}
+
+// Sums the event-timed durations of the LAST profiled forward per kernel family (ms) and launch counts.
+// Synchronises on the last recorded event.
+extern "C" DFD_API int dfd_engine_profile_read(dfd_engine* e, float* ms4, int* count4) {
+  DFD_REQUIRE(e && ms4 && count4, DFD_ERR_BAD_ARG, "profile_read: null pointer");
+  DeviceGuard guard(e->device);
+  for (int i = 0; i < 4; ++i) { ms4[i] = 0.f; count4[i] = 0; }
+  if (e->prof_n == 0) return DFD_OK;
+  DFD_CUDA(cudaEventSynchronize(e->prof_ev[2 * e->prof_n - 1]));
+  for (int i = 0; i < e->prof_n; ++i) {
+    float ms = 0.f;
+    DFD_CUDA(cudaEventElapsedTime(&ms, e->prof_ev[2 * i], e->prof_ev[2 * i + 1]));
+    ms4[e->prof_fam[i] & 3] += ms;
+    count4[e->prof_fam[i] & 3] += 1;
+  }
+  return DFD_OK;
+}
+
 extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int pix_format, int B, int Hin,
                                           int Win, int resize_mode, void* pooled, void* last_hidden,
                                           void* stream) {
@@ -391,72 +443,73 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
   const int M = B * N;
   const float eps = e->cfg.ln_eps;
   const float scale = 1.0f / sqrtf((float)hd);
+  e->prof_n = 0;
 
-  DFD_TRY(patchify(pixels, pix_format, B, Hin, Win, e->S, e->P, resize_mode, e->patches, e->Kpad, st));
+  DFD_OP(3, patchify(pixels, pix_format, B, Hin, Win, e->S, e->P, resize_mode, e->patches, e->Kpad, st));
   {
     dfd_gemm_epilogue ep{};
     ep.bias = e->b_pe;
     ep.pos = e->pos;
     ep.pos_rows = N;
-    DFD_TRY(gemm_bf16_dispatch(e->patches, e->Kpad, e->w_pe, e->Kpad, e->x, D, M, D, e->Kpad, &ep, 0, st));
+    DFD_OP(0, gemm_bf16_dispatch(e->patches, e->Kpad, e->w_pe, e->Kpad, e->x, D, M, D, e->Kpad, &ep, 0, st));
   }
   for (int li = 0; li < e->L; ++li) {
     const Layer& l = e->layers[li];
-    DFD_TRY(layernorm_bf16(e->x, D, e->h, D, l.ln1_g, l.ln1_b, M, D, eps, st));
+    DFD_OP(2, layernorm_bf16(e->x, D, e->h, D, l.ln1_g, l.ln1_b, M, D, eps, st));
     {
       dfd_gemm_epilogue ep{};
       ep.bias = l.b_qkv;
-      DFD_TRY(gemm_bf16_dispatch(e->h, D, l.w_qkv, D, e->qkv, 3 * D, M, 3 * D, D, &ep, 0, st));
+      DFD_OP(0, gemm_bf16_dispatch(e->h, D, l.w_qkv, D, e->qkv, 3 * D, M, 3 * D, D, &ep, 0, st));
     }
-    DFD_TRY(attention_bf16(e->qkv, 3 * D, e->att, D, B, N, H, hd, scale, st));
+    DFD_OP(1, attention_bf16(e->qkv, 3 * D, e->att, D, B, N, H, hd, scale, st));
     {
       dfd_gemm_epilogue ep{};
       ep.bias = l.b_o;
       ep.residual = e->x;
       ep.ldr = D;
-      DFD_TRY(gemm_bf16_dispatch(e->att, D, l.w_o, D, e->x, D, M, D, D, &ep, 0, st));
+      DFD_OP(0, gemm_bf16_dispatch(e->att, D, l.w_o, D, e->x, D, M, D, D, &ep, 0, st));
     }
-    DFD_TRY(layernorm_bf16(e->x, D, e->h, D, l.ln2_g, l.ln2_b, M, D, eps, st));
+    DFD_OP(2, layernorm_bf16(e->x, D, e->h, D, l.ln2_g, l.ln2_b, M, D, eps, st));
     {
       dfd_gemm_epilogue ep{};
       ep.bias = l.b_fc1;
       ep.act = 1;
-      DFD_TRY(gemm_bf16_dispatch(e->h, D, l.w_fc1, D, e->mlp, I, M, I, D, &ep, 0, st));
+      DFD_OP(0, gemm_bf16_dispatch(e->h, D, l.w_fc1, D, e->mlp, I, M, I, D, &ep, 0, st));
     }
     {
       dfd_gemm_epilogue ep{};
       ep.bias = l.b_fc2;
       ep.residual = e->x;
       ep.ldr = D;
-      DFD_TRY(gemm_bf16_dispatch(e->mlp, I, l.w_fc2, I, e->x, D, M, D, I, &ep, 0, st));
+      DFD_OP(0, gemm_bf16_dispatch(e->mlp, I, l.w_fc2, I, e->x, D, M, D, I, &ep, 0, st));
     }
   }
   __nv_bfloat16* xp = last_hidden ? reinterpret_cast<__nv_bfloat16*>(last_hidden) : e->h;
-  DFD_TRY(layernorm_bf16(e->x, D, xp, D, e->post_g, e->post_b, M, D, eps, st));
+  DFD_OP(2, layernorm_bf16(e->x, D, xp, D, e->post_g, e->post_b, M, D, eps, st));
   {  // K | V projection of every token (rows D..3D of in_proj)
     dfd_gemm_epilogue ep{};
     ep.bias = e->b_in + D;
-    DFD_TRY(gemm_bf16_dispatch(xp, D, e->w_in + (int64_t)D * D, D, e->qkv, 2 * D, M, 2 * D, D, &ep, 0, st));
+    DFD_OP(0, gemm_bf16_dispatch(xp, D, e->w_in + (int64_t)D * D, D, e->qkv, 2 * D, M, 2 * D, D, &ep, 0, st));
   }
-  DFD_TRY(map_attention_bf16(e->qkv, 2 * D, e->q_probe, e->ao, D, B, N, H, hd, scale, st));
+  DFD_OP(3, map_attention_bf16(e->qkv, 2 * D, e->q_probe, e->ao, D, B, N, H, hd, scale, st));
   {
     dfd_gemm_epilogue ep{};
     ep.bias = e->b_mo;
-    DFD_TRY(gemm_bf16_dispatch(e->ao, D, e->w_mo, D, e->r, D, B, D, D, &ep, 0, st));
+    DFD_OP(0, gemm_bf16_dispatch(e->ao, D, e->w_mo, D, e->r, D, B, D, D, &ep, 0, st));
   }
-  DFD_TRY(layernorm_bf16(e->r, D, e->h2, D, e->hln_g, e->hln_b, B, D, eps, st));
+  DFD_OP(2, layernorm_bf16(e->r, D, e->h2, D, e->hln_g, e->hln_b, B, D, eps, st));
   {
     dfd_gemm_epilogue ep{};
     ep.bias = e->b_mfc1;
     ep.act = 1;
-    DFD_TRY(gemm_bf16_dispatch(e->h2, D, e->w_mfc1, D, e->m2, I, B, I, D, &ep, 0, st));
+    DFD_OP(0, gemm_bf16_dispatch(e->h2, D, e->w_mfc1, D, e->m2, I, B, I, D, &ep, 0, st));
   }
   {
     dfd_gemm_epilogue ep{};
     ep.bias = e->b_mfc2;
     ep.residual = e->r;
     ep.ldr = D;
-    DFD_TRY(gemm_bf16_dispatch(e->m2, I, e->w_mfc2, I, pooled, D, B, D, I, &ep, 0, st));
+    DFD_OP(0, gemm_bf16_dispatch(e->m2, I, e->w_mfc2, I, pooled, D, B, D, I, &ep, 0, st));
   }
   return DFD_OK;
 }

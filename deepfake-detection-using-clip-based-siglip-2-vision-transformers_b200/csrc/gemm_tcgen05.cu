@@ -21,7 +21,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int kEpiWarps = 8;                       // two groups of 4 warps (one warp per TMEM lane quadrant)
-constexpr int kGemmThreads = (2 + kEpiWarps) * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kGemmThreads = (3 + kEpiWarps) * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 residual TMA
+constexpr int kResSlots = 4;                        // residual chunks in flight (RES kernels only)
 constexpr int kChunkN = 64;                         // epilogue / TMA-store granularity along N
 constexpr int kStageCBytes = BM * kChunkN * 2;      // 16 KB staging tile per epilogue group
 
@@ -41,16 +42,17 @@ struct EpiArgs {
 
 // CG = CTAs per MMA (1, or 2 = cta_group::2: a 256 x BN tile shared by an SM pair, each CTA staging its own
 // 128 rows of A and HALF of the B tile, which roughly halves shared-memory traffic per MMA)
-template <int BN, int CG>
+// RES = the epilogue adds a bf16 residual tile; it is prefetched chunk by chunk with TMA into its own ring.
+template <int BN, int CG, int RES>
 struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (BN / CG) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (227 * 1024 - 2 * kStageCBytes - 256 - 1024) / kStageBytes > 8
-                                     ? 8
-                                     : (227 * 1024 - 2 * kStageCBytes - 256 - 1024) / kStageBytes;
+  static constexpr int kResBytes = RES ? kResSlots * kStageCBytes : 0;
+  static constexpr int kAvail = 227 * 1024 - 2 * kStageCBytes - kResBytes - 256 - 1024;
+  static constexpr int kStages = kAvail / kStageBytes > 8 ? 8 : kAvail / kStageBytes;
   static constexpr int kTileBytes = kStages * kStageBytes;
-  static constexpr int kCBytes = 2 * kStageCBytes;
+  static constexpr int kCBytes = 2 * kStageCBytes + kResBytes;  // C staging (2) then the residual ring
   static constexpr int kBarBytes = 256;
   static constexpr int kTotal = kTileBytes + kCBytes + kBarBytes + 1024;  // +1024 alignment slack
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
@@ -70,12 +72,13 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   return fmaf(hx, t, hx);
 }
 
-template <int BN, int CG>
+template <int BN, int CG, int RES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                          const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmC, int M, int N, int K, EpiArgs epi) {
-  using S = GemmSmem<BN, CG>;
+                         const __grid_constant__ CUtensorMap tmC,
+                         const __grid_constant__ CUtensorMap tmR, int M, int N, int K, EpiArgs epi) {
+  using S = GemmSmem<BN, CG, RES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -85,7 +88,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   uint64_t* empty_bar = full_bar + S::kStages;
   uint64_t* tfull_bar = empty_bar + S::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* rfull_bar = tempty_bar + 2;
+  uint64_t* rempty_bar = rfull_bar + kResSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + kResSlots);
+  uint8_t* smem_r = smem_c + 2 * kStageCBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -112,6 +118,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], kEpiWarps * CG);
+    }
+#pragma unroll
+    for (int r = 0; r < kResSlots; ++r) {
+      mbar_init(&rfull_bar[r], 1);
+      mbar_init(&rempty_bar[r], 4);
     }
     mbar_fence_init();
   }
@@ -192,6 +203,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
+  } else if (warp == 2 + kEpiWarps) {
+    // ------------------------------- residual producer --------------------------
+    if (RES && lane == 0) {
+      tma_prefetch_desc(&tmR);
+      uint32_t q = 0;  // running chunk number of this CTA
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int m0 = (tile / num_n) * (BM * CG) + (int)cta_rank * BM;
+        const int n0 = (tile % num_n) * BN;
+        const int nvalid = min(BN / kChunkN, (N - n0 + kChunkN - 1) / kChunkN);
+        for (int c = 0; c < nvalid; ++c, ++q) {
+          const int slot = q % kResSlots;
+          mbar_wait(&rempty_bar[slot], ((q / kResSlots) & 1u) ^ 1u);
+          mbar_expect_tx(&rfull_bar[slot], kStageCBytes);
+          tma_load_2d(&tmR, &rfull_bar[slot], smem_r + slot * kStageCBytes, n0 + c * kChunkN, m0);
+        }
+      }
+    }
   } else {
     // ------------------------------- epilogue -----------------------------------
     // 8 warps = 2 groups; group g takes the 64-column chunks c ≡ g (mod 2) of every tile.  A chunk goes
@@ -207,6 +235,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     constexpr int kChunks = BN / kChunkN;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t q_base = 0;  // running residual chunk number at the start of the tile
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       const int m0 = (tile / num_n) * (BM * CG) + (int)cta_rank * BM;
       const int n0 = (tile % num_n) * BN;
@@ -222,22 +251,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       }
       const float* pos_row =
           epi.pos != nullptr ? epi.pos + (int64_t)(row_ok ? (row % epi.pos_rows) : 0) * N : nullptr;
-      const __nv_bfloat16* res_row =
-          (epi.residual != nullptr && row_ok) ? epi.residual + (int64_t)row * epi.ldr : nullptr;
       float st_sum = 0.f, st_sq = 0.f;
-
-      // residual of this group's first chunk is fetched before the accumulator is ready
-      uint4 res[8];
-      auto load_res = [&](int c) {
-        const int c0 = n0 + c * kChunkN;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          res[j] = make_uint4(0u, 0u, 0u, 0u);
-          if (res_row != nullptr && c < kChunks && c0 + j * 8 < N)
-            res[j] = *reinterpret_cast<const uint4*>(res_row + c0 + j * 8);
-        }
-      };
-      load_res(grp);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -270,6 +284,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             else mbar_arrive(&tempty_bar[acc]);
           }
         }
+        uint4 res[8];
+        if (RES) {
+          // this chunk's residual tile was prefetched by the residual warp (128B-swizzled, like the C staging)
+          const uint32_t q = q_base + (uint32_t)c;
+          const int slot = q % kResSlots;
+          mbar_wait(&rfull_bar[slot], (q / kResSlots) & 1u);
+          const uint32_t rrow = smem_u32(smem_r + slot * kStageCBytes) + static_cast<uint32_t>(row_in_tile * 128);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+                         : "=r"(res[g].x), "=r"(res[g].y), "=r"(res[g].z), "=r"(res[g].w)
+                         : "r"(rrow + static_cast<uint32_t>((g ^ sw) << 4)));
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&rempty_bar[slot]);
+        }
         uint4 o[8];
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -301,7 +331,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
               v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
               v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
             }
-            if (res_row != nullptr) {
+            if (RES) {
               const float2 a0 = unpack_bf16x2(res[g].x), a1 = unpack_bf16x2(res[g].y),
                            a2 = unpack_bf16x2(res[g].z), a3 = unpack_bf16x2(res[g].w);
               v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
@@ -320,7 +350,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                      ((q2.x * q2.x + q2.y * q2.y) + (q3.x * q3.x + q3.y * q3.y));
           }
         }
-        load_res(c + 2);  // next chunk's residual travels while this one is stored
         // staging tile free? (the previous TMA store of this group has finished reading it)
         if (leader) tma_store_wait_read<0>();
         named_bar_sync(1 + grp, 128);
@@ -342,6 +371,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         atomicAdd(epi.stats_out + 2 * (int64_t)row, st_sum);
         atomicAdd(epi.stats_out + 2 * (int64_t)row + 1, st_sq);
       }
+      q_base += (uint32_t)nvalid;
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (leader) tma_store_wait<0>();
@@ -402,13 +432,13 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t 
   return DFD_OK;
 }
 
-template <int BN, int CG>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N,
-                       int K, const EpiArgs& ea, cudaStream_t st) {
-  using S = GemmSmem<BN, CG>;
+template <int BN, int CG, int RES>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                       const CUtensorMap& tmR, int M, int N, int K, const EpiArgs& ea, cudaStream_t st) {
+  using S = GemmSmem<BN, CG, RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    DFD_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CG>,
+    DFD_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CG, RES>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
@@ -427,7 +457,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DFD_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CG>, tmA, tmB, tmC, M, N, K, ea));
+  DFD_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CG, RES>, tmA, tmB, tmC, tmR, M, N, K, ea));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return DFD_OK;
 }
@@ -437,7 +467,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 static void pick_tile(int M, int N, int* bn_out, int* cg_out) {
   const int cg = (M > BM * kNumSMs / 2) ? 2 : 1;
   const int cands[3] = {256, 192, 128};
-  const double penalty[3] = {1.0, 1.12, 1.35};
+  const double penalty[3] = {1.0, 1.2, 1.45};
   int best = 128;
   double best_cost = 1e30;
   const int num_m = (M + BM * cg - 1) / (BM * cg);
@@ -484,6 +514,7 @@ int gemm_bf16_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, v
     DFD_REQUIRE(ea.ln_colsum == nullptr || epi->ln_dim > 0, DFD_ERR_BAD_ARG, "gemm: ln_dim must be > 0");
     DFD_REQUIRE(ea.residual == nullptr || (ea.ldr % 8 == 0 && ea.ldr >= N), DFD_ERR_SHAPE,
                 "gemm: residual leading dimension invalid");
+    DFD_REQUIRE((uintptr_t)ea.residual % 16 == 0, DFD_ERR_BAD_ARG, "gemm: residual must be 16-byte aligned");
   }
   int bn = 0, cg = 1;
   pick_tile(M, N, &bn, &cg);
@@ -493,28 +524,30 @@ int gemm_bf16_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, v
     else if (force_bn >= 1000) cg = 1;
   }
   DFD_REQUIRE(bn == 128 || bn == 192 || bn == 256, DFD_ERR_UNSUPPORTED, "gemm: unsupported tile N %d", bn);
-  CUtensorMap tmA, tmB, tmC;
+  CUtensorMap tmA, tmB, tmC, tmR;
   int rc = make_tmap_bf16_2d(&tmA, A, M, K, lda, BM);
   if (rc != DFD_OK) return rc;
   rc = make_tmap_bf16_2d(&tmB, W, N, K, ldw, bn / cg);
   if (rc != DFD_OK) return rc;
   rc = make_tmap_bf16_2d(&tmC, C, M, N, ldc, BM, true);
   if (rc != DFD_OK) return rc;
-  if (cg == 2) {
-    switch (bn) {
-      case 256: return launch_gemm<256, 2>(tmA, tmB, tmC, M, N, K, ea, st);
-      case 192: return launch_gemm<192, 2>(tmA, tmB, tmC, M, N, K, ea, st);
-      case 128: return launch_gemm<128, 2>(tmA, tmB, tmC, M, N, K, ea, st);
-      default: break;
-    }
-  } else {
-    switch (bn) {
-      case 256: return launch_gemm<256, 1>(tmA, tmB, tmC, M, N, K, ea, st);
-      case 192: return launch_gemm<192, 1>(tmA, tmB, tmC, M, N, K, ea, st);
-      case 128: return launch_gemm<128, 1>(tmA, tmB, tmC, M, N, K, ea, st);
-      default: break;
-    }
+  const bool has_res = ea.residual != nullptr;
+  tmR = tmC;
+  if (has_res) {
+    rc = make_tmap_bf16_2d(&tmR, ea.residual, M, N, ea.ldr, BM);
+    if (rc != DFD_OK) return rc;
   }
+#define DFD_GEMM_CASE(BN_, CG_)                                                                   \
+  if (bn == BN_ && cg == CG_)                                                                     \
+    return has_res ? launch_gemm<BN_, CG_, 1>(tmA, tmB, tmC, tmR, M, N, K, ea, st)                 \
+                   : launch_gemm<BN_, CG_, 0>(tmA, tmB, tmC, tmR, M, N, K, ea, st);
+  DFD_GEMM_CASE(256, 2)
+  DFD_GEMM_CASE(192, 2)
+  DFD_GEMM_CASE(128, 2)
+  DFD_GEMM_CASE(256, 1)
+  DFD_GEMM_CASE(192, 1)
+  DFD_GEMM_CASE(128, 1)
+#undef DFD_GEMM_CASE
   set_last_error("gemm: unsupported tile N %d", bn);
   return DFD_ERR_UNSUPPORTED;
 }

@@ -221,3 +221,21 @@ class SiglipEngine:
         return pooled, last
 
     __call__ = forward
+
+    def profile(self, enable: bool = True) -> None:
+        """Bracket every launch of the following forwards with CUDA events (bench.py roofline)."""
+        check(self._lib.dfd_engine_profile(self._h, int(enable)))
+
+    def profile_read(self) -> dict:
+        """Per kernel family of the LAST forward: {'gemm': (ms, launches), 'attention': ..., 'layernorm': ..., 'other': ...}."""
+        ms, cnt = (C.c_float * 4)(), (C.c_int * 4)()
+        check(self._lib.dfd_engine_profile_read(self._h, ms, cnt))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("gemm", "attention", "layernorm", "other"))}
+
+    def gemm_flops(self, batch: int) -> float:
+        """Algorithmic FLOPs of all GEMM launches of one forward of `batch` images (2·M·N·K each; the
+        patch-embedding K is the unpadded 3·P²)."""
+        a = self.arch
+        N, D, I, L, P = a.tokens, a.hidden_size, a.intermediate_size, a.num_hidden_layers, a.patch_size
+        per_img = 2 * N * 3 * P * P * D + L * (8 * N * D * D + 4 * N * D * I) + 4 * N * D * D + 2 * D * D + 4 * D * I
+        return float(per_img) * batch

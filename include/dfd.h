@@ -216,6 +216,11 @@ DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int pix_format
                                int Win, int resize_mode, void* pooled, void* last_hidden,
                                void* stream);
 DFD_API int64_t dfd_engine_workspace_bytes(const dfd_engine* e);
+/* Measurement aid (bench.py roofline): when enabled, dfd_engine_forward brackets every launch with CUDA events
+ * on the caller's stream.  dfd_engine_profile_read sums the last forward's durations per kernel family
+ * (ms4/count4 index: 0 GEMM, 1 attention, 2 LayerNorm, 3 other) and synchronises on the last event. */
+DFD_API int dfd_engine_profile(dfd_engine* e, int enable);
+DFD_API int dfd_engine_profile_read(dfd_engine* e, float* ms4, int* count4);
 
 #ifdef __cplusplus
 }
