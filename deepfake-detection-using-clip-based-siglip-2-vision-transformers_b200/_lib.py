@@ -99,6 +99,7 @@ SIGNATURES = {
     "dfd_layernorm_bf16": (_I, [_P, _L, _P, _L, _P, _P, _I, _I, _F, _P]),
     "dfd_rowstats_bf16": (_I, [_P, _L, _P, _I, _I, _P]),
     "dfd_attention_bf16": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _F, _P]),
+    "dfd_attention_bf16_impl": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _F, _I, _P]),
     "dfd_patchify": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
     "dfd_map_attention_bf16": (_I, [_P, _L, _P, _P, _L, _I, _I, _I, _I, _F, _P]),
     "dfd_head_fwd": (_I, [C.POINTER(HeadWeights), _P, _L, _I, _P, _P, _P, _P, _P]),

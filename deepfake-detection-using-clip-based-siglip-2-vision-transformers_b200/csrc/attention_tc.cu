@@ -1,0 +1,335 @@
+// Non-causal attention on the 5th-gen tensor cores (tcgen05 + TMEM), for the 196..1024-token SigLIP sequences.
+//
+// One CTA = 128 query rows of one (image, head); two CTAs share an SM (256 TMEM columns and ~101 KB smem each),
+// so one CTA's softmax overlaps the other's MMAs.
+//
+//   warp 0      TMA loader: Q once, then K/V tiles of 128 keys through a 2-stage mbarrier ring.  The operand is
+//               addressed through a 4-D tensor map (head-dim, head, token, image) so that (a) rows past the
+//               image's last token and (b) head-dim columns past hd (72 -> 80) are zero-filled by the TMA unit.
+//   warp 1      MMA issuer: S = Q·Kᵀ   (M=128, N<=128, K=64 via SWIZZLE_128B tiles + K=16 tail via SWIZZLE_32B tiles)
+//                           O += P·V   (A = P read from TMEM, B = V tile as an MN-major operand; N=64 + N=16 tail)
+//   warps 2..5  softmax: one thread per query row reads its S row from TMEM (no shuffles), keeps the running
+//               max/sum in fp32, writes P (bf16) back into the S columns, rescales O in TMEM only when the running
+//               max moved by more than 2^8 (exact: O and l always share the same reference max), and finally
+//               normalises and stores O.
+//
+// Reference semantics: HF:modeling_siglip.py:229-249,293-306 (softmax(q·kᵀ/sqrt(hd)) v, fp32 softmax, no mask).
+#include "dfd_common.cuh"
+
+#include <atomic>
+#include <mutex>
+
+namespace dfd {
+
+extern std::atomic<int64_t> g_launches;
+
+namespace {
+
+constexpr int kQ = 128;     // query rows per CTA
+constexpr int kKV = 128;    // keys per tile
+constexpr int kAttnThreads = 192;
+constexpr int kStagesKV = 2;
+constexpr int kTmemCols = 256;
+constexpr int kColS = 0;    // S: fp32 [128 x 128]; P (bf16 pairs) aliases columns 0..63
+constexpr int kColO = 128;  // O: fp32 [128 x 80]
+
+template <int HD>
+struct AttnSmem {
+  static constexpr bool kTail = (HD % 64) != 0;
+  static constexpr int kMainBytes = kQ * 64 * 2;              // 128 rows x 128 B, SWIZZLE_128B
+  static constexpr int kTailBytes = kTail ? kQ * 16 * 2 : 0;  // 128 rows x 32 B, SWIZZLE_32B
+  static constexpr int kTileBytes = kMainBytes + kTailBytes;
+  static constexpr int kBarBytes = 128;
+  static constexpr int kTotal = kTileBytes * (1 + 2 * kStagesKV) + kBarBytes + 1024;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_constant__ CUtensorMap tmTail,
+                    __nv_bfloat16* __restrict__ out, int64_t ldo, int N, int H, float scale_log2) {
+  using S = AttnSmem<HD>;
+  constexpr bool kTail = S::kTail;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + S::kTileBytes;                       // [stage]
+  uint8_t* sV = smem + S::kTileBytes * (1 + kStagesKV);     // [stage]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kTileBytes * (1 + 2 * kStagesKV));
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + kStagesKV;
+  uint64_t* s_full = kv_empty + kStagesKV;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_full = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = (N + kKV - 1) / kKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmMain);
+    if (kTail) tma_prefetch_desc(&tmTail);
+    mbar_init(q_full, 1);
+#pragma unroll
+    for (int s = 0; s < kStagesKV; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------ TMA loader ------------------------------------
+    if (lane == 0) {
+      mbar_expect_tx(q_full, S::kTileBytes);
+      tma_load_4d(&tmMain, q_full, sQ, 0, h, qt * kQ, b);
+      if (kTail) tma_load_4d(&tmTail, q_full, sQ + S::kMainBytes, 64, h, qt * kQ, b);
+      for (int j = 0; j < T; ++j) {
+        const int st = j % kStagesKV;
+        mbar_wait(&kv_empty[st], ((j / kStagesKV) & 1u) ^ 1u);
+        mbar_expect_tx(&kv_full[st], 2 * S::kTileBytes);
+        uint8_t* k = sK + st * S::kTileBytes;
+        uint8_t* v = sV + st * S::kTileBytes;
+        tma_load_4d(&tmMain, &kv_full[st], k, 0, H + h, j * kKV, b);
+        tma_load_4d(&tmMain, &kv_full[st], v, 0, 2 * H + h, j * kKV, b);
+        if (kTail) {
+          tma_load_4d(&tmTail, &kv_full[st], k + S::kMainBytes, 64, H + h, j * kKV, b);
+          tma_load_4d(&tmTail, &kv_full[st], v + S::kMainBytes, 64, 2 * H + h, j * kKV, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------ MMA issuer ------------------------------------
+    if (lane == 0) {
+      const uint32_t tS = tmem_base + kColS, tO = tmem_base + kColO;
+      const uint64_t dQ = umma_desc(smem_u32(sQ), 16, 1024, 2);
+      const uint64_t dQt = umma_desc(smem_u32(sQ + S::kMainBytes), 16, 256, 6);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < T; ++j) {
+        const int st = j % kStagesKV;
+        const int valid = min(kKV, N - j * kKV);
+        const int n16 = (valid + 15) & ~15;  // keys of this tile, rounded to the MMA N granule
+        mbar_wait(&kv_full[st], (j / kStagesKV) & 1u);
+        tc_fence_after();
+        // ---- S = Q · K^T ----
+        const uint32_t kaddr = smem_u32(sK + st * S::kTileBytes);
+        const uint64_t dK = umma_desc(kaddr, 16, 1024, 2);
+        const uint32_t idesc_qk = umma_idesc_bf16_major(kQ, n16, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tS, dQ + static_cast<uint64_t>(2 * k), dK + static_cast<uint64_t>(2 * k), idesc_qk, k != 0);
+        if (kTail) {
+          const uint64_t dKt = umma_desc(kaddr + S::kMainBytes, 16, 256, 6);
+          umma_bf16_ss(tS, dQt, dKt, idesc_qk, 1u);
+        }
+        umma_commit(s_full);
+        // ---- O += P · V ----  (P written by the softmax warps into the S columns)
+        mbar_wait(p_full, j & 1u);
+        tc_fence_after();
+        const uint32_t vaddr = smem_u32(sV + st * S::kTileBytes);
+        const uint64_t dV = umma_desc(vaddr, 16, 1024, 2);           // MN-major, 8-key groups 1024 B apart
+        const uint64_t dVt = umma_desc(vaddr + S::kMainBytes, 16, 256, 6);
+        constexpr uint32_t idesc_pv = umma_idesc_bf16_major(kQ, 64, 0, 1);
+        constexpr uint32_t idesc_pvt = umma_idesc_bf16_major(kQ, 16, 0, 1);
+        const int ksteps = n16 >> 4;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint32_t acc = (j | kk) != 0 ? 1u : 0u;
+          // 16 keys per step: 16 rows x 128 B (main) / 16 rows x 32 B (tail); P: 8 packed columns per step
+          umma_bf16_ts(tO, tS + static_cast<uint32_t>(8 * kk), dV + static_cast<uint64_t>(kk * 128), idesc_pv, acc);
+          if (kTail)
+            umma_bf16_ts(tO + 64, tS + static_cast<uint32_t>(8 * kk), dVt + static_cast<uint64_t>(kk * 32), idesc_pvt,
+                         acc);
+        }
+        umma_commit(&kv_empty[st]);  // K/V stage back to the loader once these MMAs retire
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // ------------------------------------ softmax / output ------------------------------------
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int grow = qt * kQ + row;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + kColS;
+    const uint32_t tO = tmem_base + lane_off + kColO;
+    constexpr int kOChunks = (HD + 15) / 16;  // 16-column chunks of O
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const int valid = min(kKV, N - j * kKV);
+      mbar_wait(s_full, j & 1u);
+      tc_fence_after();
+      uint32_t s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        tmem_ld_32x32b_x32(tS + static_cast<uint32_t>(32 * c), *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
+      tmem_ld_wait();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 128; ++c) {
+        float v = __uint_as_float(s[c]) * scale_log2;
+        if (c >= valid) v = -INFINITY;  // keys past the sequence end (zero-filled K rows)
+        s[c] = __float_as_uint(v);
+        mx = fmaxf(mx, v);
+      }
+      // lazy rescale: keep the old reference max unless the new one is more than 2^8 larger
+      const float m_new = (mx > m + 8.0f) ? mx : m;
+      const bool moved = m_new != m;
+      const float alpha = (j == 0) ? 0.f : fast_exp2(m - m_new);
+      if (j > 0 && __any_sync(0xffffffffu, moved)) {
+#pragma unroll
+        for (int c = 0; c < kOChunks; ++c) {
+          uint32_t o[16];
+          tmem_ld_32x32b_x16(tO + static_cast<uint32_t>(16 * c), o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32b_x16(tO + static_cast<uint32_t>(16 * c), o);
+        }
+      }
+      m = m_new;
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        const float p0 = fast_exp2(__uint_as_float(s[2 * c]) - m);
+        const float p1 = fast_exp2(__uint_as_float(s[2 * c + 1]) - m);
+        sum += p0 + p1;
+        s[c] = pack_bf16x2(p0, p1);  // in place: s[2c], s[2c+1] (indices >= c) are consumed first
+      }
+      l = l * alpha + sum;
+      tmem_st_32x32b_x32(tS, *reinterpret_cast<const uint32_t(*)[32]>(&s[0]));
+      tmem_st_32x32b_x32(tS + 32, *reinterpret_cast<const uint32_t(*)[32]>(&s[32]));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- O / l -> bf16 -> global ----
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    __nv_bfloat16* orow = out + ((int64_t)b * N + grow) * ldo + h * HD;
+#pragma unroll
+    for (int c = 0; c < kOChunks; ++c) {
+      uint32_t o[16];
+      tmem_ld_32x32b_x16(tO + static_cast<uint32_t>(16 * c), o);
+      tmem_ld_wait();
+      if (grow < N) {
+        uint4 lo, hi;
+        lo.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+        lo.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+        lo.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+        lo.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+        hi.x = pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+        hi.y = pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+        hi.z = pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+        hi.w = pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+        *reinterpret_cast<uint4*>(orow + 16 * c) = lo;
+        if (16 * c + 8 < HD) *reinterpret_cast<uint4*>(orow + 16 * c + 8) = hi;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// qkv [B*N, ld] viewed as (hd, 3H, N, B); box = box_cols x 1 x 128 x 1
+int make_tmap_qkv(CUtensorMap* out, const void* base, int hd, int heads3, int N, int B, int64_t ld, int box_cols,
+                  CUtensorMapSwizzle sw) {
+  PFN_encodeTiled fn = encode_fn();
+  DFD_REQUIRE(fn != nullptr, DFD_ERR_NO_DEVICE, "cuTensorMapEncodeTiled unavailable (no CUDA driver on this host)");
+  cuuint64_t gdim[4] = {(cuuint64_t)hd, (cuuint64_t)heads3, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)hd * 2, (cuuint64_t)ld * 2, (cuuint64_t)N * (cuuint64_t)ld * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_cols, 1, (cuuint32_t)kKV, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DFD_REQUIRE(r == CUDA_SUCCESS, DFD_ERR_CUDA, "cuTensorMapEncodeTiled(qkv 4-D) failed (%d)", (int)r);
+  return DFD_OK;
+}
+
+}  // namespace
+
+int attention_tc_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
+                      float scale, cudaStream_t st) {
+  DFD_REQUIRE(qkv && out, DFD_ERR_BAD_ARG, "attention: null pointer");
+  DFD_REQUIRE(B > 0 && N > 0 && H > 0, DFD_ERR_SHAPE, "attention: B, N, H must be positive");
+  DFD_REQUIRE(hd == 64 || hd == 72, DFD_ERR_UNSUPPORTED, "attention: head dim %d not supported (64, 72)", hd);
+  DFD_REQUIRE(ldqkv % 8 == 0 && ldqkv >= 3 * H * hd && ldo % 8 == 0 && ldo >= H * hd, DFD_ERR_SHAPE,
+              "attention: bad leading dimensions");
+  DFD_REQUIRE(B <= 65535 && H <= 65535, DFD_ERR_SHAPE, "attention: B and H must be <= 65535");
+  DFD_REQUIRE(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0), DFD_ERR_BAD_ARG,
+              "attention: pointers must be 16-byte aligned");
+  CUtensorMap tmMain, tmTail;
+  int rc = make_tmap_qkv(&tmMain, qkv, hd, 3 * H, N, B, ldqkv, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != DFD_OK) return rc;
+  tmTail = tmMain;
+  if (hd == 72) {
+    rc = make_tmap_qkv(&tmTail, qkv, hd, 3 * H, N, B, ldqkv, 16, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (rc != DFD_OK) return rc;
+  }
+  const float scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((N + kQ - 1) / kQ, H, B);
+  static bool attr[2] = {false, false};
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (hd == 64) {
+    if (!attr[0]) {
+      DFD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    AttnSmem<64>::kTotal));
+      attr[0] = true;
+    }
+    attention_tc_kernel<64><<<grid, kAttnThreads, AttnSmem<64>::kTotal, st>>>(tmMain, tmTail, o, ldo, N, H, scale_log2);
+  } else {
+    if (!attr[1]) {
+      DFD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    AttnSmem<72>::kTotal));
+      attr[1] = true;
+    }
+    attention_tc_kernel<72><<<grid, kAttnThreads, AttnSmem<72>::kTotal, st>>>(tmMain, tmTail, o, ldo, N, H, scale_log2);
+  }
+  DFD_LAUNCH_CHECK();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return DFD_OK;
+}
+
+}  // namespace dfd
+
+// Test / A-B hook: impl 0 = warp-level mma.sync kernel (attention.cu), 1 = tcgen05 kernel (this file).
+extern "C" DFD_API int dfd_attention_bf16_impl(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N,
+                                               int H, int hd, float scale, int impl, void* stream) {
+  if (impl == 1)
+    return dfd::attention_tc_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));
+  return dfd::attention_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -80,14 +80,22 @@ def rowstats_bf16(x: torch.Tensor) -> torch.Tensor:
     return st
 
 
-def attention_bf16(qkv: torch.Tensor, B: int, N: int, H: int, hd: int, scale: Optional[float] = None) -> torch.Tensor:
-    """qkv [B*N, 3*H*hd] (q | k | v) -> [B*N, H*hd]; non-causal softmax(q k^T scale) v."""
+def attention_bf16(qkv: torch.Tensor, B: int, N: int, H: int, hd: int, scale: Optional[float] = None,
+                   impl: Optional[int] = None) -> torch.Tensor:
+    """qkv [B*N, 3*H*hd] (q | k | v) -> [B*N, H*hd]; non-causal softmax(q k^T scale) v.
+    impl None = product path (tcgen05 kernel); 0 / 1 select the mma.sync / tcgen05 kernel (A/B tests)."""
     _need_cuda(qkv)
     assert qkv.dtype == torch.bfloat16 and qkv.shape == (B * N, 3 * H * hd) and qkv.stride(1) == 1
     out = torch.empty((B * N, H * hd), dtype=torch.bfloat16, device=qkv.device)
     scale = (1.0 / math.sqrt(hd)) if scale is None else scale
-    check(_lib.load().dfd_attention_bf16(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), B, N, H, hd,
-                                         scale, current_stream()))
+    lib = _lib.load()
+    if impl is None:
+        rc = lib.dfd_attention_bf16(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), B, N, H, hd, scale,
+                                    current_stream())
+    else:
+        rc = lib.dfd_attention_bf16_impl(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), B, N, H, hd,
+                                         scale, impl, current_stream())
+    check(rc)
     return out
 
 

@@ -97,6 +97,11 @@ DFD_API int dfd_rowstats_bf16(const void* x, int64_t ldx, float* stats, int M, i
 DFD_API int dfd_attention_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N,
                                int H, int hd, float scale, void* stream);
 
+/* Same, with the kernel chosen explicitly (A/B tests): impl 0 = warp-level mma.sync kernel, 1 = tcgen05/TMEM
+ * kernel (what dfd_attention_bf16 runs). */
+DFD_API int dfd_attention_bf16_impl(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N,
+                                    int H, int hd, float scale, int impl, void* stream);
+
 /* Fused preprocess + im2col: pixels -> bf16 patch matrix A[B·G·G, Kpad] with column order (c, ky, kx)
  * (= conv weight [D,3,P,P] flattened), value (u8/255 − 0.5)/0.5 (ToTensor + Normalize(.5,.5):
  * inference_ai_human_images.py:200-204; train_fusion_head_only.py:67-74), optional resize of the
