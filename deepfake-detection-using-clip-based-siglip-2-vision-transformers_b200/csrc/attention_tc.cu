@@ -1,12 +1,13 @@
 // Non-causal attention on the 5th-gen tensor cores (tcgen05 + TMEM), for the 196..1024-token SigLIP sequences.
 //
-// One CTA = 128 query rows of one (image, head); two CTAs share an SM (256 TMEM columns and ~101 KB smem each),
-// so one CTA's softmax overlaps the other's MMAs.
+// One CTA = 128 query rows of one (image, head); two CTAs share an SM (256 TMEM columns and ~101 KB smem each).
+// Keys are processed in tiles of 64; S is double buffered in TMEM so the MMA warp computes S_{j+1} (and S_{j+2})
+// while the softmax warps work on S_j.
 //
-//   warp 0      TMA loader: Q once, then K/V tiles of 128 keys through a 2-stage mbarrier ring.  The operand is
+//   warp 0      TMA loader: Q once, then K/V tiles of 64 keys through a 4-stage mbarrier ring.  The operand is
 //               addressed through a 4-D tensor map (head-dim, head, token, image) so that (a) rows past the
 //               image's last token and (b) head-dim columns past hd (72 -> 80) are zero-filled by the TMA unit.
-//   warp 1      MMA issuer: S = Q·Kᵀ   (M=128, N<=128, K=64 via SWIZZLE_128B tiles + K=16 tail via SWIZZLE_32B tiles)
+//   warp 1      MMA issuer: S = Q·Kᵀ   (M=128, N<=64, K=64 via SWIZZLE_128B tiles + K=16 tail via SWIZZLE_32B tiles)
 //                           O += P·V   (A = P read from TMEM, B = V tile as an MN-major operand; N=64 + N=16 tail)
 //   warps 2..5  softmax: one thread per query row reads its S row from TMEM (no shuffles), keeps the running
 //               max/sum in fp32, writes P (bf16) back into the S columns, rescales O in TMEM only when the running
@@ -26,21 +27,24 @@ extern std::atomic<int64_t> g_launches;
 namespace {
 
 constexpr int kQ = 128;     // query rows per CTA
-constexpr int kKV = 128;    // keys per tile
+constexpr int kKV = 64;     // keys per tile
 constexpr int kAttnThreads = 192;
-constexpr int kStagesKV = 2;
+constexpr int kStagesKV = 4;
 constexpr int kTmemCols = 256;
-constexpr int kColS = 0;    // S: fp32 [128 x 128]; P (bf16 pairs) aliases columns 0..63
+constexpr int kColS = 0;    // S: two fp32 [128 x 64] buffers at columns 0 and 64; P_j (bf16 pairs) aliases the
+                            // first 32 columns of S_j
 constexpr int kColO = 128;  // O: fp32 [128 x 80]
 
 template <int HD>
 struct AttnSmem {
   static constexpr bool kTail = (HD % 64) != 0;
-  static constexpr int kMainBytes = kQ * 64 * 2;              // 128 rows x 128 B, SWIZZLE_128B
-  static constexpr int kTailBytes = kTail ? kQ * 16 * 2 : 0;  // 128 rows x 32 B, SWIZZLE_32B
-  static constexpr int kTileBytes = kMainBytes + kTailBytes;
-  static constexpr int kBarBytes = 128;
-  static constexpr int kTotal = kTileBytes * (1 + 2 * kStagesKV) + kBarBytes + 1024;
+  static constexpr int kMainBytes = kKV * 64 * 2;              // 64 rows x 128 B, SWIZZLE_128B
+  static constexpr int kTailBytes = kTail ? kKV * 16 * 2 : 0;  // 64 rows x 32 B, SWIZZLE_32B
+  static constexpr int kQMain = 2 * kMainBytes, kQTail = 2 * kTailBytes;  // Q = two 64-row boxes per part
+  static constexpr int kQBytes = kQMain + kQTail;
+  static constexpr int kTileBytes = kMainBytes + kTailBytes;   // one K or V tile
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = kQBytes + 2 * kStagesKV * kTileBytes + kBarBytes + 1024;
 };
 
 template <int HD>
@@ -53,15 +57,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + S::kTileBytes;                       // [stage]
-  uint8_t* sV = smem + S::kTileBytes * (1 + kStagesKV);     // [stage]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kTileBytes * (1 + 2 * kStagesKV));
+  uint8_t* sK = smem + S::kQBytes;                                 // [stage]
+  uint8_t* sV = sK + kStagesKV * S::kTileBytes;                    // [stage]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStagesKV * S::kTileBytes);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = kv_full + kStagesKV;
-  uint64_t* s_full = kv_empty + kStagesKV;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* o_full = p_full + 1;
+  uint64_t* s_full = kv_empty + kStagesKV;   // [2]
+  uint64_t* p_full = s_full + 2;             // [2]
+  uint64_t* o_done = p_full + 2;             // phase k completes when P_k·V_k has retired
+  uint64_t* o_full = o_done + 1;             // completes once, when the last P·V has retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -77,8 +82,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 4);
+    }
+    mbar_init(o_done, 1);
     mbar_init(o_full, 1);
     mbar_fence_init();
   }
@@ -91,9 +100,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
   if (warp == 0) {
     // ------------------------------------ TMA loader ------------------------------------
     if (lane == 0) {
-      mbar_expect_tx(q_full, S::kTileBytes);
-      tma_load_4d(&tmMain, q_full, sQ, 0, h, qt * kQ, b);
-      if (kTail) tma_load_4d(&tmTail, q_full, sQ + S::kMainBytes, 64, h, qt * kQ, b);
+      mbar_expect_tx(q_full, S::kQBytes);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        tma_load_4d(&tmMain, q_full, sQ + i * S::kMainBytes, 0, h, qt * kQ + i * kKV, b);
+        if (kTail) tma_load_4d(&tmTail, q_full, sQ + S::kQMain + i * S::kTailBytes, 64, h, qt * kQ + i * kKV, b);
+      }
       for (int j = 0; j < T; ++j) {
         const int st = j % kStagesKV;
         mbar_wait(&kv_empty[st], ((j / kStagesKV) & 1u) ^ 1u);
@@ -111,17 +123,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
   } else if (warp == 1) {
     // ------------------------------------ MMA issuer ------------------------------------
     if (lane == 0) {
-      const uint32_t tS = tmem_base + kColS, tO = tmem_base + kColO;
+      const uint32_t tO = tmem_base + kColO;
       const uint64_t dQ = umma_desc(smem_u32(sQ), 16, 1024, 2);
-      const uint64_t dQt = umma_desc(smem_u32(sQ + S::kMainBytes), 16, 256, 6);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < T; ++j) {
+      const uint64_t dQt = umma_desc(smem_u32(sQ + S::kQMain), 16, 256, 6);
+      // S_j = Q · K_j^T into S buffer j&1 (runs one tile ahead of the softmax)
+      auto issue_qk = [&](int j) {
         const int st = j % kStagesKV;
-        const int valid = min(kKV, N - j * kKV);
-        const int n16 = (valid + 15) & ~15;  // keys of this tile, rounded to the MMA N granule
+        const int n16 = (min(kKV, N - j * kKV) + 15) & ~15;
         mbar_wait(&kv_full[st], (j / kStagesKV) & 1u);
         tc_fence_after();
-        // ---- S = Q · K^T ----
+        const uint32_t tS = tmem_base + kColS + static_cast<uint32_t>((j & 1) * kKV);
         const uint32_t kaddr = smem_u32(sK + st * S::kTileBytes);
         const uint64_t dK = umma_desc(kaddr, 16, 1024, 2);
         const uint32_t idesc_qk = umma_idesc_bf16_major(kQ, n16, 0, 0);
@@ -132,12 +143,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
           const uint64_t dKt = umma_desc(kaddr + S::kMainBytes, 16, 256, 6);
           umma_bf16_ss(tS, dQt, dKt, idesc_qk, 1u);
         }
-        umma_commit(s_full);
-        // ---- O += P · V ----  (P written by the softmax warps into the S columns)
-        mbar_wait(p_full, j & 1u);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      if (T > 1) issue_qk(1);
+      for (int j = 0; j < T; ++j) {
+        const int st = j % kStagesKV;
+        const int n16 = (min(kKV, N - j * kKV) + 15) & ~15;
+        // ---- O += P_j · V_j ----  (P_j written by the softmax warps into the S_j columns)
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1u);
         tc_fence_after();
+        const uint32_t tP = tmem_base + kColS + static_cast<uint32_t>((j & 1) * kKV);
         const uint32_t vaddr = smem_u32(sV + st * S::kTileBytes);
-        const uint64_t dV = umma_desc(vaddr, 16, 1024, 2);           // MN-major, 8-key groups 1024 B apart
+        const uint64_t dV = umma_desc(vaddr, 16, 1024, 2);  // MN-major, 8-key groups 1024 B apart
         const uint64_t dVt = umma_desc(vaddr + S::kMainBytes, 16, 256, 6);
         constexpr uint32_t idesc_pv = umma_idesc_bf16_major(kQ, 64, 0, 1);
         constexpr uint32_t idesc_pvt = umma_idesc_bf16_major(kQ, 16, 0, 1);
@@ -145,12 +164,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
         for (int kk = 0; kk < ksteps; ++kk) {
           const uint32_t acc = (j | kk) != 0 ? 1u : 0u;
           // 16 keys per step: 16 rows x 128 B (main) / 16 rows x 32 B (tail); P: 8 packed columns per step
-          umma_bf16_ts(tO, tS + static_cast<uint32_t>(8 * kk), dV + static_cast<uint64_t>(kk * 128), idesc_pv, acc);
+          umma_bf16_ts(tO, tP + static_cast<uint32_t>(8 * kk), dV + static_cast<uint64_t>(kk * 128), idesc_pv, acc);
           if (kTail)
-            umma_bf16_ts(tO + 64, tS + static_cast<uint32_t>(8 * kk), dVt + static_cast<uint64_t>(kk * 32), idesc_pvt,
+            umma_bf16_ts(tO + 64, tP + static_cast<uint32_t>(8 * kk), dVt + static_cast<uint64_t>(kk * 32), idesc_pvt,
                          acc);
         }
         umma_commit(&kv_empty[st]);  // K/V stage back to the loader once these MMAs retire
+        umma_commit(o_done);
+        // the tensor pipe executes in issue order, so S_{j&1} / P_j are free for tile j+2 right after P_j·V_j
+        if (j + 2 < T) issue_qk(j + 2);
       }
       umma_commit(o_full);
     }
@@ -160,32 +182,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
     const int row = quad * 32 + lane;
     const int grow = qt * kQ + row;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tS = tmem_base + lane_off + kColS;
     const uint32_t tO = tmem_base + lane_off + kColO;
     constexpr int kOChunks = (HD + 15) / 16;  // 16-column chunks of O
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f;             // m is kept in log2 units (already multiplied by scale_log2)
     for (int j = 0; j < T; ++j) {
       const int valid = min(kKV, N - j * kKV);
-      mbar_wait(s_full, j & 1u);
+      const uint32_t tS = tmem_base + lane_off + kColS + static_cast<uint32_t>((j & 1) * kKV);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1u);
       tc_fence_after();
-      uint32_t s[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        tmem_ld_32x32b_x32(tS + static_cast<uint32_t>(32 * c), *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
+      uint32_t s[64];
+      tmem_ld_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      tmem_ld_32x32b_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
       tmem_ld_wait();
+      if (valid < kKV) {  // last tile: keys past the sequence end (zero-filled K rows) never win
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (c >= valid) s[c] = __float_as_uint(-INFINITY);
+      }
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 128; ++c) {
-        float v = __uint_as_float(s[c]) * scale_log2;
-        if (c >= valid) v = -INFINITY;  // keys past the sequence end (zero-filled K rows)
-        s[c] = __float_as_uint(v);
-        mx = fmaxf(mx, v);
-      }
+      for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(s[c]));
+      mx *= scale_log2;  // scale > 0
       // lazy rescale: keep the old reference max unless the new one is more than 2^8 larger
       const float m_new = (mx > m + 8.0f) ? mx : m;
       const bool moved = m_new != m;
       const float alpha = (j == 0) ? 0.f : fast_exp2(m - m_new);
       if (j > 0 && __any_sync(0xffffffffu, moved)) {
+        mbar_wait(o_done, (j - 1) & 1u);  // P_{j-1}·V_{j-1} has retired: O is stable
+        tc_fence_after();
 #pragma unroll
         for (int c = 0; c < kOChunks; ++c) {
           uint32_t o[16];
@@ -197,23 +221,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
         }
       }
       m = m_new;
-      float sum = 0.f;
+      float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const float p0 = fast_exp2(__uint_as_float(s[2 * c]) - m);
-        const float p1 = fast_exp2(__uint_as_float(s[2 * c + 1]) - m);
-        sum += p0 + p1;
+      for (int c = 0; c < 32; ++c) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(s[2 * c]), scale_log2, -m));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), scale_log2, -m));
+        sum0 += p0;
+        sum1 += p1;
         s[c] = pack_bf16x2(p0, p1);  // in place: s[2c], s[2c+1] (indices >= c) are consumed first
       }
-      l = l * alpha + sum;
+      l = l * alpha + (sum0 + sum1);
       tmem_st_32x32b_x32(tS, *reinterpret_cast<const uint32_t(*)[32]>(&s[0]));
-      tmem_st_32x32b_x32(tS + 32, *reinterpret_cast<const uint32_t(*)[32]>(&s[32]));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
     }
     // ---- O / l -> bf16 -> global ----
+    // (o_done cannot be used here: with S running a tile ahead, its previous same-parity phase may already
+    //  satisfy the wait before the last two P·V products have retired)
     mbar_wait(o_full, 0);
     tc_fence_after();
     const float inv = 1.0f / l;
@@ -271,7 +297,7 @@ int make_tmap_qkv(CUtensorMap* out, const void* base, int hd, int heads3, int N,
   DFD_REQUIRE(fn != nullptr, DFD_ERR_NO_DEVICE, "cuTensorMapEncodeTiled unavailable (no CUDA driver on this host)");
   cuuint64_t gdim[4] = {(cuuint64_t)hd, (cuuint64_t)heads3, (cuuint64_t)N, (cuuint64_t)B};
   cuuint64_t gstr[3] = {(cuuint64_t)hd * 2, (cuuint64_t)ld * 2, (cuuint64_t)N * (cuuint64_t)ld * 2};
-  cuuint32_t box[4] = {(cuuint32_t)box_cols, 1, (cuuint32_t)kKV, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_cols, 1, (cuuint32_t)kKV, 1};  // 64 token rows per box
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
