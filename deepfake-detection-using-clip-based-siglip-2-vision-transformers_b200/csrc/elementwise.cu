@@ -216,15 +216,18 @@ int patchify(const void* pixels, int pix_format, int B, int Hin, int Win, int S,
   DFD_REQUIRE(resize_mode >= 0 && resize_mode <= 2, DFD_ERR_BAD_ARG, "patchify: resize_mode must be 0..2");
   DFD_REQUIRE(B > 0 && Hin > 0 && Win > 0 && S > 0 && P > 0 && P <= S, DFD_ERR_SHAPE,
               "patchify: bad shape");
-  DFD_REQUIRE(resize_mode != 0 || (Hin == S && Win == S), DFD_ERR_SHAPE,
-              "patchify: resize_mode 0 needs %dx%d input, got %dx%d", S, S, Hin, Win);
+  // mode 0 reads the top-left G*P x G*P pixels only (conv padding='valid'), so any input on the same patch grid
+  // is accepted: so400m-patch14 takes 378..391-pixel sides for its 27x27 grid.
+  const int GP = (S / P) * P;
+  DFD_REQUIRE(resize_mode != 0 || (Hin >= GP && Hin < GP + P && Win >= GP && Win < GP + P), DFD_ERR_SHAPE,
+              "patchify: resize_mode 0 needs %d..%d-pixel sides, got %dx%d", GP, GP + P - 1, Hin, Win);
   const int K = 3 * P * P;
   DFD_REQUIRE(lda % 8 == 0 && lda >= K, DFD_ERR_SHAPE, "patchify: lda must be a multiple of 8 and >= 3*P*P");
   PatchArgs a;
   a.pixels = pixels;
   a.fmt = pix_format;
   a.B = B; a.Hin = Hin; a.Win = Win; a.S = S; a.P = P; a.G = S / P; a.K = K;
-  a.mode = (Hin == S && Win == S) ? 0 : resize_mode;
+  a.mode = (Hin >= GP && Hin < GP + P && Win >= GP && Win < GP + P) ? 0 : resize_mode;
   a.sy = (float)Hin / (float)S;
   a.sx = (float)Win / (float)S;
   a.A = reinterpret_cast<__nv_bfloat16*>(A);

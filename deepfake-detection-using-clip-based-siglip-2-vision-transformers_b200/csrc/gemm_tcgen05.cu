@@ -22,7 +22,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int kEpiWarps = 8;                       // two groups of 4 warps (one warp per TMEM lane quadrant)
 constexpr int kGemmThreads = (3 + kEpiWarps) * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 residual TMA
-constexpr int kResSlots = 4;                        // residual chunks in flight (RES kernels only)
+constexpr int kResSlots = 2;                        // residual chunks in flight (RES kernels only)
 constexpr int kChunkN = 64;                         // epilogue / TMA-store granularity along N
 constexpr int kStageCBytes = BM * kChunkN * 2;      // 16 KB staging tile per epilogue group
 

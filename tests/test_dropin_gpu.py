@@ -1,0 +1,227 @@
+"""GPU tests of the reference-shaped Python surface (dfd.dropin, dfd.pipeline, dfd.train_fusion) against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _bc(head, name="tiny-hd64"):
+    from dfd import dropin
+    from oracle import siglip_ref as R
+
+    c = R.CONFIGS[name]
+    sd = R.init_state_dict(c, 0)
+    hs = R.init_head(head, c.hidden_size, 1)
+    m = dropin.BinaryClassifier(device=DEV, head=head, arch=name, max_batch=8)
+    ck = {"backbone.vision_model." + k: v for k, v in sd.items()}
+    ck.update(hs)
+    ck["backbone.text.whatever"] = torch.zeros(4)
+    m.load_state_dict(ck, strict=True)
+    return m, c, sd, hs
+
+
+@pytest.mark.parametrize("head,eps", [("A", 0.0), ("B", 1e-6)])
+def test_binary_classifier_forward(head, eps):
+    from oracle import siglip_ref as R
+
+    m, c, sd, hs = _bc(head)
+    assert m.resolution == c.image_size and set(m.classifier.state_dict()) >= {"0.weight", "2.weight", "5.weight"}
+    x = R.preprocess_u8(R.synthetic_images(5, c.image_size, 3))
+    z = m(x).cpu()
+    pooled = R.siglip_vision_forward(sd, c, x, "fp32")["pooler_output"]
+    z_ref = R.classifier_head(hs, head, pooled, eps)
+    assert (z - z_ref).abs().max() < 1e-2 * max(1.0, float(z_ref.abs().max())), (z, z_ref)
+    if head == "B":  # off-size input -> F.interpolate default (nearest) inside the model
+        xs = R.preprocess_u8(R.synthetic_images(3, 40, 4))
+        z2 = m(xs).cpu()
+        p2 = R.siglip_vision_forward(sd, c, R.resize_input(xs, c.image_size, "nearest"), "fp32")["pooler_output"]
+        assert (z2 - R.classifier_head(hs, "B", p2, 1e-6)).abs().max() < 2e-2
+
+
+def test_run_inference_and_prototypes():
+    from dfd import dropin
+    from oracle import siglip_ref as R
+
+    m, c, sd, hs = _bc("A")
+    imgs = R.preprocess_u8(R.synthetic_images(12, c.image_size, 5))
+    labels = torch.tensor([0, 1] * 6)
+    loader = [(imgs[i:i + 4], labels[i:i + 4], [f"f{j}.png" for j in range(i, i + 4)]) for i in range(0, 12, 4)]
+    lab, probs, files = dropin.run_inference(m, loader, torch.device(DEV))
+    pooled = R.siglip_vision_forward(sd, c, imgs, "fp32")["pooler_output"]
+    p_ref = torch.sigmoid(R.classifier_head(hs, "A", pooled, 0.0)).numpy()
+    assert lab.tolist() == labels.tolist() and files[5] == "f5.png"
+    assert np.abs(probs - p_ref).max() < 5e-3
+    _, pinv, _ = dropin.run_inference(m, loader, torch.device(DEV), invert_logits=True)
+    assert np.abs(pinv - (1 - p_ref)).max() < 5e-3
+    protos = dropin.few_shot_prototype(m, loader, torch.device(DEV))
+    f = R.l2_normalize(pooled)
+    pr = torch.stack([f[labels == 0].mean(0), f[labels == 1].mean(0)])
+    pr = pr / pr.norm(dim=-1, keepdim=True)
+    assert (protos["real"].cpu() - pr[0]).abs().max() < 5e-3 and (protos["fake"].cpu() - pr[1]).abs().max() < 5e-3
+    _, pp, _ = dropin.run_inference(m, loader, torch.device(DEV), prototypes=protos)
+    pp_ref = R.prototype_prob(f, protos["real"].cpu(), protos["fake"].cpu()).numpy()
+    assert np.abs(pp - pp_ref).max() < 5e-3
+
+
+def test_hf_shaped_vision_model():
+    from dfd import dropin
+    from oracle import siglip_ref as R
+
+    c = R.CONFIGS["tiny-hd72"]
+    sd = R.init_state_dict(c, 0)
+    m = dropin.SiglipVisionModel.from_state_dict({"vision_model." + k: v for k, v in sd.items()}, DEV, num_heads=2)
+    assert m.config.hidden_size == c.hidden_size
+    x = R.preprocess_u8(R.synthetic_images(2, c.image_size, 0))
+    o = m(pixel_values=x)
+    ref = R.siglip_vision_forward(sd, c, x, "fp32")
+    assert R.cosine_report(o.pooler_output.cpu(), ref["pooler_output"])["cos_min"] >= 0.999
+    assert o.last_hidden_state.shape == (2, c.tokens, c.hidden_size)
+    with pytest.raises(NotImplementedError):
+        m(pixel_values=x, output_hidden_states=True)
+
+
+def test_import_shims():
+    from dfd import dropin
+    from oracle import scoring_ref as S
+
+    dropin.install_import_shims()
+    import open_clip
+    import pywt
+
+    model, _, pre = open_clip.create_model_and_transforms("tiny-hd64", pretrained="webli", device=DEV)
+    assert model.embed_dim == 128 and callable(pre)
+    from PIL import Image
+
+    t = pre(Image.fromarray(np.zeros((50, 70, 3), np.uint8)))
+    assert t.shape == (3, 64, 64) and float(t.max()) == -1.0
+    x = np.random.default_rng(0).random((16, 16)).astype(np.float32)
+    cA, (cH, cV, cD) = pywt.dwt2(x, "db1")
+    for a, b in zip((cA, cH, cV, cD), S.haar2(x)):
+        assert np.array_equal(a, b)
+
+
+def test_detection_pipeline_host_buffers_vs_oracle():
+    """The public e2e call (pinned host buffers in, packed score records out) against the oracle stack."""
+    from dfd import pipeline, scoring
+    from oracle import scoring_ref as S
+    from oracle import siglip_ref as R
+
+    name = "tiny-hd72"
+    c = R.CONFIGS[name]
+    sd, hs = R.init_state_dict(c, 0), R.init_head("B", c.hidden_size, 1)
+    cuts = [-1.0, -0.2, 0.3, 1.5]
+    st = scoring.ScoringStack(DEV, S.init_freq_mlp_g2(2), S.init_fusion_g2(3), cuts, 1.1)
+    pipe = pipeline.DetectionPipeline(name, sd, hs, st, device=0, max_batch=4)
+    img = R.synthetic_images(6, c.image_size, 7)
+    gray = np.stack([S.gray256_from_rgb_u8(im.numpy(), True) for im in img])
+    rec = pipe.detect(img.pin_memory(), torch.from_numpy(gray).pin_memory())
+    assert rec.shape == (6, len(pipeline.PACKED_FIELDS))
+    col = {k: i for i, k in enumerate(pipeline.PACKED_FIELDS)}
+    pooled = R.siglip_vision_forward(sd, c, R.preprocess_u8(img), "fp32")["pooler_output"]
+    z_sig = R.classifier_head(hs, "B", pooled, 1e-6).numpy()
+    feats = np.stack([S.extract_freq_vector(g) for g in gray])
+    z_freq = S.freq_mlp_g2(S.init_freq_mlp_g2(2), feats)
+    z = S.fusion_g2(S.init_fusion_g2(3), z_freq, z_sig)
+    d = S.detect_scores(z, np.array(cuts, np.float32), 1.1)
+    # Logit gate.  BASELINE asks for 1e-2 at the named (768/1152-wide) architectures — checked in
+    # tests/test_engine_gpu.py::test_base_224_logits.  On this 144-wide toy model bf16 noise averages over 5-8x fewer
+    # channels: the reference's own bf16-autocast path is already up to 8e-3 from fp32 here, so the bound is 2e-2
+    # (max) with the median held at 5e-3.
+    pooled_ac = R.siglip_vision_forward(sd, c, R.preprocess_u8(img), "autocast")["pooler_output"]
+    z_sig_ac = R.classifier_head(hs, "B", pooled_ac, 1e-6).numpy()
+    for zr in (z_sig, z_sig_ac):
+        e = np.abs(rec[:, col["z_sig"]] - zr)
+        assert e.max() < 2e-2 and np.median(e) < 5e-3, e
+    assert np.abs(rec[:, col["z_freq"]] - z_freq).max() < 1e-3
+    assert np.abs(rec[:, col["z"]] - z).max() < 2e-2
+    assert np.abs(rec[:, col["p_blend"]] - d["p_blend"]).max() < 5e-3
+    tp = S.coral_transition_points(np.array(cuts, np.float32))
+    near = np.abs(d["z_scaled"][:, None] - tp[None]).min(1) < 1e-2
+    assert np.array_equal(rec[:, col["risk_idx"]].astype(int)[~near], d["risk_idx"][~near])
+
+
+def _reference_fit(z_freq, z_sig, labels, batch_size, epochs, seed):
+    """train_fusion_head_only.py:402-447 restated with torch autograd under enable_grad."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from torch.utils.data import DataLoader, TensorDataset
+
+    class Head(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.mlp = nn.Sequential(nn.Linear(3, 32), nn.GELU(), nn.Linear(32, 2))
+            self.T = nn.Parameter(torch.tensor(1.0))
+
+        def forward(self, zf, zs):
+            w = F.softmax(self.mlp(torch.stack([zf, zs, (zf - zs).abs()], -1)), -1)
+            return (w[..., 0] * zf + w[..., 1] * zs) / (self.T + 1e-6)
+
+    torch.manual_seed(seed)
+    h = Head()
+    loader = DataLoader(TensorDataset(torch.stack([z_freq, z_sig], 1), labels), batch_size=batch_size, shuffle=True)
+    opt = torch.optim.AdamW(h.parameters(), lr=5e-4)
+    with torch.enable_grad():
+        for _ in range(epochs):
+            for xb, yb in loader:
+                opt.zero_grad()
+                loss = nn.BCEWithLogitsLoss()(h(xb[:, 0], xb[:, 1]), yb)
+                loss.backward()
+                nn.utils.clip_grad_norm_(h.parameters(), max_norm=5.0)
+                opt.step()
+    return torch.cat([p.detach().reshape(-1) for p in (h.mlp[0].weight, h.mlp[0].bias, h.mlp[2].weight, h.mlp[2].bias, h.T)])
+
+
+def test_fit_fusion_head_matches_reference_loop():
+    from dfd import train_fusion
+
+    rng = np.random.default_rng(0)
+    n = 203  # ragged last mini-batch
+    y = torch.from_numpy((rng.random(n) > 0.5).astype(np.float32))
+    zs = torch.from_numpy((rng.normal(0, 2, n) + 2.0 * (y.numpy() - 0.5)).astype(np.float32))
+    zf = torch.from_numpy((rng.normal(0, 2, n) + 1.0 * (y.numpy() - 0.5)).astype(np.float32))
+    ref = _reference_fit(zf, zs, y, 32, 3, seed=11)
+    torch.manual_seed(11)
+    head, best, auc = train_fusion.fit_fusion_head(zf, zs, y, batch_size=32, epochs=3, device=DEV, verbose=False)
+    got = head.flat.data.cpu()
+    assert (got - ref).abs().max() < 2e-4, (got - ref).abs().max()
+    assert set(best) == {"mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias", "temp.T"}
+    assert tuple(best["mlp.0.weight"].shape) == (32, 3) and best["temp.T"].shape == ()
+    assert auc > 0.6
+
+
+def test_train_fusion_head_end_to_end(tmp_path):
+    """Entry point #2 on synthetic image folders: extraction -> training -> fusion_head.safetensors in the
+    reference layout, loadable by the G2 scoring stack."""
+    from PIL import Image
+    from safetensors.torch import load_file, save_file
+
+    from dfd import scoring, train_fusion
+    from oracle import scoring_ref as S
+    from oracle import siglip_ref as R
+
+    rng = np.random.default_rng(1)
+    for cls, shift in (("real", 0), ("fake", 60)):
+        os.makedirs(tmp_path / cls)
+        for i in range(6):
+            arr = np.clip(rng.normal(110 + shift, 40, (48 + 8 * i, 64, 3)), 0, 255).astype(np.uint8)
+            Image.fromarray(arr).save(tmp_path / cls / f"{i}.png")
+    c = R.CONFIGS["tiny-hd64"]
+    ck = {"backbone.vision_model." + k: v.contiguous() for k, v in R.init_state_dict(c, 0).items()}
+    ck.update({k: v.contiguous() for k, v in R.init_head("B", c.hidden_size, 1).items()})
+    save_file(ck, str(tmp_path / "best_model.safetensors"))
+    save_file({k: v.contiguous() for k, v in S.init_freq_mlp_g2(2).items()}, str(tmp_path / "freq_mlp.safetensors"))
+    out = tmp_path / "fusion_head.safetensors"
+    torch.manual_seed(0)
+    best = train_fusion.train_fusion_head(str(tmp_path / "real"), str(tmp_path / "fake"), str(tmp_path / "best_model.safetensors"),
+                                          str(tmp_path / "freq_mlp.safetensors"), str(out), batch_size=4, epochs=2,
+                                          device=DEV, arch="tiny-hd64")
+    sd = load_file(str(out))
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {"mlp.0.weight": (32, 3), "mlp.0.bias": (32,), "mlp.2.weight": (2, 32),
+                                                        "mlp.2.bias": (2,), "temp.T": ()}
+    assert all(torch.equal(sd[k], best[k]) for k in sd)
+    st = scoring.ScoringStack(DEV, load_file(str(tmp_path / "freq_mlp.safetensors")), sd, [-1.0, -0.2, 0.3, 1.5], 1.0)
+    assert st.gen == 2
