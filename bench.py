@@ -196,7 +196,7 @@ def run_ours(args):
     bsd = weights.random_vision_state_dict(arch, seed=0, device=dev)
     st = scoring.ScoringStack(dev, weights.random_freq_mlp_g2(2), weights.random_fusion_g2(3), [-1.0, -0.2, 0.3, 1.5], 1.0)
     pipe = pipeline.DetectionPipeline(arch, bsd, weights.random_classifier_head("B", arch.hidden_size, 1), st,
-                                      device=local, max_batch=min(B, args.max_batch))
+                                      device=local, max_batch=min(B, args.max_batch), fuse_ln=bool(args.fuse_ln))
     del bsd
     S = arch.image_size
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -286,7 +286,7 @@ def run_ours(args):
         "config": {"workload": f"{args.workload}: {arch_name} detect (backbone+H-B head+freq features+G2 fusion+CORAL)",
                    "per_gpu_batch": B, "global_batch": B * world, "tokens": arch.tokens, "parallelism": f"dp{world}",
                    "l2": "per-step inputs (u8 images + gray256) and activations are >> the 126 MB L2; no flush needed",
-                   "weights": "random init (seeded), bf16"},
+                   "weights": "random init (seeded), bf16", "fuse_ln": bool(args.fuse_ln)},
         "tensor_pipe_frac_of_step": arch.flops_per_image() * value / world / 1e12 / float(peaks["bf16_tflops_sustained"]),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -315,6 +315,7 @@ def main():
     ap.add_argument("--max-batch", type=int, default=512, help="engine workspace batch (larger batches are chunked)")
     ap.add_argument("--gemm-traffic", type=float, default=None,
                     help="dram bytes per GEMM launch from an ncu --set full capture (profiles/), else null")
+    ap.add_argument("--fuse-ln", type=int, default=0, help="1 = LayerNorm folded into the qkv/fc1 GEMMs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

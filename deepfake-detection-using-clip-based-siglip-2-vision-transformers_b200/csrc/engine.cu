@@ -52,10 +52,35 @@ __global__ void probe_query_kernel(const float* __restrict__ probe, const __nv_b
   if (lane == 0) q[j] = acc + bq[j];
 }
 
+// LayerNorm folded through a Linear (one warp per output row n), in place:
+//   W'[n,k] = bf16(W[n,k]·gamma[k]);  colsum[n] = sum_k W'[n,k];  bias[n] += sum_k W[n,k]·beta[k]
+// so that  Linear(LN(x)) = rstd·(x·W'^T − mean·colsum) + bias'   (the GEMM epilogue applies the right-hand side)
+__global__ void fold_ln_kernel(__nv_bfloat16* __restrict__ W, float* __restrict__ bias, float* __restrict__ colsum,
+                               const float* __restrict__ gamma, const float* __restrict__ beta, int N, int K) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float cs = 0.f, bs = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = __bfloat162float(W[(int64_t)n * K + k]);
+    const __nv_bfloat16 wf = __float2bfloat16(w * gamma[k]);
+    W[(int64_t)n * K + k] = wf;
+    cs += __bfloat162float(wf);
+    bs += w * beta[k];
+  }
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  if (lane == 0) {
+    colsum[n] = cs;
+    bias[n] += bs;
+  }
+}
+
 struct Layer {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   __nv_bfloat16 *w_qkv, *w_o, *w_fc1, *w_fc2;
   float *b_qkv, *b_o, *b_fc1, *b_fc2;
+  float *cs_qkv, *cs_fc1;  // column sums of the LN-folded weights (fuse_ln)
 };
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
@@ -83,6 +108,8 @@ struct dfd_engine {
   uint8_t* aslab;
   int64_t abytes;
   __nv_bfloat16 *patches, *x, *h, *qkv, *att, *mlp, *ao, *r, *h2, *m2;
+  float *stats_a, *stats_b;  // per-row (sum, sum of squares) of the residual stream (fuse_ln)
+  bool folded;
   void* staging;
   int64_t staging_bytes;
   // optional per-launch CUDA-event timing of the forward (bench.py roofline): family 0 GEMM, 1 attention,
@@ -121,6 +148,7 @@ void carve_weights(dfd_engine* e, uint8_t* base, int64_t* total) {
     l.w_o = c.take<__nv_bfloat16>(D * D); l.b_o = c.take<float>(D);
     l.w_fc1 = c.take<__nv_bfloat16>(I * D); l.b_fc1 = c.take<float>(I);
     l.w_fc2 = c.take<__nv_bfloat16>(D * I); l.b_fc2 = c.take<float>(D);
+    l.cs_qkv = c.take<float>(3 * D); l.cs_fc1 = c.take<float>(I);
   }
   e->post_g = c.take<float>(D); e->post_b = c.take<float>(D);
   e->probe = c.take<float>(D); e->q_probe = c.take<float>(D);
@@ -145,6 +173,8 @@ void carve_acts(dfd_engine* e, uint8_t* base, int64_t* total) {
   e->r = c.take<__nv_bfloat16>(B * D);
   e->h2 = c.take<__nv_bfloat16>(B * D);
   e->m2 = c.take<__nv_bfloat16>(B * I);
+  e->stats_a = c.take<float>(M * 2);
+  e->stats_b = c.take<float>(M * 2);
   *total = c.off;
 }
 
@@ -274,7 +304,7 @@ extern "C" DFD_API int dfd_engine_create(const dfd_config* cfg, int device, int 
   DFD_REQUIRE(cfg->hidden % 8 == 0 && cfg->inter % 8 == 0, DFD_ERR_SHAPE,
               "engine_create: hidden and inter must be multiples of 8");
   DFD_REQUIRE(cfg->gelu_tanh == 1, DFD_ERR_UNSUPPORTED, "engine_create: only gelu_pytorch_tanh backbones");
-  DFD_REQUIRE(cfg->fuse_ln == 0, DFD_ERR_UNIMPLEMENTED, "engine_create: fuse_ln=1 not implemented yet");
+  DFD_REQUIRE(cfg->fuse_ln == 0 || cfg->fuse_ln == 1, DFD_ERR_BAD_ARG, "engine_create: fuse_ln must be 0 or 1");
   int ndev = 0;
   DFD_CUDA(cudaGetDeviceCount(&ndev));
   DFD_REQUIRE(device >= 0 && device < ndev, DFD_ERR_NO_DEVICE, "engine_create: device %d of %d", device, ndev);
@@ -294,6 +324,7 @@ extern "C" DFD_API int dfd_engine_create(const dfd_config* cfg, int device, int 
   e->Kpe = 3 * e->P * e->P;
   e->Kpad = (int)align_up(e->Kpe, 64);
   e->finalized = false;
+  e->folded = false;
   e->wslab = e->aslab = nullptr;
   e->staging = nullptr;
   e->staging_bytes = 0;
@@ -364,6 +395,11 @@ extern "C" DFD_API int dfd_engine_set_tensor(dfd_engine* e, const char* name, co
   DFD_CUDA(cudaDeviceSynchronize());  // weight loading is not a hot path; keeps staging reuse simple
   mark_set(e, name);
   e->finalized = false;
+  if (e->folded) {  // weights were folded in place: a partial reload would mix folded and raw tensors
+    e->folded = false;
+    list_required(e);
+    mark_set(e, name);
+  }
   return DFD_OK;
 }
 
@@ -378,6 +414,14 @@ extern "C" DFD_API int dfd_engine_finalize(dfd_engine* e) {
   // the MAP query is batch independent: q = probe · W_qᵀ + b_q  (first D rows of in_proj)
   probe_query_kernel<<<(e->D + 7) / 8, 256>>>(e->probe, e->w_in, e->b_in, e->q_probe, e->D);
   DFD_LAUNCH_CHECK();
+  if (e->cfg.fuse_ln && !e->folded) {
+    for (auto& l : e->layers) {
+      fold_ln_kernel<<<(3 * e->D + 7) / 8, 256>>>(l.w_qkv, l.b_qkv, l.cs_qkv, l.ln1_g, l.ln1_b, 3 * e->D, e->D);
+      fold_ln_kernel<<<(e->I + 7) / 8, 256>>>(l.w_fc1, l.b_fc1, l.cs_fc1, l.ln2_g, l.ln2_b, e->I, e->D);
+    }
+    DFD_LAUNCH_CHECK();
+    e->folded = true;
+  }
   DFD_CUDA(cudaDeviceSynchronize());
   e->finalized = true;
   return DFD_OK;
@@ -446,17 +490,32 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
   e->prof_n = 0;
 
   DFD_OP(3, patchify(pixels, pix_format, B, Hin, Win, e->S, e->P, resize_mode, e->patches, e->Kpad, st));
+  const bool fuse = e->cfg.fuse_ln != 0;
+  const size_t stats_bytes = (size_t)M * 2 * sizeof(float);
   {
     dfd_gemm_epilogue ep{};
     ep.bias = e->b_pe;
     ep.pos = e->pos;
     ep.pos_rows = N;
+    if (fuse) {
+      DFD_CUDA(cudaMemsetAsync(e->stats_a, 0, stats_bytes, st));
+      ep.stats_out = e->stats_a;
+    }
     DFD_OP(0, gemm_bf16_dispatch(e->patches, e->Kpad, e->w_pe, e->Kpad, e->x, D, M, D, e->Kpad, &ep, 0, st));
   }
   for (int li = 0; li < e->L; ++li) {
     const Layer& l = e->layers[li];
-    DFD_OP(2, layernorm_bf16(e->x, D, e->h, D, l.ln1_g, l.ln1_b, M, D, eps, st));
-    {
+    if (fuse) {
+      // LN1 folded into the qkv GEMM: row statistics came from the GEMM that produced x
+      dfd_gemm_epilogue ep{};
+      ep.bias = l.b_qkv;
+      ep.ln_rowstats = e->stats_a;
+      ep.ln_colsum = l.cs_qkv;
+      ep.ln_dim = D;
+      ep.ln_eps = eps;
+      DFD_OP(0, gemm_bf16_dispatch(e->x, D, l.w_qkv, D, e->qkv, 3 * D, M, 3 * D, D, &ep, 0, st));
+    } else {
+      DFD_OP(2, layernorm_bf16(e->x, D, e->h, D, l.ln1_g, l.ln1_b, M, D, eps, st));
       dfd_gemm_epilogue ep{};
       ep.bias = l.b_qkv;
       DFD_OP(0, gemm_bf16_dispatch(e->h, D, l.w_qkv, D, e->qkv, 3 * D, M, 3 * D, D, &ep, 0, st));
@@ -467,10 +526,23 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
       ep.bias = l.b_o;
       ep.residual = e->x;
       ep.ldr = D;
+      if (fuse) {
+        DFD_CUDA(cudaMemsetAsync(e->stats_b, 0, stats_bytes, st));
+        ep.stats_out = e->stats_b;
+      }
       DFD_OP(0, gemm_bf16_dispatch(e->att, D, l.w_o, D, e->x, D, M, D, D, &ep, 0, st));
     }
-    DFD_OP(2, layernorm_bf16(e->x, D, e->h, D, l.ln2_g, l.ln2_b, M, D, eps, st));
-    {
+    if (fuse) {
+      dfd_gemm_epilogue ep{};
+      ep.bias = l.b_fc1;
+      ep.act = 1;
+      ep.ln_rowstats = e->stats_b;
+      ep.ln_colsum = l.cs_fc1;
+      ep.ln_dim = D;
+      ep.ln_eps = eps;
+      DFD_OP(0, gemm_bf16_dispatch(e->x, D, l.w_fc1, D, e->mlp, I, M, I, D, &ep, 0, st));
+    } else {
+      DFD_OP(2, layernorm_bf16(e->x, D, e->h, D, l.ln2_g, l.ln2_b, M, D, eps, st));
       dfd_gemm_epilogue ep{};
       ep.bias = l.b_fc1;
       ep.act = 1;
@@ -481,6 +553,10 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
       ep.bias = l.b_fc2;
       ep.residual = e->x;
       ep.ldr = D;
+      if (fuse && li + 1 < e->L) {  // statistics for the next layer's LN1 (the post-LN runs as a kernel)
+        DFD_CUDA(cudaMemsetAsync(e->stats_a, 0, stats_bytes, st));
+        ep.stats_out = e->stats_a;
+      }
       DFD_OP(0, gemm_bf16_dispatch(e->mlp, I, l.w_fc2, I, e->x, D, M, D, I, &ep, 0, st));
     }
   }

@@ -143,15 +143,18 @@ class SiglipEngine:
     """One engine per (device, architecture).  `forward` accepts uint8 NHWC images (preprocess fused into the
     im2col kernel) or float32 NCHW tensors that are already normalised, and returns bf16 pooled embeddings."""
 
-    def __init__(self, arch: VisionArch, device: int | torch.device = 0, max_batch: int = 64):
+    def __init__(self, arch: VisionArch, device: int | torch.device = 0, max_batch: int = 64, fuse_ln: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("SiglipEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.arch = arch
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         self.max_batch = int(max_batch)
+        # fuse_ln: LayerNorm1/2 folded into the qkv / fc1 GEMMs (row statistics accumulated by the GEMM that wrote
+        # the residual stream, with fp32 atomics — results then differ run to run in the last bf16 bit)
+        self.fuse_ln = bool(fuse_ln)
         self._lib = _lib.load()
         cfg = EngineConfig(arch.image_size, arch.patch_size, arch.hidden_size, arch.intermediate_size,
-                           arch.num_hidden_layers, arch.num_attention_heads, 1, arch.layer_norm_eps, 0)
+                           arch.num_hidden_layers, arch.num_attention_heads, 1, arch.layer_norm_eps, int(self.fuse_ln))
         h = C.c_void_p()
         check(self._lib.dfd_engine_create(C.byref(cfg), self.device.index or 0, self.max_batch, C.byref(h)))
         self._h = h

@@ -87,15 +87,15 @@ def attention(B, arch):
           f"({by / med / 1e6 / PEAKS['hbm_gbs'] * 100:4.1f}% of measured)", flush=True)
 
 
-def full(name, B, iters=3):
+def full(name, B, iters=3, fuse_ln=False):
     from oracle import siglip_ref as R
 
     arch = engine.ARCHS[name]
-    eng = engine.SiglipEngine(arch, 0, max_batch=B).load_state_dict(R.init_state_dict(R.CONFIGS[name], 0))
+    eng = engine.SiglipEngine(arch, 0, max_batch=B, fuse_ln=fuse_ln).load_state_dict(R.init_state_dict(R.CONFIGS[name], 0))
     img = torch.randint(0, 256, (B, arch.image_size, arch.image_size, 3), dtype=torch.uint8, device=DEV)
     med, best = timeit(lambda: eng(img), iters=iters, warm=2, flush=False)
     tf = arch.flops_per_image() * B / med / 1e9
-    print(f"engine {name} B={B}: {med:9.3f} ms  {B / med * 1e3:9.1f} img/s  {tf:7.1f} TF/s "
+    print(f"engine {name} B={B} fuse_ln={fuse_ln}: {med:9.3f} ms  {B / med * 1e3:9.1f} img/s  {tf:7.1f} TF/s "
           f"({tf / PEAKS['bf16_tflops_sustained'] * 100:4.1f}% of measured sustained) ws={eng.workspace_bytes / 2**30:.2f} GiB",
           flush=True)
     eng.close()
@@ -111,5 +111,6 @@ if __name__ == "__main__":
         attention(64, so)
         attention(256, ba)
     if "full" in what:
-        full("siglip2-base-patch16-224", 256)
-        full("siglip2-so400m-patch14-384", 128)
+        for f in (False, True):
+            full("siglip2-base-patch16-224", 256, fuse_ln=f)
+            full("siglip2-so400m-patch14-384", 128, fuse_ln=f)

@@ -12,12 +12,12 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _engine(name, max_batch):
+def _engine(name, max_batch, fuse_ln=False):
     from dfd import engine
     from oracle import siglip_ref as R
 
     sd = R.init_state_dict(R.CONFIGS[name], 0)
-    eng = engine.SiglipEngine(engine.ARCHS[name], 0, max_batch=max_batch).load_state_dict(sd)
+    eng = engine.SiglipEngine(engine.ARCHS[name], 0, max_batch=max_batch, fuse_ln=fuse_ln).load_state_dict(sd)
     return eng, sd
 
 
@@ -43,6 +43,33 @@ def test_small_configs_vs_oracle_and_golden(name, B, golden_backbone):
     assert rep["cos_min"] >= 0.998 and rep["rel_l2"] <= 0.03, rep
     gl = torch.from_numpy(golden_backbone[name + "/last_hidden_sub"])
     assert (last[:, ::7, ::5] - gl).abs().max() <= 0.03 * gl.abs().max() + 0.05
+
+
+@pytest.mark.parametrize("name,B", [("tiny-hd64", 3), ("small-hd72", 2), ("siglip2-base-patch16-224", 2)])
+def test_fused_layernorm_path(name, B, golden_backbone):
+    """fuse_ln=1: LayerNorm1/2 folded into the qkv / fc1 GEMMs (gamma into the weights, (x-mean)*rstd through the
+    epilogue, row statistics from the producing GEMM's epilogue).  Same gates as the unfused path; the two paths
+    agree with each other to bf16 noise."""
+    from oracle import siglip_ref as R
+
+    c = R.CONFIGS[name]
+    eng, sd = _engine(name, 4, fuse_ln=True)
+    ref_eng, _ = _engine(name, 4, fuse_ln=False)
+    img = R.synthetic_images(B, c.image_size, 0)
+    pooled, last = eng(img.to(DEV), want_last_hidden=True)
+    pooled0, _ = ref_eng(img.to(DEV))
+    torch.cuda.synchronize()
+    gold = torch.from_numpy(golden_backbone[name + "/pooled"])
+    rep = R.cosine_report(pooled.float().cpu(), gold)
+    assert rep["cos_min"] >= 0.999 and rep["cos_centered_min"] >= 0.995 and rep["rel_l2"] <= 0.04, rep
+    rep2 = R.cosine_report(pooled.float().cpu(), pooled0.float().cpu())
+    assert rep2["cos_min"] >= 0.9995 and rep2["rel_l2"] <= 0.03, rep2
+    gl = torch.from_numpy(golden_backbone[name + "/last_hidden_sub"])
+    assert (last.float().cpu()[:, ::7, ::5] - gl).abs().max() <= 0.04 * gl.abs().max() + 0.05
+    # reloading weights into an engine whose tensors were folded in place must start from a full state dict
+    eng.load_state_dict(sd)
+    p2, _ = eng(img.to(DEV))
+    assert R.cosine_report(p2.float().cpu(), pooled.float().cpu())["cos_min"] >= 0.9999
 
 
 def test_f32_nchw_input_equals_u8_path():
