@@ -315,7 +315,7 @@ def main():
     ap.add_argument("--max-batch", type=int, default=512, help="engine workspace batch (larger batches are chunked)")
     ap.add_argument("--gemm-traffic", type=float, default=None,
                     help="dram bytes per GEMM launch from an ncu --set full capture (profiles/), else null")
-    ap.add_argument("--fuse-ln", type=int, default=0, help="1 = LayerNorm folded into the qkv/fc1 GEMMs")
+    ap.add_argument("--fuse-ln", type=int, default=1, help="1 = LayerNorm folded into the qkv/fc1 GEMMs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -199,9 +199,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
         for (int c = 0; c < 64; ++c)
           if (c >= valid) s[c] = __float_as_uint(-INFINITY);
       }
-      float mx = -INFINITY;
+      // 8 independent chains (a single running max would be a 64-deep dependent chain)
+      float mx8[8];
 #pragma unroll
-      for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(s[c]));
+      for (int c = 0; c < 8; ++c) mx8[c] = __uint_as_float(s[c]);
+#pragma unroll
+      for (int c = 8; c < 64; ++c) mx8[c & 7] = fmaxf(mx8[c & 7], __uint_as_float(s[c]));
+      float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                       fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
       mx *= scale_log2;  // scale > 0
       // lazy rescale: keep the old reference max unless the new one is more than 2^8 larger
       const float m_new = (mx > m + 8.0f) ? mx : m;
@@ -221,16 +226,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
         }
       }
       m = m_new;
-      float sum0 = 0.f, sum1 = 0.f;
+      float sum8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const float neg_m = -m;
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(s[2 * c]), scale_log2, -m));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), scale_log2, -m));
-        sum0 += p0;
-        sum1 += p1;
+        const float p0 = fast_exp2(fmaf(__uint_as_float(s[2 * c]), scale_log2, neg_m));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), scale_log2, neg_m));
+        sum8[(2 * c) & 7] += p0;
+        sum8[(2 * c + 1) & 7] += p1;
         s[c] = pack_bf16x2(p0, p1);  // in place: s[2c], s[2c+1] (indices >= c) are consumed first
       }
-      l = l * alpha + (sum0 + sum1);
+      l = l * alpha + (((sum8[0] + sum8[1]) + (sum8[2] + sum8[3])) + ((sum8[4] + sum8[5]) + (sum8[6] + sum8[7])));
       tmem_st_32x32b_x32(tS, *reinterpret_cast<const uint32_t(*)[32]>(&s[0]));
       tmem_st_wait();
       tc_fence_before();
