@@ -36,6 +36,10 @@ class GemmEpilogue(C.Structure):
     ]
 
 
+class DenseLayer(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("out_dim", C.c_int), ("in_dim", C.c_int), ("act", C.c_int)]
+
+
 class HeadWeights(C.Structure):
     _fields_ = [
         ("kind", C.c_int),
@@ -44,9 +48,8 @@ class HeadWeights(C.Structure):
         ("ln_eps", C.c_float),
         ("se_w1", C.c_void_p), ("se_b1", C.c_void_p), ("se_w2", C.c_void_p), ("se_b2", C.c_void_p),
         ("ln_g", C.c_void_p), ("ln_b", C.c_void_p),
-        ("w1", C.c_void_p), ("b1", C.c_void_p),
-        ("w2", C.c_void_p), ("b2", C.c_void_p),
-        ("w3", C.c_void_p), ("b3", C.c_void_p),
+        ("n_layers", C.c_int),
+        ("layers", DenseLayer * 6),
     ]
 
 
@@ -113,6 +116,7 @@ SIGNATURES = {
     "dfd_engine_finalize": (_I, [_P]),
     "dfd_engine_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "dfd_engine_workspace_bytes": (_L, [_P]),
+    "dfd_engine_set_hidden_tap": (_I, [_P, _P]),
     "dfd_engine_profile": (_I, [_P, _I]),
     "dfd_engine_profile_read": (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
 }

@@ -110,6 +110,7 @@ struct dfd_engine {
   __nv_bfloat16 *patches, *x, *h, *qkv, *att, *mlp, *ao, *r, *h2, *m2;
   float *stats_a, *stats_b;  // per-row (sum, sum of squares) of the residual stream (fuse_ln)
   bool folded;
+  void* hidden_tap;          // optional [L+1, B, N, D] bf16 destination of the per-layer hidden states
   void* staging;
   int64_t staging_bytes;
   // optional per-launch CUDA-event timing of the forward (bench.py roofline): family 0 GEMM, 1 attention,
@@ -325,6 +326,7 @@ extern "C" DFD_API int dfd_engine_create(const dfd_config* cfg, int device, int 
   e->Kpad = (int)align_up(e->Kpe, 64);
   e->finalized = false;
   e->folded = false;
+  e->hidden_tap = nullptr;
   e->wslab = e->aslab = nullptr;
   e->staging = nullptr;
   e->staging_bytes = 0;
@@ -445,6 +447,14 @@ extern "C" DFD_API int dfd_engine_finalize(dfd_engine* e) {
     }                                                                                       \
   } while (0)
 
+// hidden_states tap (Siglip2sidafrozen.py:787-793: output_hidden_states=True): when set, the next forwards copy the
+// embedding output and every encoder layer's output into buf[(l) * B * N * D ...] (bf16, B = that forward's batch).
+extern "C" DFD_API int dfd_engine_set_hidden_tap(dfd_engine* e, void* buf) {
+  DFD_REQUIRE(e, DFD_ERR_BAD_ARG, "set_hidden_tap: null engine");
+  e->hidden_tap = buf;
+  return DFD_OK;
+}
+
 extern "C" DFD_API int dfd_engine_profile(dfd_engine* e, int enable) {
   DFD_REQUIRE(e, DFD_ERR_BAD_ARG, "profile: null engine");
   DeviceGuard guard(e->device);
@@ -503,6 +513,8 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
     }
     DFD_OP(0, gemm_bf16_dispatch(e->patches, e->Kpad, e->w_pe, e->Kpad, e->x, D, M, D, e->Kpad, &ep, 0, st));
   }
+  const size_t hid_bytes = (size_t)M * D * sizeof(__nv_bfloat16);
+  if (e->hidden_tap) DFD_CUDA(cudaMemcpyAsync(e->hidden_tap, e->x, hid_bytes, cudaMemcpyDeviceToDevice, st));
   for (int li = 0; li < e->L; ++li) {
     const Layer& l = e->layers[li];
     if (fuse) {
@@ -559,6 +571,9 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
       }
       DFD_OP(0, gemm_bf16_dispatch(e->mlp, I, l.w_fc2, I, e->x, D, M, D, I, &ep, 0, st));
     }
+    if (e->hidden_tap)
+      DFD_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(e->hidden_tap) + (size_t)(li + 1) * hid_bytes, e->x, hid_bytes,
+                               cudaMemcpyDeviceToDevice, st));
   }
   __nv_bfloat16* xp = last_hidden ? reinterpret_cast<__nv_bfloat16*>(last_hidden) : e->h;
   DFD_OP(2, layernorm_bf16(e->x, D, xp, D, e->post_g, e->post_b, M, D, eps, st));

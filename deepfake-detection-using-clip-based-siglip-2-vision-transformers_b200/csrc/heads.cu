@@ -145,20 +145,16 @@ head_fwd_kernel(dfd_head_weights w, const __nv_bfloat16* __restrict__ pooled, in
       a[s * D + k] = (x[s * D + k] - mean) * rstd * __ldg(w.ln_g + k) + __ldg(w.ln_b + k);
   }
   __syncthreads();
-  float* h1 = (x == c) ? f : c;  // free buffer
-  dense_rows(w.w1, w.b1, a, D, h1, D, D / 2, D, 2);
-  __syncthreads();
-  if (w.kind == 1) {
-    dense_rows(w.w2, w.b2, h1, D, a, D, 1, D / 2, 0);
-  } else {
-    dense_rows(w.w2, w.b2, h1, D, a, D, D / 4, D / 2, 2);
+  // dense chain, ping-ponging between `a` and the buffer that is free (f or c)
+  float* cur = a;
+  float* nxt = (x == c) ? f : c;
+  for (int li = 0; li < w.n_layers; ++li) {
+    const dfd_dense_layer& L = w.layers[li];
+    dense_rows(L.w, L.b, cur, D, nxt, D, L.out_dim, L.in_dim, L.act);
     __syncthreads();
-    dense_rows(w.w3, w.b3, a, D, h1, D, 1, D / 4, 0);
-    __syncthreads();
-    if (threadIdx.x < kHeadS) a[threadIdx.x * D] = h1[threadIdx.x * D];
+    float* t = cur; cur = nxt; nxt = t;
   }
-  __syncthreads();
-  if (threadIdx.x < kHeadS && b0 + threadIdx.x < B) z_sig[b0 + threadIdx.x] = a[threadIdx.x * D];
+  if (threadIdx.x < kHeadS && b0 + threadIdx.x < B) z_sig[b0 + threadIdx.x] = cur[threadIdx.x * D];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -398,10 +394,20 @@ int head_fwd(const dfd_head_weights* w, const void* pooled, int64_t ldp, int B, 
               "head_fwd: bad shape (B=%d dim=%d ldp=%lld)", B, w->dim, (long long)ldp);
   DFD_REQUIRE(w->kind >= 0 && w->kind <= 2, DFD_ERR_BAD_ARG, "head_fwd: kind must be 0, 1 or 2");
   if (w->kind != 0 && z_sig != nullptr) {
-    DFD_REQUIRE(w->ln_g && w->ln_b && w->w1 && w->b1 && w->w2 && w->b2, DFD_ERR_BAD_ARG,
-                "head_fwd: classifier weights missing");
-    DFD_REQUIRE(w->kind != 2 || (w->se_w1 && w->se_b1 && w->se_w2 && w->se_b2 && w->w3 && w->b3),
-                DFD_ERR_BAD_ARG, "head_fwd: SE / third-layer weights missing for kind 2");
+    DFD_REQUIRE(w->ln_g && w->ln_b, DFD_ERR_BAD_ARG, "head_fwd: LayerNorm weights missing");
+    DFD_REQUIRE(w->n_layers >= 1 && w->n_layers <= 6, DFD_ERR_BAD_ARG, "head_fwd: n_layers must be 1..6");
+    int in_dim = w->dim;
+    for (int i = 0; i < w->n_layers; ++i) {
+      const dfd_dense_layer& L = w->layers[i];
+      DFD_REQUIRE(L.w != nullptr && L.in_dim == in_dim && L.out_dim >= 1 && L.out_dim <= w->dim && L.act >= 0 &&
+                      L.act <= 3,
+                  DFD_ERR_SHAPE, "head_fwd: layer %d is inconsistent (in %d, expected %d, out %d)", i, L.in_dim, in_dim,
+                  L.out_dim);
+      in_dim = L.out_dim;
+    }
+    DFD_REQUIRE(in_dim == 1, DFD_ERR_SHAPE, "head_fwd: the last layer must have out_dim 1");
+    DFD_REQUIRE(w->kind != 2 || (w->se_w1 && w->se_b1 && w->se_w2 && w->se_b2), DFD_ERR_BAD_ARG,
+                "head_fwd: SE weights missing for kind 2");
   }
   const int smem = 3 * kHeadS * w->dim * (int)sizeof(float);
   DFD_REQUIRE(smem <= 200 * 1024, DFD_ERR_UNSUPPORTED, "head_fwd: dim %d too large", w->dim);

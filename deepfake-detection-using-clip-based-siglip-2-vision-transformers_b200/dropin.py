@@ -226,6 +226,43 @@ class BinaryClassifier:
         return ops.head_fwd(self._head(), self._pooled(x), want_features=True)[0]
 
 
+class FastBinaryClassifier(BinaryClassifier):
+    """cifake_binary_classifier.py:597-749 (BASELINE config 4): bilinear align_corners=False resize inside the model
+    (32x32 CiFake images -> S), f/||f|| -> LayerNorm -> one-token attention -> size-dependent classifier (head H-D).
+    State-dict keys follow the reference: layer_norm.*, attention.*, classifier.*."""
+
+    CONFIGS = {"tiny": "ViT-B-16-SigLIP-256", "small": "ViT-B-16-SigLIP-384", "medium": "ViT-L-16-SigLIP-384",
+               "large": "ViT-SO400M-16-SigLIP2-512"}
+
+    def __init__(self, model_size: str = "small", device="cuda", arch: Optional[str] = None, max_batch: int = 64,
+                 backbone_state: Optional[dict] = None, head_state: Optional[dict] = None, **_):
+        name = arch or self.CONFIGS[model_size]
+        self.model_size = model_size
+        self.device = _as_device(device)
+        self.backbone, _, self.preprocess = create_model_and_transforms(name, None, self.device, max_batch, backbone_state)
+        self.arch = self.backbone.arch
+        self.resolution = self.arch.image_size
+        self.feature_dim = self.arch.hidden_size
+        self.head_kind = "D"
+        self.backbone.resize_mode = ops.RESIZE_BILINEAR
+        self._head_state = {k: v.detach().float().cpu().clone() for k, v in (head_state or {}).items()}
+        self._params = None
+
+    def load_state_dict(self, sd: dict, strict: bool = True):
+        sd = {k[len("_orig_mod."):] if k.startswith("_orig_mod.") else k: v for k, v in sd.items()}
+        head = {k: v.detach().float().cpu().clone() for k, v in sd.items()
+                if k.startswith(("layer_norm.", "attention.", "classifier."))}
+        if head:
+            self._head_state = head
+        bb = {k: v for k, v in sd.items() if k.startswith("backbone.") and not k.startswith("backbone.text.")}
+        if bb:
+            self.backbone.load_state_dict(bb)
+        if strict and (not head or not bb):
+            raise RuntimeError("missing keys: " + ("head " if not head else "") + ("backbone.*" if not bb else ""))
+        self._params = None
+        return types.SimpleNamespace(missing_keys=[], unexpected_keys=[])
+
+
 @torch.no_grad()
 def run_inference(model: BinaryClassifier, dataloader, device=None, use_amp: bool = True, desc: str = "Inference",
                   invert_logits: bool = False, prototypes: Optional[dict] = None):
@@ -269,8 +306,8 @@ def few_shot_prototype(model: BinaryClassifier, support_loader, device=None, use
 
 class SiglipVisionModel:
     """HF-shaped wrapper: `SiglipVisionModel.from_state_dict(sd)(pixel_values=x)` -> .pooler_output [B,D] f32,
-    .last_hidden_state [B,N,D] (Siglip2sidafrozen.py:753,787-793).  Per-layer `hidden_states` taps are a listed
-    'next' row and raise NotImplementedError."""
+    .last_hidden_state [B,N,D], and with output_hidden_states=True the tuple of L+1 per-layer states
+    (Siglip2sidafrozen.py:753,787-793)."""
 
     def __init__(self, arch: VisionArch, state_dict: dict, device="cuda", max_batch: int = 32):
         self.arch = arch
@@ -293,13 +330,16 @@ class SiglipVisionModel:
 
     def __call__(self, pixel_values: torch.Tensor, output_hidden_states: bool = False,
                  interpolate_pos_encoding: bool = False, **_):
-        if output_hidden_states:
-            raise NotImplementedError("per-layer hidden_states taps are not built yet (SURVEY.md §8f.4)")
         gp, P = self.arch.grid * self.arch.patch_size, self.arch.patch_size
         if not all(gp <= s < gp + P for s in pixel_values.shape[-2:]):
             raise ValueError(f"pixel_values sides must be in [{gp}, {gp + P}) (position-embedding interpolation "
                              "for other grids is not built)")
-        pooled, last = self.engine(pixel_values.to(self.device).float(), want_last_hidden=True)
+        x = pixel_values.to(self.device).float()
+        if output_hidden_states:  # tuple of L+1 tensors, as SigLIP2_MTL consumes them (Siglip2sidafrozen.py:790-793)
+            pooled, last, hid = self.engine.forward_hidden(x)
+            return types.SimpleNamespace(pooler_output=pooled.float(), last_hidden_state=last.float(),
+                                         hidden_states=tuple(h.float() for h in hid))
+        pooled, last = self.engine(x, want_last_hidden=True)
         return types.SimpleNamespace(pooler_output=pooled.float(), last_hidden_state=last.float(), hidden_states=None)
 
 

@@ -195,6 +195,22 @@ class SiglipEngine:
         self._finalized = True
         return self
 
+    def forward_hidden(self, pixels: torch.Tensor, resize_mode: int = 0):
+        """Like forward(), plus the L+1 per-layer hidden states (HF `output_hidden_states=True`):
+        returns (pooled [B,D], last_hidden [B,N,D], hidden [L+1,B,N,D]) in bf16.  B <= max_batch."""
+        B = pixels.shape[0]
+        if B > self.max_batch:
+            raise ValueError("forward_hidden: batch must fit the engine workspace (max_batch)")
+        a = self.arch
+        hidden = torch.empty((a.num_hidden_layers + 1, B, a.tokens, a.hidden_size), dtype=torch.bfloat16,
+                             device=self.device)
+        check(self._lib.dfd_engine_set_hidden_tap(self._h, hidden.data_ptr()))
+        try:
+            pooled, last = self.forward(pixels, resize_mode, want_last_hidden=True)
+        finally:
+            check(self._lib.dfd_engine_set_hidden_tap(self._h, None))
+        return pooled, last, hidden
+
     def forward(self, pixels: torch.Tensor, resize_mode: int = 0, want_last_hidden: bool = False):
         """pixels: uint8 [B,H,W,3] or float32 [B,3,H,W] on this engine's device.  Batches larger than
         max_batch are processed in chunks.  Returns (pooled bf16 [B,D], last_hidden bf16 [B,N,D] | None)."""

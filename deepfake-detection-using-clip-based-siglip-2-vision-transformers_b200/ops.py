@@ -138,16 +138,36 @@ def _f32(t, dev):
     return t.detach().to(device=dev, dtype=torch.float32).contiguous()
 
 
-class HeadParams:
-    """Device copy of a classifier head (H-A: kind 1, H-B: kind 2, none: kind 0) for dfd_head_fwd."""
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3
 
-    def __init__(self, kind: int, dim: int, norm_eps: float, tensors: dict, device, ln_eps: float = 1e-5):
+
+class HeadParams:
+    """Device copy of a classifier head for dfd_head_fwd.
+    kind 0: L2-normalise only; 1: LN -> dense chain; 2: SE gate -> LN -> dense chain.
+    `layers` = [(weight [out,in], bias [out] | None, act), ...]; the last layer must have one output."""
+
+    def __init__(self, kind: int, dim: int, norm_eps: float, device, ln=None, se=None, layers=(), ln_eps: float = 1e-5):
         self.kind, self.dim = kind, dim
-        self._keep = {k: _f32(v, device) for k, v in tensors.items()}
+        self._keep = []
         w = HeadWeights()
         w.kind, w.dim, w.norm_eps, w.ln_eps = kind, dim, norm_eps, ln_eps
-        for k, v in self._keep.items():
-            setattr(w, k, v.data_ptr())
+
+        def put(t):
+            if t is None:
+                return None
+            d = _f32(t, device)
+            self._keep.append(d)
+            return d.data_ptr()
+
+        if ln is not None:
+            w.ln_g, w.ln_b = put(ln[0]), put(ln[1])
+        if se is not None:
+            w.se_w1, w.se_b1, w.se_w2, w.se_b2 = (put(t) for t in se)
+        assert len(layers) <= 6
+        w.n_layers = len(layers)
+        for i, (wt, bs, act) in enumerate(layers):
+            w.layers[i].w, w.layers[i].b = put(wt), put(bs)
+            w.layers[i].out_dim, w.layers[i].in_dim, w.layers[i].act = int(wt.shape[0]), int(wt.shape[1]), int(act)
         self.struct = w
 
 

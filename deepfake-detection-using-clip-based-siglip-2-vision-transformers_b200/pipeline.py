@@ -24,15 +24,32 @@ PACKED_FIELDS = ("z_sig", "z_freq", "z", "z_scaled", "p_raw", "p_coral", "entrop
 
 
 def head_params_from_state(sd: Dict[str, torch.Tensor], dim: int, device) -> "ops.HeadParams":
-    """`BinaryClassifier` heads: H-A keys classifier.{0,2,5} (inference_ai_human_images.py:131-138,
-    no eps on the norm) or H-B keys se.{0,2} + classifier.{0,2,5,7} (train_fusion_head_only.py:84-99, +1e-6)."""
-    t = {"ln_g": sd["classifier.0.weight"], "ln_b": sd["classifier.0.bias"], "w1": sd["classifier.2.weight"],
-         "b1": sd["classifier.2.bias"], "w2": sd["classifier.5.weight"], "b2": sd["classifier.5.bias"]}
+    """`BinaryClassifier` / `FastBinaryClassifier` heads, recognised by their key names:
+      H-A  classifier.{0,2,5}                 inference_ai_human_images.py:131-138 (no eps on the L2 norm)
+      H-B  se.{0,2} + classifier.{0,2,5,7}    train_fusion_head_only.py:84-99 (norm + 1e-6)
+      H-D  layer_norm + [attention.*] + classifier.{0,3[,6]} or {1}   cifake_binary_classifier.py:643-684,728-749
+           (attention over ONE token is exactly proj(v(x)): softmax of a single score is 1)"""
+    G, N = ops.ACT_GELU, ops.ACT_NONE
+    if "layer_norm.weight" in sd:  # H-D
+        layers = []
+        if "attention.qkv.weight" in sd:        # LightweightAttention: rows [2D,3D) of the fused qkv are v
+            layers += [(sd["attention.qkv.weight"][2 * dim:], sd["attention.qkv.bias"][2 * dim:], N),
+                       (sd["attention.proj.weight"], sd["attention.proj.bias"], N)]
+        elif "attention.in_proj_weight" in sd:  # nn.MultiheadAttention
+            layers += [(sd["attention.in_proj_weight"][2 * dim:], sd["attention.in_proj_bias"][2 * dim:], N),
+                       (sd["attention.out_proj.weight"], sd["attention.out_proj.bias"], N)]
+        idx = sorted(int(k.split(".")[1]) for k in sd if k.startswith("classifier.") and k.endswith(".weight"))
+        for n, i in enumerate(idx):
+            layers.append((sd[f"classifier.{i}.weight"], sd[f"classifier.{i}.bias"], G if n + 1 < len(idx) else N))
+        return ops.HeadParams(1, dim, 0.0, device, ln=(sd["layer_norm.weight"], sd["layer_norm.bias"]), layers=layers)
+    ln = (sd["classifier.0.weight"], sd["classifier.0.bias"])
     if "se.0.weight" in sd:
-        t.update({"se_w1": sd["se.0.weight"], "se_b1": sd["se.0.bias"], "se_w2": sd["se.2.weight"],
-                  "se_b2": sd["se.2.bias"], "w3": sd["classifier.7.weight"], "b3": sd["classifier.7.bias"]})
-        return ops.HeadParams(2, dim, 1e-6, t, device)
-    return ops.HeadParams(1, dim, 0.0, t, device)
+        se = (sd["se.0.weight"], sd["se.0.bias"], sd["se.2.weight"], sd["se.2.bias"])
+        layers = [(sd["classifier.2.weight"], sd["classifier.2.bias"], G), (sd["classifier.5.weight"], sd["classifier.5.bias"], G),
+                  (sd["classifier.7.weight"], sd["classifier.7.bias"], N)]
+        return ops.HeadParams(2, dim, 1e-6, device, ln=ln, se=se, layers=layers)
+    layers = [(sd["classifier.2.weight"], sd["classifier.2.bias"], G), (sd["classifier.5.weight"], sd["classifier.5.bias"], N)]
+    return ops.HeadParams(1, dim, 0.0, device, ln=ln, layers=layers)
 
 
 class DetectionPipeline:
@@ -63,6 +80,58 @@ class DetectionPipeline:
         """[B, 14] fp32 score records (PACKED_FIELDS) — the unit that is all-gathered across ranks."""
         cols = [out[k].float() for k in PACKED_FIELDS[:8]] + [out["risk_idx"].float()]
         return torch.cat([torch.stack(cols, 1), out["risk_probs"]], 1)
+
+    # ---- detect_core: multicrop, one batched call (deepfake-detector-v2/app.py:1329-1412, 1418-1430) ---------------
+    MULTICROP_WEIGHTS = (0.4, 0.4, 0.05, 0.05, 0.05, 0.05)
+
+    def make_multicrops(self, pil):
+        """The reference's 6 views: full image, bicubic S x S resize, four quadrants; weights .4/.4/.05x4."""
+        from PIL import Image
+
+        S = self.arch.image_size
+        w, h = pil.size
+        w2, h2 = max(1, w // 2), max(1, h // 2)
+        return [pil, pil.resize((S, S), Image.BICUBIC), pil.crop((0, 0, w2, h2)), pil.crop((w2, 0, w, h2)),
+                pil.crop((0, h2, w2, h)), pil.crop((w2, h2, w, h))]
+
+    @torch.no_grad()
+    def detect_core(self, pils, multicrop: bool = True, clahe: bool = False, preprocess=None, freq_temp: float = 1.25):
+        """Batched `detect_core`: every crop of every image goes through ONE backbone / feature batch, crop logits
+        are combined with the reference's weights (on logits, app.py:1346-1347), then one score epilogue per image.
+        Returns a list of dicts with the reference's keys."""
+        import numpy as np
+
+        from .dropin import make_preprocess
+        from .scoring import pil_to_gray256
+
+        pre = preprocess or make_preprocess(self.arch.image_size, "bilinear")
+        views, wts = [], []
+        for pil in pils:
+            pil = pil.convert("RGB")
+            cs = self.make_multicrops(pil) if multicrop else [pil]
+            views += cs
+            wts.append(list(self.MULTICROP_WEIGHTS) if multicrop else [1.0])
+        nv = len(wts[0])
+        x = torch.stack([pre(v) for v in views]).to(self.device, non_blocking=True)
+        gray = torch.from_numpy(np.stack([pil_to_gray256(v, clahe) for v in views])).to(self.device, non_blocking=True)
+        pooled, _ = self.engine(x)
+        z_sig = ops.head_fwd(self.head, pooled)[1]
+        z_freq = self.scoring(torch.zeros_like(z_sig), feats=self.freq.from_gray(gray))["z_freq"]
+        w = torch.tensor(wts, dtype=torch.float32, device=self.device)
+        zs = (z_sig.view(-1, nv) * w).sum(1).contiguous()
+        zf = (z_freq.view(-1, nv) * w).sum(1).contiguous()
+        out = self.scoring(zs, z_freq=zf)
+        host = {k: v.cpu().numpy() for k, v in out.items()}
+        res = []
+        for i in range(len(pils)):
+            zsi, zfi = float(host["z_sig"][i]), float(host["z_freq"][i])
+            res.append({"z_sig": zsi, "z_freq": zfi, "z_scaled": float(host["z_scaled"][i]),
+                        "p_fake_raw": float(host["p_raw"][i]), "p_fake_coral": float(host["p_coral"][i]),
+                        "p_blend": float(host["p_blend"][i]), "visual_prob": 1.0 / (1.0 + np.exp(-zsi)),
+                        "freq_prob": 1.0 / (1.0 + np.exp(-zfi / freq_temp)), "p_or": None, "p_moe": None,
+                        "risk_idx": int(host["risk_idx"][i]), "risk_probs": torch.from_numpy(host["risk_probs"][i].copy()),
+                        "entropy": float(host["entropy"][i])})
+        return res
 
     # ---- host-buffer path (what a caller of the reference loops sees) -----------------------------------
     def detect(self, images_host: torch.Tensor, gray256_host: torch.Tensor, resize_mode: int = 0) -> np.ndarray:

@@ -124,6 +124,20 @@ def fit_coral_cutpoints(logits, labels=None, num_classes: int = 5) -> list:
     return [float(s[int(q * len(s))]) for q in (0.15, 0.35, 0.55, 0.75)]
 
 
+def write_coral_artifacts(out_prefix: str, fused_logits, temperature: float = 1.0) -> dict:
+    """coral.py:375-397 ("fit_coral_v5"): `<prefix>_cutpoints.json` = list of 4 logit-space cutpoints,
+    `<prefix>_temp.json` = {"temperature": 1.0}, `<prefix>_bins.npy` = np.histogram(logits, 50)[0].  The files load
+    back through load_coral()."""
+    lg = np.asarray(fused_logits.detach().cpu() if hasattr(fused_logits, "detach") else fused_logits, dtype=np.float32)
+    cuts = fit_coral_cutpoints(lg)
+    with open(out_prefix + "_cutpoints.json", "w") as f:
+        json.dump(cuts, f, indent=2)
+    with open(out_prefix + "_temp.json", "w") as f:
+        json.dump({"temperature": temperature}, f, indent=2)
+    np.save(out_prefix + "_bins.npy", np.histogram(lg, bins=50)[0])
+    return {"cutpoints": cuts, "temperature": temperature}
+
+
 def detect_generation(freq_state: Optional[dict], fusion_state: Optional[dict]) -> int:
     """G1: keys net.* / fc.*; G2: normer.* / mlp.* (SURVEY.md App. B)."""
     for sd, g1, g2 in ((freq_state, "net.1.weight", "normer.mean"), (fusion_state, "fc.weight", "mlp.0.weight")):

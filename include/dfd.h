@@ -121,20 +121,27 @@ DFD_API int dfd_map_attention_bf16(const void* kv, int64_t ldkv, const float* q,
 
 /* Classifier head on pooled embeddings (fp32 weights, fp32 math):
  *   f = pooled / (‖pooled‖₂ + norm_eps)                       inference_ai_human_images.py:149; +1e-6: train_fusion_head_only.py:106
- *   kind 1 (H-A): LN → Linear(D,D/2) → GELU(erf) → Linear(D/2,1)            inference_ai_human_images.py:131-138
- *   kind 2 (H-B): f·sigmoid(W2·relu(W1·f)) → LN → Linear → GELU → Linear → GELU → Linear(·,1)   train_fusion_head_only.py:84-99,107-108
+ *   then, if kind >= 1: [kind 2: SE gate f·sigmoid(W2·relu(W1·f))  train_fusion_head_only.py:84-89,107]
+ *                       -> LayerNorm(ln_g, ln_b, ln_eps) -> a chain of up to 6 dense layers (act: 0 none, 1 relu,
+ *                          2 GELU(erf), 3 sigmoid); the last layer must have out_dim 1 and yields the logit.
+ *     H-A  LN → Linear(D,D/2)+GELU → Linear(D/2,1)                       inference_ai_human_images.py:131-138
+ *     H-B  SE → LN → Linear+GELU → Linear+GELU → Linear(·,1)             train_fusion_head_only.py:90-99,107-108
+ *     H-D  LN → [1-token attention ≡ proj(v(x))] → 1-3 layer classifier  cifake_binary_classifier.py:643-684,728-749
  *   prototypes (optional [2,D] real,fake): p_proto = softmax([−‖f−p_r‖, −‖f−p_f‖])[1]        inference_ai_human_images.py:288-295
- * Weights are passed as a flat table of device pointers (see dfd_head_weights). */
+ * All weights are fp32 device pointers; every layer dimension must be <= dim. */
+typedef struct dfd_dense_layer {
+  const float *w, *b;       /* [out_dim, in_dim] row-major, [out_dim] (b may be NULL) */
+  int out_dim, in_dim, act;
+} dfd_dense_layer;
 typedef struct dfd_head_weights {
-  int kind;                 /* 0 = none (only normalise / prototypes), 1 = H-A, 2 = H-B */
+  int kind;                 /* 0 = none (only normalise / prototypes), 1 = LN -> layers, 2 = SE -> LN -> layers */
   int dim;                  /* D */
   float norm_eps;           /* added to the L2 norm (0 or 1e-6) */
   float ln_eps;             /* classifier LayerNorm eps (1e-5) */
   const float *se_w1, *se_b1, *se_w2, *se_b2;          /* [D/16,D],[D/16],[D,D/16],[D] (kind 2) */
   const float *ln_g, *ln_b;                             /* [D] */
-  const float *w1, *b1;                                 /* [D/2,D],[D/2] */
-  const float *w2, *b2;                                 /* kind1: [1,D/2],[1]; kind2: [D/4,D/2],[D/4] */
-  const float *w3, *b3;                                 /* kind2: [1,D/4],[1] */
+  int n_layers;
+  dfd_dense_layer layers[6];
 } dfd_head_weights;
 DFD_API int dfd_head_fwd(const dfd_head_weights* w, const void* pooled_bf16, int64_t ldp, int B,
                          const float* prototypes, float* feat_out /*[B,D] normalised, or NULL*/,
@@ -220,6 +227,10 @@ DFD_API int dfd_engine_finalize(dfd_engine* e);
 DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int pix_format, int B, int Hin,
                                int Win, int resize_mode, void* pooled, void* last_hidden,
                                void* stream);
+/* Per-layer hidden states (HF output_hidden_states=True, Siglip2sidafrozen.py:787-793): when buf != NULL the following
+ * forwards also copy the embedding output and each encoder layer's output to buf as bf16 [L+1][B][N][D] (B = the
+ * batch of that forward).  NULL switches the tap off. */
+DFD_API int dfd_engine_set_hidden_tap(dfd_engine* e, void* buf);
 DFD_API int64_t dfd_engine_workspace_bytes(const dfd_engine* e);
 /* Measurement aid (bench.py roofline): when enabled, dfd_engine_forward brackets every launch with CUDA events
  * on the caller's stream.  dfd_engine_profile_read sums the last forward's durations per kernel family

@@ -219,6 +219,39 @@ def make_heads():
             g[f"protos_{D}"] = protos.numpy()
             dr, df = torch.cdist(f, protos[0:1]), torch.cdist(f, protos[1:2])
             g[f"pproto_{D}"] = torch.softmax(torch.cat([-dr, -df], 1), 1)[:, 1].numpy()
+    # H-D (cifake_binary_classifier.py): LightweightAttention is the reference's own class (extracted); the 'large'
+    # variant uses nn.MultiheadAttention; forward as in FastBinaryClassifier.forward:727-749
+    ns = extract(f"{REF}/cifake_binary_classifier.py", {"LightweightAttention"}, base_namespace())
+    D = 128
+    pooled = torch.from_numpy(g["pooled_128"])
+    for size in ("tiny", "small", "medium", "large"):
+        sd = R.init_head_d(size, D, 4)
+        ln = nn.LayerNorm(D)
+        ln.load_state_dict({"weight": sd["layer_norm.weight"], "bias": sd["layer_norm.bias"]})
+        att = None
+        if size in ("tiny", "small"):
+            att = ns["LightweightAttention"](D, num_heads=4)
+            att.load_state_dict({k[len("attention."):]: v for k, v in sd.items() if k.startswith("attention.")})
+        elif size == "large":
+            att = nn.MultiheadAttention(D, min(8, D // 64), dropout=0.1, batch_first=True).eval()
+            att.load_state_dict({k[len("attention."):]: v for k, v in sd.items() if k.startswith("attention.")})
+        if size == "tiny":
+            cls = nn.Sequential(nn.Dropout(0.05), nn.Linear(D, 1))
+        elif size == "small":
+            cls = nn.Sequential(nn.Linear(D, D // 4), nn.GELU(), nn.Dropout(0.1), nn.Linear(D // 4, 1))
+        else:
+            cls = nn.Sequential(nn.Linear(D, D // 2), nn.GELU(), nn.Dropout(0.1), nn.Linear(D // 2, D // 4), nn.GELU(),
+                                nn.Dropout(0.05), nn.Linear(D // 4, 1))
+        cls.eval()
+        cls.load_state_dict({k[len("classifier."):]: v for k, v in sd.items() if k.startswith("classifier.")})
+        with torch.no_grad():
+            f = pooled / pooled.norm(dim=-1, keepdim=True)
+            f = ln(f)
+            if att is not None:
+                f = f.unsqueeze(1)
+                f = att(f) if size in ("tiny", "small") else att(f, f, f)[0]
+                f = f.squeeze(1)
+            g[f"zD_{size}_{D}"] = cls(f).squeeze(-1).numpy()
     np.savez_compressed(os.path.join(OUT, "heads_golden.npz"), **g)
     print("heads_golden.npz:", {k: v.shape for k, v in g.items()})
 

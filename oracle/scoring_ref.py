@@ -332,4 +332,4 @@ def fusion_loss_and_grads(sd: dict, z_freq: np.ndarray, z_sig: np.ndarray, y: np
         loss = torch.nn.functional.binary_cross_entropy_with_logits(out, torch.as_tensor(y, dtype=torch.float64))
         loss.backward()
     grads = torch.cat([p[k].grad.reshape(-1) for k in names]).numpy()
-    return float(loss), grads, out.detach().numpy()
+    return float(loss.detach()), grads, out.detach().numpy()

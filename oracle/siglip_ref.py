@@ -263,6 +263,54 @@ def classifier_head(sd: dict, kind: str, pooled: torch.Tensor, norm_eps: float) 
     return (y @ sd["classifier.7.weight"].t() + sd["classifier.7.bias"]).squeeze(-1)
 
 
+def init_head_d(model_size: str, D: int, seed: int = 4) -> dict:
+    """FastBinaryClassifier head state dict (cifake_binary_classifier.py:643-687): layer_norm, attention
+    (LightweightAttention for tiny/small, nn.MultiheadAttention for large, none for medium), classifier."""
+    g = torch.Generator().manual_seed(seed)
+
+    def rn(*shape, std):
+        return torch.randn(*shape, generator=g, dtype=torch.float32) * std
+
+    sd = {"layer_norm.weight": 1.0 + rn(D, std=0.1), "layer_norm.bias": rn(D, std=0.1)}
+    if model_size in ("tiny", "small"):
+        sd["attention.qkv.weight"], sd["attention.qkv.bias"] = rn(3 * D, D, std=1.0 / math.sqrt(D)), rn(3 * D, std=0.1)
+        sd["attention.proj.weight"], sd["attention.proj.bias"] = rn(D, D, std=1.0 / math.sqrt(D)), rn(D, std=0.1)
+    elif model_size == "large":
+        sd["attention.in_proj_weight"], sd["attention.in_proj_bias"] = rn(3 * D, D, std=1.0 / math.sqrt(D)), rn(3 * D, std=0.1)
+        sd["attention.out_proj.weight"], sd["attention.out_proj.bias"] = rn(D, D, std=1.0 / math.sqrt(D)), rn(D, std=0.1)
+    if model_size == "tiny":
+        dims, idx = [D, 1], [1]
+    elif model_size == "small":
+        dims, idx = [D, D // 4, 1], [0, 3]
+    else:
+        dims, idx = [D, D // 2, D // 4, 1], [0, 3, 6]
+    for i, n in enumerate(idx):
+        sd[f"classifier.{n}.weight"] = rn(dims[i + 1], dims[i], std=1.0 / math.sqrt(dims[i]))
+        sd[f"classifier.{n}.bias"] = rn(dims[i + 1], std=0.1)
+    return sd
+
+
+@torch.no_grad()
+def classifier_head_d(sd: dict, pooled: torch.Tensor) -> torch.Tensor:
+    """cifake_binary_classifier.py:727-749: f/||f|| -> LayerNorm -> attention over ONE token -> classifier.
+    With a single token the softmax weight is exactly 1, so attention(x) = proj(v(x))."""
+    f = l2_normalize(pooled.to(torch.float32), 0.0)
+    D = f.shape[-1]
+    y = F.layer_norm(f, (D,), sd["layer_norm.weight"], sd["layer_norm.bias"], 1e-5)
+    if "attention.qkv.weight" in sd:
+        v = y @ sd["attention.qkv.weight"][2 * D:].t() + sd["attention.qkv.bias"][2 * D:]
+        y = v @ sd["attention.proj.weight"].t() + sd["attention.proj.bias"]
+    elif "attention.in_proj_weight" in sd:
+        v = y @ sd["attention.in_proj_weight"][2 * D:].t() + sd["attention.in_proj_bias"][2 * D:]
+        y = v @ sd["attention.out_proj.weight"].t() + sd["attention.out_proj.bias"]
+    idx = sorted(int(k.split(".")[1]) for k in sd if k.startswith("classifier.") and k.endswith(".weight"))
+    for n, i in enumerate(idx):
+        y = y @ sd[f"classifier.{i}.weight"].t() + sd[f"classifier.{i}.bias"]
+        if n + 1 < len(idx):
+            y = F.gelu(y)
+    return y.squeeze(-1)
+
+
 @torch.no_grad()
 def prototype_prob(features: torch.Tensor, real_proto: torch.Tensor, fake_proto: torch.Tensor) -> torch.Tensor:
     """inference_ai_human_images.py:288-295: softmax([-d_real, -d_fake])[:, 1] with Euclidean cdist."""

@@ -163,4 +163,11 @@ def test_coral_loader_formats(tmp_path, shipped):
     (tmp_path / "t2.json").write_text(json.dumps({"temp": 0.8}))
     assert scoring.load_coral(None, str(tmp_path / "t2.json"))[1] == 0.8
     assert abs(scoring.load_coral(None, None)[0][0] - scoring._logit(0.32)) < 1e-12
+    # coral.py-style writer round-trips through the loader
+    rng = __import__("numpy").random.default_rng(0)
+    lg = rng.normal(0, 2, 501).astype("float32")
+    art = scoring.write_coral_artifacts(str(tmp_path / "coral"), lg)
+    c2, t2 = scoring.load_coral(str(tmp_path / "coral_cutpoints.json"), str(tmp_path / "coral_temp.json"))
+    assert c2 == art["cutpoints"] == scoring.fit_coral_cutpoints(lg) and t2 == 1.0
+    assert __import__("numpy").load(str(tmp_path / "coral_bins.npy")).sum() == 501
     assert scoring.fit_coral_cutpoints_shipped(shipped["bins"]) == {k: float(shipped["cuts"][k]) for k in ("q25", "q50", "q75", "max")}

@@ -42,6 +42,27 @@ def test_binary_classifier_forward(head, eps):
         assert (z2 - R.classifier_head(hs, "B", p2, 1e-6)).abs().max() < 2e-2
 
 
+def test_fast_binary_classifier_cifake_path():
+    """BASELINE config 4: 32x32 images, bilinear align_corners=False upsampling inside the model, head H-D."""
+    from dfd import dropin
+    from oracle import siglip_ref as R
+
+    c = R.CONFIGS["tiny-hd64"]
+    sd = R.init_state_dict(c, 0)
+    for size in ("small", "large"):
+        hd = R.init_head_d(size, c.hidden_size, 4)
+        m = dropin.FastBinaryClassifier(size, DEV, arch="tiny-hd64", max_batch=8)
+        ck = {"backbone.vision_model." + k: v for k, v in sd.items()}
+        ck.update(hd)
+        m.load_state_dict(ck)
+        img = R.synthetic_images(7, 32, 8)
+        for x in (img, R.preprocess_u8(img)):  # u8 NHWC and normalised f32 NCHW
+            z = m(x).cpu()
+            xr = R.resize_input(R.preprocess_u8(img), c.image_size, "bilinear")
+            z_ref = R.classifier_head_d(hd, R.siglip_vision_forward(sd, c, xr, "fp32")["pooler_output"])
+            assert (z - z_ref).abs().max() < 2e-2 * max(1.0, float(z_ref.abs().max())), (size, z, z_ref)
+
+
 def test_run_inference_and_prototypes():
     from dfd import dropin
     from oracle import siglip_ref as R
@@ -80,8 +101,14 @@ def test_hf_shaped_vision_model():
     ref = R.siglip_vision_forward(sd, c, x, "fp32")
     assert R.cosine_report(o.pooler_output.cpu(), ref["pooler_output"])["cos_min"] >= 0.999
     assert o.last_hidden_state.shape == (2, c.tokens, c.hidden_size)
-    with pytest.raises(NotImplementedError):
-        m(pixel_values=x, output_hidden_states=True)
+    # per-layer hidden states (SigLIP2_MTL taps, Siglip2sidafrozen.py:787-793)
+    oh = m(pixel_values=x, output_hidden_states=True)
+    rh = R.siglip_vision_forward(sd, c, x, "fp32", output_hidden_states=True)["hidden_states"]
+    assert len(oh.hidden_states) == c.num_hidden_layers + 1 == len(rh)
+    for a, b in zip(oh.hidden_states, rh):
+        rep = R.cosine_report(a.cpu().reshape(-1, c.hidden_size), b.reshape(-1, c.hidden_size))
+        assert rep["cos_min"] >= 0.998 and rep["rel_l2"] <= 0.03, rep
+    assert torch.equal(oh.pooler_output, o.pooler_output)
 
 
 def test_import_shims():
@@ -142,6 +169,49 @@ def test_detection_pipeline_host_buffers_vs_oracle():
     tp = S.coral_transition_points(np.array(cuts, np.float32))
     near = np.abs(d["z_scaled"][:, None] - tp[None]).min(1) < 1e-2
     assert np.array_equal(rec[:, col["risk_idx"]].astype(int)[~near], d["risk_idx"][~near])
+
+
+def test_detect_core_multicrop_vs_oracle():
+    """`detect_core(pil, multicrop=True)` for a batch of images in one call vs the reference flow restated with the
+    oracle: 6 crops, weights on logits, G1 shipped heads (z-scored features), temperature, CORAL."""
+    from PIL import Image
+
+    from dfd import dropin, pipeline, scoring
+    from oracle import scoring_ref as S
+    from oracle import siglip_ref as R
+    from tests.conftest import SIGLIP_ARTEFACTS
+
+    name = "tiny-hd64"
+    c = R.CONFIGS[name]
+    sd, hs = R.init_state_dict(c, 0), R.init_head("B", c.hidden_size, 1)
+    st = scoring.ScoringStack.from_dir(SIGLIP_ARTEFACTS, DEV)
+    pipe = pipeline.DetectionPipeline(name, sd, hs, st, device=0, max_batch=16)
+    rng = np.random.default_rng(3)
+    pils = [Image.fromarray(np.clip(rng.normal(120, 50, (90 + 20 * i, 130, 3)), 0, 255).astype(np.uint8)) for i in range(2)]
+    res = pipe.detect_core(pils, multicrop=True, clahe=False)
+    assert len(res) == 2 and set(res[0]) >= {"z_sig", "z_freq", "z_scaled", "p_fake_raw", "p_fake_coral", "p_blend",
+                                             "risk_idx", "risk_probs", "entropy", "visual_prob", "freq_prob"}
+    import json
+    from safetensors.torch import load_file
+
+    fm, fu = load_file(f"{SIGLIP_ARTEFACTS}/freq_mlp.safetensors"), load_file(f"{SIGLIP_ARTEFACTS}/fusion_head.safetensors")
+    cuts = S.coral_cut_logits(json.load(open(f"{SIGLIP_ARTEFACTS}/coral_cutpoints.json")))
+    temp = json.load(open(f"{SIGLIP_ARTEFACTS}/coral_temp.json"))["temperature"]
+    pre = dropin.make_preprocess(c.image_size, "bilinear")
+    w = np.array(pipeline.DetectionPipeline.MULTICROP_WEIGHTS)
+    for pil, r in zip(pils, res):
+        crops = pipe.make_multicrops(pil)
+        x = torch.stack([pre(v) for v in crops])
+        pooled = R.siglip_vision_forward(sd, c, x, "fp32")["pooler_output"]
+        z_sig = float((R.classifier_head(hs, "B", pooled, 1e-6).numpy() * w).sum())
+        feats = np.stack([S.extract_freq_vector(S.gray256_from_rgb_u8(np.asarray(v), False), zscore=True) for v in crops])
+        z_freq = float((S.freq_mlp_g1(fm, feats) * w).sum())
+        z = S.fusion_g1(fu, np.array([z_sig]), np.array([z_freq]))
+        d = S.detect_scores(z, cuts, temp)
+        assert abs(r["z_sig"] - z_sig) < 2e-2 and abs(r["z_freq"] - z_freq) < 2e-3
+        assert abs(r["z_scaled"] - float(d["z_scaled"][0])) < 1e-2 and abs(r["p_blend"] - float(d["p_blend"][0])) < 5e-3
+        assert r["risk_idx"] == int(d["risk_idx"][0])
+        assert abs(r["visual_prob"] - 1 / (1 + np.exp(-z_sig))) < 5e-3
 
 
 def _reference_fit(z_freq, z_sig, labels, batch_size, epochs, seed):

@@ -253,6 +253,7 @@ def test_map_attention(B, N, H, hd):
 @pytest.mark.parametrize("D", [128, 1152])
 def test_heads(D, golden_heads):
     from dfd import ops
+    from dfd.pipeline import head_params_from_state
     from oracle import siglip_ref as R
 
     pooled = torch.from_numpy(golden_heads[f"pooled_{D}"])
@@ -261,12 +262,8 @@ def test_heads(D, golden_heads):
     protos = torch.from_numpy(golden_heads[f"protos_{D}"]).to(DEV)
     for kind, eps in (("A", 0.0), ("B", 1e-6)):
         sd = R.init_head(kind, D, 1)
-        t = {"ln_g": sd["classifier.0.weight"], "ln_b": sd["classifier.0.bias"], "w1": sd["classifier.2.weight"],
-             "b1": sd["classifier.2.bias"], "w2": sd["classifier.5.weight"], "b2": sd["classifier.5.bias"]}
-        if kind == "B":
-            t.update({"se_w1": sd["se.0.weight"], "se_b1": sd["se.0.bias"], "se_w2": sd["se.2.weight"],
-                      "se_b2": sd["se.2.bias"], "w3": sd["classifier.7.weight"], "b3": sd["classifier.7.bias"]})
-        head = ops.HeadParams(1 if kind == "A" else 2, D, eps, t, DEV)
+        head = head_params_from_state(sd, D, DEV)
+        assert head.kind == (1 if kind == "A" else 2)
         feats, z, pp = ops.head_fwd(head, pb, prototypes=protos, want_features=True)
         torch.cuda.synchronize()
         z_ref = R.classifier_head(sd, kind, pr, eps)
@@ -279,8 +276,14 @@ def test_heads(D, golden_heads):
             p_ref = R.prototype_prob(f_ref, protos[0].cpu(), protos[1].cpu())
             assert torch.allclose(pp.cpu(), p_ref, atol=1e-5)
             assert np.abs(pp.cpu().numpy() - golden_heads[f"pproto_{D}"]).max() < 2e-3
+    if D == 128:  # H-D (CiFake FastBinaryClassifier): LN -> one-token attention -> classifier, all four sizes
+        for size in ("tiny", "small", "medium", "large"):
+            sd = R.init_head_d(size, D, 4)
+            z = ops.head_fwd(head_params_from_state(sd, D, DEV), pb)[1].cpu()
+            assert torch.allclose(z, R.classifier_head_d(sd, pr), atol=2e-5, rtol=1e-5), size
+            assert np.abs(z.numpy() - golden_heads[f"zD_{size}_{D}"]).max() < 1e-2
     # kind 0: normalise only
-    head0 = ops.HeadParams(0, D, 0.0, {}, DEV)
+    head0 = ops.HeadParams(0, D, 0.0, DEV)
     feats, z, pp = ops.head_fwd(head0, pb, want_features=True)
     assert z is None and pp is None and torch.allclose(feats.cpu(), R.l2_normalize(pr, 0.0), atol=1e-6)
 

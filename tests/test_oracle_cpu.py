@@ -66,6 +66,15 @@ def test_heads_oracle_matches_golden(golden_heads):
         assert np.abs(p - golden_heads[f"pproto_{D}"]).max() < 1e-6
 
 
+def test_head_d_oracle_matches_reference_modules(golden_heads):
+    """H-D: one-token attention == proj(v(x)); checked against the reference's LightweightAttention and
+    nn.MultiheadAttention outputs stored in the golden file."""
+    pooled = torch.from_numpy(golden_heads["pooled_128"])
+    for size in ("tiny", "small", "medium", "large"):
+        z = R.classifier_head_d(R.init_head_d(size, 128, 4), pooled).numpy()
+        assert np.abs(z - golden_heads[f"zD_{size}_128"]).max() < 2e-5, size
+
+
 def test_freq_features_oracle_matches_reference(golden_scoring):
     gray = golden_scoring["gray_u8"].astype(np.float32) / 255.0
     for i in range(gray.shape[0]):
