@@ -99,7 +99,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
 
   if (warp == 0) {
     // ------------------------------------ TMA loader ------------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(q_full, S::kQBytes);
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -122,7 +122,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------------ MMA issuer ------------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t tO = tmem_base + kColO;
       const uint64_t dQ = umma_desc(smem_u32(sQ), 16, 1024, 2);
       const uint64_t dQt = umma_desc(smem_u32(sQ + S::kQMain), 16, 256, 6);
@@ -314,6 +314,14 @@ int make_tmap_qkv(CUtensorMap* out, const void* base, int hd, int heads3, int N,
 
 }  // namespace
 
+// shared with attention_ws.cu: qkv [B*N, ld] viewed as (hd, 3H, N, B), box = box_cols x 1 x box_rows x 1
+int make_tmap_qkv_4d(CUtensorMap* out, const void* base, int hd, int heads3, int N, int B, int64_t ld, int box_cols,
+                     int box_rows, int swizzle32) {
+  (void)box_rows;  // both kernels use 64-token boxes
+  return make_tmap_qkv(out, base, hd, heads3, N, B, ld, box_cols,
+                       swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 int attention_tc_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
                       float scale, cudaStream_t st) {
   DFD_REQUIRE(qkv && out, DFD_ERR_BAD_ARG, "attention: null pointer");
@@ -358,9 +366,12 @@ int attention_tc_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, in
 
 }  // namespace dfd
 
-// Test / A-B hook: impl 0 = warp-level mma.sync kernel (attention.cu), 1 = tcgen05 kernel (this file).
+// Test / A-B hook: impl 0 = warp-level mma.sync kernel (attention.cu), 1 = tcgen05 kernel (this file),
+// 2 = persistent tcgen05 kernel (attention_ws.cu).
 extern "C" DFD_API int dfd_attention_bf16_impl(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N,
                                                int H, int hd, float scale, int impl, void* stream) {
+  if (impl == 2)
+    return dfd::attention_ws_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));
   if (impl == 1)
     return dfd::attention_tc_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));
   return dfd::attention_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));

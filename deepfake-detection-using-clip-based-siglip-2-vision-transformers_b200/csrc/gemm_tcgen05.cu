@@ -22,7 +22,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int kEpiWarps = 8;                       // two groups of 4 warps (one warp per TMEM lane quadrant)
 constexpr int kGemmThreads = (3 + kEpiWarps) * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 residual TMA
-constexpr int kResSlots = 2;                        // residual chunks in flight (RES kernels only)
+constexpr int kResSlots = 2;                        // one residual chunk in flight per epilogue group (RES kernels)
 constexpr int kChunkN = 64;                         // epilogue / TMA-store granularity along N
 constexpr int kStageCBytes = BM * kChunkN * 2;      // 16 KB staging tile per epilogue group
 
@@ -138,7 +138,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
+    // elect.sync rather than `lane == 0`: ptxas then knows exactly one thread is active and emits the TMA / MMA /
+    // commit instructions bare; behind `lane == 0` every one of them sits in an ELECT..BRA.U.ANY loop that costs
+    // ~100 cycles per issue (scripts/ubench_tc.cu) — as much as a 128x256x16 MMA takes to execute.
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
@@ -166,7 +169,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0 && is_leader) {
+    if (is_leader && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -205,16 +208,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
   } else if (warp == 2 + kEpiWarps) {
     // ------------------------------- residual producer --------------------------
-    if (RES && lane == 0) {
+    if (RES && elect_one()) {
       tma_prefetch_desc(&tmR);
-      uint32_t q = 0;  // running chunk number of this CTA
+      // slot g belongs to epilogue group g (chunks c ≡ g mod 2): each slot has exactly one consumer, so the parity
+      // waits stay one phase apart whatever the number of chunks per tile (a shared ring broke for odd counts)
+      uint32_t uses[kResSlots] = {0, 0};
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int m0 = (tile / num_n) * (BM * CG) + (int)cta_rank * BM;
         const int n0 = (tile % num_n) * BN;
         const int nvalid = min(BN / kChunkN, (N - n0 + kChunkN - 1) / kChunkN);
-        for (int c = 0; c < nvalid; ++c, ++q) {
-          const int slot = q % kResSlots;
-          mbar_wait(&rempty_bar[slot], ((q / kResSlots) & 1u) ^ 1u);
+        for (int c = 0; c < nvalid; ++c) {
+          const int slot = c & 1;
+          mbar_wait(&rempty_bar[slot], (uses[slot]++ & 1u) ^ 1u);
           mbar_expect_tx(&rfull_bar[slot], kStageCBytes);
           tma_load_2d(&tmR, &rfull_bar[slot], smem_r + slot * kStageCBytes, n0 + c * kChunkN, m0);
         }
@@ -228,14 +233,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const int grp = ew >> 2;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int row_in_tile = quad * 32 + lane;
-    const bool leader = ((ew & 3) == 0) && (lane == 0);
+    const bool store_warp = (ew & 3) == 0;  // its elected lane issues (and waits for) the group's TMA stores
     uint8_t* stage_c = smem_c + grp * kStageCBytes;
     const uint32_t stage_row = smem_u32(stage_c) + static_cast<uint32_t>(row_in_tile * 128);
     const int sw = row_in_tile & 7;
     constexpr int kChunks = BN / kChunkN;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t q_base = 0;  // running residual chunk number at the start of the tile
+    uint32_t res_uses = 0;  // residual chunks this group has consumed from its slot
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       const int m0 = (tile / num_n) * (BM * CG) + (int)cta_rank * BM;
       const int n0 = (tile % num_n) * BN;
@@ -287,9 +292,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         uint4 res[8];
         if (RES) {
           // this chunk's residual tile was prefetched by the residual warp (128B-swizzled, like the C staging)
-          const uint32_t q = q_base + (uint32_t)c;
-          const int slot = q % kResSlots;
-          mbar_wait(&rfull_bar[slot], (q / kResSlots) & 1u);
+          const int slot = grp;
+          mbar_wait(&rfull_bar[slot], res_uses++ & 1u);
           const uint32_t rrow = smem_u32(smem_r + slot * kStageCBytes) + static_cast<uint32_t>(row_in_tile * 128);
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
@@ -297,6 +301,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                          : "=r"(res[g].x), "=r"(res[g].y), "=r"(res[g].z), "=r"(res[g].w)
                          : "r"(rrow + static_cast<uint32_t>((g ^ sw) << 4)));
           }
+          // generic-proxy reads above vs the TMA (async-proxy) refill of this slot: the proxy fence makes every
+          // lane's loads complete before its warp releases the slot (without it one 16-byte piece of one row was,
+          // rarely, read after the refill had landed — tests/test_ops_gpu.py::test_gemm_residual_many_tiles)
+          fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&rempty_bar[slot]);
         }
@@ -351,7 +359,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           }
         }
         // staging tile free? (the previous TMA store of this group has finished reading it)
-        if (leader) tma_store_wait_read<0>();
+        if (store_warp && elect_one()) tma_store_wait_read<0>();
         named_bar_sync(1 + grp, 128);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -362,7 +370,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         }
         fence_proxy_async_smem();
         named_bar_sync(1 + grp, 128);
-        if (leader) {
+        if (store_warp && elect_one()) {
           tma_store_2d(&tmC, stage_c, c0, m0);  // rows >= M and columns >= N are clipped by the TMA unit
           tma_store_commit();
         }
@@ -371,10 +379,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         atomicAdd(epi.stats_out + 2 * (int64_t)row, st_sum);
         atomicAdd(epi.stats_out + 2 * (int64_t)row + 1, st_sq);
       }
-      q_base += (uint32_t)nvalid;
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-    if (leader) tma_store_wait<0>();
+    if (store_warp && elect_one()) tma_store_wait<0>();
   }
 
   tc_fence_before();

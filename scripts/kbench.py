@@ -70,9 +70,10 @@ def gemms(B, arch):
 def attention(B, arch):
     N, H, hd = arch.tokens, arch.num_attention_heads, arch.head_dim
     qkv = torch.randn(B * N, 3 * H * hd, device=DEV).to(torch.bfloat16)
-    med, best = timeit(lambda: ops.attention_bf16(qkv, B, N, H, hd))
     fl = 4.0 * N * N * H * hd * B
-    print(f"attention B={B} N={N} H={H} hd={hd}: {med:8.3f} ms {fl / med / 1e9:7.1f} TF/s best {best:.3f}", flush=True)
+    for impl in (1, 2):
+        med, best = timeit(lambda: ops.attention_bf16(qkv, B, N, H, hd, impl=impl))
+        print(f"attention impl={impl} B={B} N={N} H={H} hd={hd}: {med:8.3f} ms {fl / med / 1e9:7.1f} TF/s best {best:.3f}", flush=True)
     try:
         q, k, v = (qkv[:, i * H * hd:(i + 1) * H * hd].reshape(B, N, H, hd).transpose(1, 2) for i in range(3))
         med, _ = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))

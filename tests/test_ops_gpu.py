@@ -95,6 +95,28 @@ def test_gemm_epilogues(M, N, K):
     assert torch.allclose(st[:, 1], (of * of).sum(1), rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("N,tile_n", [(1152, 2192), (1152, 1192), (320, 2256), (320, 1256), (1152, 2256), (192, 1128)])
+def test_gemm_residual_many_tiles(N, tile_n):
+    """Several tiles per CTA with a residual: the two epilogue groups drift apart, and with an odd number of
+    64-column chunks per tile (tile 192, or an N tail of 1 or 3 chunks) they once shared residual slots."""
+    from dfd import ops
+
+    M, K = 148 * 128 * 5 + 77, 128
+    g = torch.Generator(device="cpu").manual_seed(N + tile_n)
+    a = _bf(torch.randn(M, K, generator=g)).to(DEV)
+    w = _bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    res = _bf(torch.randn(M, N, generator=g)).to(DEV)
+    ref = a.float() @ w.float().t() + res.float()
+    for _ in range(3):
+        out = ops.gemm_bf16(a, w, residual=res, tile_n=tile_n)
+        torch.cuda.synchronize()
+        err = (out.float() - ref).abs()
+        bad = (err > 2.0 ** -8 * ref.abs() + 2e-3).nonzero()
+        assert bad.numel() == 0, (f"{bad.shape[0]} wrong, max {err.max().item():.3f}, rows {bad[:, 0].min().item()}.."
+                                  f"{bad[:, 0].max().item()} ({bad[:, 0].unique().numel()}), cols {bad[:, 1].min().item()}.."
+                                  f"{bad[:, 1].max().item()}, row tiles {sorted(set((bad[:, 0] // 128).tolist()))[:10]}")
+
+
 def test_gemm_ln_fold():
     """LayerNorm folded through the GEMM: LN(x)·(γ⊙W)ᵀ = rstd·(x·W'ᵀ − mean·colsum(W'))."""
     from dfd import ops
@@ -195,8 +217,9 @@ def _ref_attention(qkv, B, N, H, hd):
 
 
 @pytest.mark.parametrize("B,N,H,hd", [(2, 196, 12, 64), (1, 729, 16, 72), (3, 16, 2, 64), (2, 16, 2, 72),
-                                      (2, 225, 4, 72), (1, 1024, 2, 72), (2, 64, 1, 64), (1, 129, 3, 64), (1, 1, 2, 72)])
-@pytest.mark.parametrize("impl", [1, 0])  # tcgen05 kernel (product), mma.sync kernel
+                                      (2, 225, 4, 72), (1, 1024, 2, 72), (2, 64, 1, 64), (1, 129, 3, 64), (1, 1, 2, 72),
+                                      (40, 576, 16, 64), (330, 100, 1, 72)])
+@pytest.mark.parametrize("impl", [2, 1, 0])  # persistent tcgen05 kernel (product), tcgen05 v1, mma.sync kernel
 def test_attention(B, N, H, hd, impl):
     from dfd import ops
 
@@ -222,7 +245,7 @@ def test_attention_large_logits():
     qkv[N - 40:N, H * hd:2 * H * hd] *= 8.0                  # late keys dominate -> the running max jumps
     qkv = _bf(qkv).to(DEV)
     ref = _ref_attention(qkv, B, N, H, hd)
-    for impl in (1, 0):
+    for impl in (2, 1, 0):
         out = ops.attention_bf16(qkv, B, N, H, hd, impl=impl)
         torch.cuda.synchronize()
         assert torch.isfinite(out.float()).all()
