@@ -298,12 +298,12 @@ PFN_encodeTiled encode_fn() {
 
 // qkv [B*N, ld] viewed as (hd, 3H, N, B); box = box_cols x 1 x 128 x 1
 int make_tmap_qkv(CUtensorMap* out, const void* base, int hd, int heads3, int N, int B, int64_t ld, int box_cols,
-                  CUtensorMapSwizzle sw) {
+                  CUtensorMapSwizzle sw, int box_rows = kKV) {
   PFN_encodeTiled fn = encode_fn();
   DFD_REQUIRE(fn != nullptr, DFD_ERR_NO_DEVICE, "cuTensorMapEncodeTiled unavailable (no CUDA driver on this host)");
   cuuint64_t gdim[4] = {(cuuint64_t)hd, (cuuint64_t)heads3, (cuuint64_t)N, (cuuint64_t)B};
   cuuint64_t gstr[3] = {(cuuint64_t)hd * 2, (cuuint64_t)ld * 2, (cuuint64_t)N * (cuuint64_t)ld * 2};
-  cuuint32_t box[4] = {(cuuint32_t)box_cols, 1, (cuuint32_t)kKV, 1};  // 64 token rows per box
+  cuuint32_t box[4] = {(cuuint32_t)box_cols, 1, (cuuint32_t)box_rows, 1};  // box_rows token rows per box
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -314,12 +314,11 @@ int make_tmap_qkv(CUtensorMap* out, const void* base, int hd, int heads3, int N,
 
 }  // namespace
 
-// shared with attention_ws.cu: qkv [B*N, ld] viewed as (hd, 3H, N, B), box = box_cols x 1 x box_rows x 1
+// shared with attention_ws.cu / attention_pp.cu: qkv [B*N, ld] viewed as (hd, 3H, N, B), box = box_cols x 1 x box_rows x 1
 int make_tmap_qkv_4d(CUtensorMap* out, const void* base, int hd, int heads3, int N, int B, int64_t ld, int box_cols,
                      int box_rows, int swizzle32) {
-  (void)box_rows;  // both kernels use 64-token boxes
   return make_tmap_qkv(out, base, hd, heads3, N, B, ld, box_cols,
-                       swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+                       swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, box_rows);
 }
 
 int attention_tc_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
@@ -367,9 +366,11 @@ int attention_tc_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, in
 }  // namespace dfd
 
 // Test / A-B hook: impl 0 = warp-level mma.sync kernel (attention.cu), 1 = tcgen05 kernel (this file),
-// 2 = persistent tcgen05 kernel (attention_ws.cu).
+// 2 = persistent tcgen05 kernel (attention_ws.cu), 3 = ping-pong tcgen05 kernel (attention_pp.cu).
 extern "C" DFD_API int dfd_attention_bf16_impl(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N,
                                                int H, int hd, float scale, int impl, void* stream) {
+  if (impl == 3)
+    return dfd::attention_pp_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));
   if (impl == 2)
     return dfd::attention_ws_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));
   if (impl == 1)

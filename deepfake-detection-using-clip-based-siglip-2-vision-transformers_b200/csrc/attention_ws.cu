@@ -34,6 +34,10 @@ constexpr int kTmemCols = 256;
 constexpr int kColS = 0;           // S: two fp32 [128 x 64] buffers (columns 0 and 64); P (bf16 pairs) aliases the
                                    // first 32 columns of its S buffer
 constexpr int kColO = 128;         // O: fp32 [128 x 80]
+#ifndef DFD_ATTN_POLY_EVERY
+#define DFD_ATTN_POLY_EVERY 2
+#endif
+constexpr int kPolyEvery = DFD_ATTN_POLY_EVERY;  // every kPolyEvery-th pair of exponentials goes to the FMA pipe
 
 template <int HD>
 struct WsSmem {
@@ -67,6 +71,44 @@ __device__ __forceinline__ void pair_bar_sync(int quad) {
     case 2: asm volatile("bar.sync 3, 64;\n" ::: "memory"); break;
     default: asm volatile("bar.sync 4, 64;\n" ::: "memory"); break;
   }
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+// 2^x for a pair on the FMA pipe (the MUFU unit, 16 ex2/clk/SM, is the softmax bottleneck): round-to-nearest split
+// x = i + f, |f| <= 0.5, by the 1.5*2^23 trick, degree-3 minimax polynomial for 2^f (relative error 7.5e-5, far below
+// the 2^-9 of the bf16 P it feeds), exponent added as an integer.  x is clamped to >= -125 (result >= 2^-125 > 0).
+__device__ __forceinline__ float2 exp2_fma2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 t = fadd2(x, make_float2(12582912.0f, 12582912.0f));
+  const float2 fi = fadd2(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = ffma2(fi, make_float2(-1.0f, -1.0f), x);
+  float2 p = ffma2(make_float2(0.05517162010073662f, 0.05517162010073662f), f,
+                   make_float2(0.2426111251115799f, 0.2426111251115799f));
+  p = ffma2(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = ffma2(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+  float2 r;
+  r.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
+  r.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
+  return r;
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(a, fmaxf(b, c)); }  // -> FMNMX3
 
@@ -228,6 +270,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
     constexpr int kGroups = HD / 8;                      // 8-column groups of O that carry data
     constexpr int kG0 = (kGroups + 1) / 2;               // groups [0,kG0) -> half 0, [kG0,kGroups) -> half 1
     const int gbeg = half ? kG0 : 0, gend = half ? kGroups : kG0;
+    const float2 scale2 = make_float2(scale_log2, scale_log2);
     uint32_t g = 0, it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int qt = item % QT, h = (item / QT) % H, b = item / (QT * H);
@@ -276,18 +319,24 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
           }
         }
         m = m_new;
-        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-        const float neg_m = -m;
+        float2 sum2[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+        const float2 neg_m2 = make_float2(-m, -m);
         uint32_t p[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(s[2 * c]), scale_log2, neg_m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), scale_log2, neg_m));
-          sum4[(2 * c) & 3] += p0;
-          sum4[(2 * c + 1) & 3] += p1;
-          p[c] = pack_bf16x2(p0, p1);
+          const float2 x = ffma2(make_float2(__uint_as_float(s[2 * c]), __uint_as_float(s[2 * c + 1])), scale2, neg_m2);
+          float2 e;
+          if ((c % kPolyEvery) == kPolyEvery - 1) {  // this pair on the FMA pipe
+            e = exp2_fma2(x);
+          } else {
+            e.x = fast_exp2(x.x);
+            e.y = fast_exp2(x.y);
+          }
+          sum2[c & 3] = fadd2(sum2[c & 3], e);
+          p[c] = pack_bf16x2(e.x, e.y);
         }
-        l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+        const float2 t2 = fadd2(fadd2(sum2[0], sum2[1]), fadd2(sum2[2], sum2[3]));
+        l = l * alpha + (t2.x + t2.y);
         // the partner has loaded its S columns (it passed the named barrier), so its columns 16..31 may be overwritten
         tmem_st_32x32b_x16(tS + 16 * half, p);
         tmem_st_wait();

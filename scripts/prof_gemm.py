@@ -24,8 +24,9 @@ if which in ("outres", "qkv", "fc1", "fc2"):
 elif which == "attn":
     B, N, H, hd = 64, 729, 16, 72
     qkv = torch.randn(B * N, 3 * H * hd, device=DEV).to(torch.bfloat16)
+    impl = int(sys.argv[2]) if len(sys.argv) > 2 else None
     for _ in range(4):
-        ops.attention_bf16(qkv, B, N, H, hd)
+        ops.attention_bf16(qkv, B, N, H, hd, impl=impl)
 elif which == "engine":
     from dfd import engine
     from oracle import siglip_ref as R
