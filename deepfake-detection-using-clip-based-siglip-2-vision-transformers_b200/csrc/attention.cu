@@ -394,7 +394,7 @@ int map_attention_bf16(const void* kv, int64_t ldkv, const float* q, void* out, 
 
 extern "C" DFD_API int dfd_attention_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B,
                                           int N, int H, int hd, float scale, void* stream) {
-  return dfd::attention_tc_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));
+  return dfd::attention_auto_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));
 }
 extern "C" DFD_API int dfd_map_attention_bf16(const void* kv, int64_t ldkv, const float* q, void* out,
                                               int64_t ldo, int B, int N, int H, int hd, float scale,

@@ -314,7 +314,7 @@ int make_tmap_qkv(CUtensorMap* out, const void* base, int hd, int heads3, int N,
 
 }  // namespace
 
-// shared with attention_ws.cu / attention_pp.cu: qkv [B*N, ld] viewed as (hd, 3H, N, B), box = box_cols x 1 x box_rows x 1
+// shared with attention_ws.cu: qkv [B*N, ld] viewed as (hd, 3H, N, B), box = box_cols x 1 x box_rows x 1
 int make_tmap_qkv_4d(CUtensorMap* out, const void* base, int hd, int heads3, int N, int B, int64_t ld, int box_cols,
                      int box_rows, int swizzle32) {
   return make_tmap_qkv(out, base, hd, heads3, N, B, ld, box_cols,
@@ -363,16 +363,24 @@ int attention_tc_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, in
   return DFD_OK;
 }
 
+// Product dispatch (measured on B200, scripts/kbench.py attn): short sequences (base-224: 196 tokens, 2 query tiles
+// and 4 key tiles per head) gain 4-5 % from the persistent kernel, which hides the per-CTA prologue; at 729 tokens the
+// per-tile kernel is 3 % ahead.
+int attention_auto_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
+                        float scale, cudaStream_t st) {
+  if (N <= 256) return attention_ws_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, 64, st);
+  return attention_tc_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, st);
+}
+
 }  // namespace dfd
 
 // Test / A-B hook: impl 0 = warp-level mma.sync kernel (attention.cu), 1 = tcgen05 kernel (this file),
-// 2 = persistent tcgen05 kernel (attention_ws.cu), 3 = ping-pong tcgen05 kernel (attention_pp.cu).
+// 2 / 3 = persistent tcgen05 kernel (attention_ws.cu) with 64- / 128-key tiles.
 extern "C" DFD_API int dfd_attention_bf16_impl(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N,
                                                int H, int hd, float scale, int impl, void* stream) {
-  if (impl == 3)
-    return dfd::attention_pp_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));
-  if (impl == 2)
-    return dfd::attention_ws_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));
+  if (impl == 2 || impl == 3)
+    return dfd::attention_ws_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, impl == 2 ? 64 : 128,
+                                  reinterpret_cast<cudaStream_t>(stream));
   if (impl == 1)
     return dfd::attention_tc_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));
   return dfd::attention_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));

@@ -7,10 +7,15 @@
 //
 //   * persistent CTAs (2 per SM): each loops over (image, head, 128-query tile) work items; the loader and the MMA
 //     warp run ahead into the next item (Q', K'0, K'1, S'0, S'1) while the softmax warps finish the current one,
-//   * eight softmax warps per CTA: warps w and w+4 share a TMEM lane quadrant (the same 32 query rows) and split each
-//     64-key tile by columns (32 keys each).  The row maximum is exchanged through shared memory with one 64-thread
-//     named barrier per tile; both halves then hold the same running max, keep partial row sums (added once per
-//     item) and own one half of the O columns for the (rare) lazy rescale and for the output.
+//   * KV/32 softmax warps per TMEM lane quadrant (the same 32 query rows) split each key tile by columns, 32 keys per
+//     thread.  The row maximum is exchanged through shared memory with one named barrier per tile; all parts then hold
+//     the same running max, keep partial row sums (added once per item) and own a share of the O columns for the
+//     (rare) lazy rescale and for the output,
+//   * two instantiations: KV = 64 (2 CTAs/SM, 256 TMEM columns each, 8 softmax warps) and KV = 128 (1 CTA/SM, all
+//     512 columns, 16 softmax warps).  With everything but the barrier handshakes removed the KV = 64 kernel still
+//     takes 80 % of its time: thirteen small MMAs per 64 keys (N = 64 and N = 16) keep the tensor pipe busy at ~45 %
+//     efficiency (scripts/ubench_tc.cu: 62 cycles for a 32-cycle M128 N64 K16 SS-mode MMA, 26 for an 8-cycle N = 16
+//     one).  KV = 128 halves the MMA count per key (S = Q·Kᵀ as N = 128 MMAs).
 //
 // Reference semantics: HF:modeling_siglip.py:229-249,293-306 (softmax(q·kᵀ/sqrt(hd)) v, fp32 softmax, no mask).
 #include "dfd_common.cuh"
@@ -27,29 +32,26 @@ int make_tmap_qkv_4d(CUtensorMap* out, const void* base, int hd, int heads3, int
 namespace {
 
 constexpr int kQ = 128;            // query rows per work item
-constexpr int kKV = 64;            // keys per tile
-constexpr int kThreads = 320;      // loader, MMA, 8 softmax warps
 constexpr int kStagesKV = 4;
-constexpr int kTmemCols = 256;
-constexpr int kColS = 0;           // S: two fp32 [128 x 64] buffers (columns 0 and 64); P (bf16 pairs) aliases the
-                                   // first 32 columns of its S buffer
-constexpr int kColO = 128;         // O: fp32 [128 x 80]
-#ifndef DFD_ATTN_POLY_EVERY
-#define DFD_ATTN_POLY_EVERY 2
-#endif
-constexpr int kPolyEvery = DFD_ATTN_POLY_EVERY;  // every kPolyEvery-th pair of exponentials goes to the FMA pipe
+// TMEM: S = two fp32 [128 x KV] buffers at columns 0 and KV (P, bf16 pairs, aliases the first KV/2 columns of its S
+// buffer), O = fp32 [128 x 80] at column 2 KV
 
-template <int HD>
+template <int HD, int KV>
 struct WsSmem {
   static constexpr bool kTail = (HD % 64) != 0;
-  static constexpr int kMainBytes = kKV * 64 * 2;              // 64 rows x 128 B, SWIZZLE_128B
-  static constexpr int kTailBytes = kTail ? kKV * 16 * 2 : 0;  // 64 rows x 32 B, SWIZZLE_32B
-  static constexpr int kQMain = 2 * kMainBytes, kQTail = 2 * kTailBytes;
+  static constexpr int kParts = KV / 32;                       // softmax warps per lane quadrant
+  static constexpr int kThreads = (2 + 4 * kParts) * 32;       // loader, MMA, softmax warps
+  static constexpr int kCtasPerSm = KV == 64 ? 2 : 1;
+  static constexpr int kTmemCols = KV == 64 ? 256 : 512;
+  static constexpr int kMainBytes = KV * 64 * 2;               // KV rows x 128 B, SWIZZLE_128B
+  static constexpr int kTailBytes = kTail ? KV * 16 * 2 : 0;   // KV rows x 32 B, SWIZZLE_32B
+  static constexpr int kQMain = kQ * 64 * 2, kQTail = kTail ? kQ * 16 * 2 : 0;
   static constexpr int kQBytes = kQMain + kQTail;
   static constexpr int kTileBytes = kMainBytes + kTailBytes;   // one K or V tile
-  static constexpr int kXchgBytes = (2 * 2 * kQ + 2 * kQ) * 4; // row max [parity][half][row] + row sum [half][row]
+  static constexpr int kXchgBytes = (2 * kParts * kQ + kParts * kQ) * 4;  // row max [parity][part][row], row sum
   static constexpr int kBarBytes = 256;
   static constexpr int kTotal = kQBytes + 2 * kStagesKV * kTileBytes + kXchgBytes + kBarBytes + 1024;
+  static_assert(kTotal * kCtasPerSm <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) {
@@ -63,70 +65,36 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
                "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
-// 64-thread named barrier 1 + quad (immediate ids so that ptxas reserves 5 barriers, not all 16)
-__device__ __forceinline__ void pair_bar_sync(int quad) {
+// named barrier 1 + quad over the kThreads softmax threads of one lane quadrant (immediate operands so that ptxas
+// reserves 5 barriers, not all 16)
+template <int kThreadsPerQuad>
+__device__ __forceinline__ void quad_bar_sync(int quad) {
   switch (quad) {
-    case 0: asm volatile("bar.sync 1, 64;\n" ::: "memory"); break;
-    case 1: asm volatile("bar.sync 2, 64;\n" ::: "memory"); break;
-    case 2: asm volatile("bar.sync 3, 64;\n" ::: "memory"); break;
-    default: asm volatile("bar.sync 4, 64;\n" ::: "memory"); break;
+    case 0: asm volatile("bar.sync 1, %0;\n" ::"n"(kThreadsPerQuad) : "memory"); break;
+    case 1: asm volatile("bar.sync 2, %0;\n" ::"n"(kThreadsPerQuad) : "memory"); break;
+    case 2: asm volatile("bar.sync 3, %0;\n" ::"n"(kThreadsPerQuad) : "memory"); break;
+    default: asm volatile("bar.sync 4, %0;\n" ::"n"(kThreadsPerQuad) : "memory"); break;
   }
-}
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
-      "mov.b64 {%0, %1}, rd;\n\t}\n"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return d;
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-  float2 d;
-  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-      "add.rn.f32x2 rd, ra, rb;\n\t"
-      "mov.b64 {%0, %1}, rd;\n\t}\n"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
-// 2^x for a pair on the FMA pipe (the MUFU unit, 16 ex2/clk/SM, is the softmax bottleneck): round-to-nearest split
-// x = i + f, |f| <= 0.5, by the 1.5*2^23 trick, degree-3 minimax polynomial for 2^f (relative error 7.5e-5, far below
-// the 2^-9 of the bf16 P it feeds), exponent added as an integer.  x is clamped to >= -125 (result >= 2^-125 > 0).
-__device__ __forceinline__ float2 exp2_fma2(float2 x) {
-  x.x = fmaxf(x.x, -125.0f);
-  x.y = fmaxf(x.y, -125.0f);
-  const float2 t = fadd2(x, make_float2(12582912.0f, 12582912.0f));
-  const float2 fi = fadd2(t, make_float2(-12582912.0f, -12582912.0f));
-  const float2 f = ffma2(fi, make_float2(-1.0f, -1.0f), x);
-  float2 p = ffma2(make_float2(0.05517162010073662f, 0.05517162010073662f), f,
-                   make_float2(0.2426111251115799f, 0.2426111251115799f));
-  p = ffma2(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
-  p = ffma2(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
-  float2 r;
-  r.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
-  r.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
-  return r;
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(a, fmaxf(b, c)); }  // -> FMNMX3
 
-template <int HD>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int HD, int KV>
+__global__ void __launch_bounds__(WsSmem<HD, KV>::kThreads, WsSmem<HD, KV>::kCtasPerSm)
 attention_ws_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_constant__ CUtensorMap tmTail,
                     __nv_bfloat16* __restrict__ out, int64_t ldo, int N, int H, int n_items, float scale_log2) {
-  using S = WsSmem<HD>;
+  using S = WsSmem<HD, KV>;
   constexpr bool kTail = S::kTail;
+  constexpr int kKV = KV, kParts = S::kParts, kTmemCols = S::kTmemCols;
+  constexpr int kColS = 0, kColO = 2 * KV;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sQ = smem;
   uint8_t* sK = smem + S::kQBytes;                                 // [stage]
   uint8_t* sV = sK + kStagesKV * S::kTileBytes;                    // [stage]
-  float* s_max = reinterpret_cast<float*>(sV + kStagesKV * S::kTileBytes);  // [2][2][128]
-  float* s_sum = s_max + 2 * 2 * kQ;                                         // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_sum + 2 * kQ);
+  float* s_max = reinterpret_cast<float*>(sV + kStagesKV * S::kTileBytes);  // [2][kParts][128]
+  float* s_sum = s_max + 2 * kParts * kQ;                                    // [kParts][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_sum + kParts * kQ);
   uint64_t* q_full = bars;
   uint64_t* q_empty = bars + 1;
   uint64_t* kv_full = bars + 2;
@@ -154,7 +122,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 8);
+      mbar_init(&p_full[s], 4 * kParts);
     }
     mbar_init(o_done, 1);
     mbar_init(o_full, 1);
@@ -178,9 +146,9 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
         mbar_wait(q_empty, (it & 1u) ^ 1u);  // the previous item's last Q·Kᵀ has retired
         mbar_expect_tx(q_full, S::kQBytes);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          tma_load_4d(&tmMain, q_full, sQ + i * S::kMainBytes, 0, h, qt * kQ + i * kKV, b);
-          if (kTail) tma_load_4d(&tmTail, q_full, sQ + S::kQMain + i * S::kTailBytes, 64, h, qt * kQ + i * kKV, b);
+        for (int i = 0; i < kQ / 64; ++i) {  // 64-row TMA boxes
+          tma_load_4d(&tmMain, q_full, sQ + i * 8192, 0, h, qt * kQ + i * 64, b);
+          if (kTail) tma_load_4d(&tmTail, q_full, sQ + S::kQMain + i * 2048, 64, h, qt * kQ + i * 64, b);
         }
         for (int j = 0; j < T; ++j, ++g) {
           const uint32_t st = g % kStagesKV;
@@ -188,11 +156,14 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
           mbar_expect_tx(&kv_full[st], 2 * S::kTileBytes);
           uint8_t* k = sK + st * S::kTileBytes;
           uint8_t* v = sV + st * S::kTileBytes;
-          tma_load_4d(&tmMain, &kv_full[st], k, 0, H + h, j * kKV, b);
-          tma_load_4d(&tmMain, &kv_full[st], v, 0, 2 * H + h, j * kKV, b);
-          if (kTail) {
-            tma_load_4d(&tmTail, &kv_full[st], k + S::kMainBytes, 64, H + h, j * kKV, b);
-            tma_load_4d(&tmTail, &kv_full[st], v + S::kMainBytes, 64, 2 * H + h, j * kKV, b);
+#pragma unroll
+          for (int i = 0; i < kKV / 64; ++i) {  // 64-row TMA boxes
+            tma_load_4d(&tmMain, &kv_full[st], k + i * 8192, 0, H + h, j * kKV + i * 64, b);
+            tma_load_4d(&tmMain, &kv_full[st], v + i * 8192, 0, 2 * H + h, j * kKV + i * 64, b);
+            if (kTail) {
+              tma_load_4d(&tmTail, &kv_full[st], k + S::kMainBytes + i * 2048, 64, H + h, j * kKV + i * 64, b);
+              tma_load_4d(&tmTail, &kv_full[st], v + S::kMainBytes + i * 2048, 64, 2 * H + h, j * kKV + i * 64, b);
+            }
           }
         }
       }
@@ -263,26 +234,25 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
   } else {
     // ------------------------------------ softmax / output ------------------------------------
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;      // which 32 of the tile's 64 keys / which half of the O columns
+    const int part = (warp - 2) >> 2;      // which 32 of the tile's keys / which share of the O columns
     const int row = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tO = tmem_base + lane_off + kColO;
     constexpr int kGroups = HD / 8;                      // 8-column groups of O that carry data
-    constexpr int kG0 = (kGroups + 1) / 2;               // groups [0,kG0) -> half 0, [kG0,kGroups) -> half 1
-    const int gbeg = half ? kG0 : 0, gend = half ? kGroups : kG0;
-    const float2 scale2 = make_float2(scale_log2, scale_log2);
+    constexpr int kGPer = (kGroups + kParts - 1) / kParts;  // groups [part kGPer, (part + 1) kGPer) belong to `part`
+    const int gbeg = min(part * kGPer, kGroups), gend = min(gbeg + kGPer, kGroups);
     uint32_t g = 0, it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int qt = item % QT, h = (item / QT) % H, b = item / (QT * H);
       const int grow = qt * kQ + row;
       float m = -INFINITY, l = 0.f;        // m in log2 units (already multiplied by scale_log2); l = partial row sum
       for (int j = 0; j < T; ++j, ++g) {
-        const int valid = min(kKV, N - j * kKV) - 32 * half;   // valid keys among this half's 32 (may be <= 0)
+        const int valid = min(kKV, N - j * kKV) - 32 * part;   // valid keys among this part's 32 (may be <= 0)
         const uint32_t tS = tmem_base + lane_off + kColS + (g & 1u) * kKV;
         mbar_wait(&s_full[g & 1u], (g >> 1) & 1u);
         tc_fence_after();
         uint32_t s[32];
-        tmem_ld_32x32b_x32(tS + 32 * half, s);
+        tmem_ld_32x32b_x32(tS + 32 * part, s);
         tmem_ld_wait();
         if (valid < 32) {  // last tile: keys past the sequence end (zero-filled K rows) never win
 #pragma unroll
@@ -297,11 +267,13 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
 #pragma unroll
           for (int i = 0; i < 4; ++i) mx4[i] = fmax3(mx4[i], __uint_as_float(s[c + i]), __uint_as_float(s[c + 4 + i]));
         float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-        // exchange with the warp that holds the other 32 keys of the same rows
-        float* xm = s_max + (g & 1u) * 2 * kQ;
-        xm[half * kQ + row] = mx;
-        pair_bar_sync(quad);
-        mx = fmaxf(mx, xm[(half ^ 1) * kQ + row]) * scale_log2;  // scale > 0
+        // exchange with the warps that hold the other keys of the same rows
+        float* xm = s_max + (g & 1u) * kParts * kQ;
+        xm[part * kQ + row] = mx;
+        quad_bar_sync<32 * kParts>(quad);
+#pragma unroll
+        for (int q = 0; q < kParts; ++q) mx = fmaxf(mx, xm[q * kQ + row]);
+        mx *= scale_log2;  // scale > 0
         // lazy rescale: keep the old reference max unless the new one is more than 2^8 larger
         const float m_new = (mx > m + 8.0f) ? mx : m;
         const bool moved = m_new != m;
@@ -319,40 +291,37 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
           }
         }
         m = m_new;
-        float2 sum2[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-        const float2 neg_m2 = make_float2(-m, -m);
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+        const float neg_m = -m;
         uint32_t p[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          const float2 x = ffma2(make_float2(__uint_as_float(s[2 * c]), __uint_as_float(s[2 * c + 1])), scale2, neg_m2);
-          float2 e;
-          if ((c % kPolyEvery) == kPolyEvery - 1) {  // this pair on the FMA pipe
-            e = exp2_fma2(x);
-          } else {
-            e.x = fast_exp2(x.x);
-            e.y = fast_exp2(x.y);
-          }
-          sum2[c & 3] = fadd2(sum2[c & 3], e);
-          p[c] = pack_bf16x2(e.x, e.y);
+          const float p0 = fast_exp2(fmaf(__uint_as_float(s[2 * c]), scale_log2, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), scale_log2, neg_m));
+          sum4[(2 * c) & 3] += p0;
+          sum4[(2 * c + 1) & 3] += p1;
+          p[c] = pack_bf16x2(p0, p1);
         }
-        const float2 t2 = fadd2(fadd2(sum2[0], sum2[1]), fadd2(sum2[2], sum2[3]));
-        l = l * alpha + (t2.x + t2.y);
-        // the partner has loaded its S columns (it passed the named barrier), so its columns 16..31 may be overwritten
-        tmem_st_32x32b_x16(tS + 16 * half, p);
+        l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+        // every part has loaded its S columns (all passed the named barrier): P may overwrite the first KV/2 columns
+        tmem_st_32x32b_x16(tS + 16 * part, p);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g & 1u]);
       }
       // ---- O / l -> bf16 -> global ----
-      s_sum[half * kQ + row] = l;
+      s_sum[part * kQ + row] = l;
       mbar_wait(o_full, it & 1u);
       tc_fence_after();
-      pair_bar_sync(quad);
-      const float inv = 1.0f / (l + s_sum[(half ^ 1) * kQ + row]);
+      quad_bar_sync<32 * kParts>(quad);
+      float lsum = 0.f;
+#pragma unroll
+      for (int q = 0; q < kParts; ++q) lsum += s_sum[q * kQ + row];
+      const float inv = 1.0f / lsum;
       __nv_bfloat16* orow = out + ((int64_t)b * N + grow) * ldo + h * HD;
 #pragma unroll
-      for (int c = 0; c < kG0; ++c) {
+      for (int c = 0; c < kGPer; ++c) {
         const int gi = gbeg + c;
         if (gi < gend) {
           uint32_t o[8];
@@ -381,10 +350,36 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
   }
 }
 
+template <int HD, int KV>
+static int launch_ws(const void* qkv, int64_t ldqkv, __nv_bfloat16* out, int64_t ldo, int B, int N, int H, int n_items,
+                     float scale_log2, cudaStream_t st) {
+  using S = WsSmem<HD, KV>;
+  CUtensorMap tmMain, tmTail;
+  int rc = make_tmap_qkv_4d(&tmMain, qkv, HD, 3 * H, N, B, ldqkv, 64, 64, 0);
+  if (rc != DFD_OK) return rc;
+  tmTail = tmMain;
+  if (S::kTail) {
+    rc = make_tmap_qkv_4d(&tmTail, qkv, HD, 3 * H, N, B, ldqkv, 16, 64, 1);
+    if (rc != DFD_OK) return rc;
+  }
+  static bool attr = false;
+  if (!attr) {
+    DFD_CUDA(cudaFuncSetAttribute(attention_ws_kernel<HD, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr = true;
+  }
+  const int slots = S::kCtasPerSm * kNumSMs;
+  const int grid = n_items < slots ? n_items : slots;
+  attention_ws_kernel<HD, KV><<<grid, S::kThreads, S::kTotal, st>>>(tmMain, tmTail, out, ldo, N, H, n_items, scale_log2);
+  DFD_LAUNCH_CHECK();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return DFD_OK;
+}
+
 }  // namespace
 
+// kv_tile: 64 or 128 keys per tile; 0 = choose (128 once the sequence has more than two 128-key tiles' worth of work)
 int attention_ws_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
-                      float scale, cudaStream_t st) {
+                      float scale, int kv_tile, cudaStream_t st) {
   DFD_REQUIRE(qkv && out, DFD_ERR_BAD_ARG, "attention: null pointer");
   DFD_REQUIRE(B > 0 && N > 0 && H > 0, DFD_ERR_SHAPE, "attention: B, N, H must be positive");
   DFD_REQUIRE(hd == 64 || hd == 72, DFD_ERR_UNSUPPORTED, "attention: head dim %d not supported (64, 72)", hd);
@@ -392,41 +387,18 @@ int attention_ws_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, in
               "attention: bad leading dimensions");
   DFD_REQUIRE(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0), DFD_ERR_BAD_ARG,
               "attention: pointers must be 16-byte aligned");
+  DFD_REQUIRE(kv_tile == 0 || kv_tile == 64 || kv_tile == 128, DFD_ERR_BAD_ARG, "attention: kv_tile must be 0, 64 or 128");
   const int64_t items64 = (int64_t)((N + kQ - 1) / kQ) * H * B;
   DFD_REQUIRE(items64 < (1ll << 31), DFD_ERR_SHAPE, "attention: too many work items");
-  CUtensorMap tmMain, tmTail;
-  int rc = make_tmap_qkv_4d(&tmMain, qkv, hd, 3 * H, N, B, ldqkv, 64, kKV, 0);
-  if (rc != DFD_OK) return rc;
-  tmTail = tmMain;
-  if (hd == 72) {
-    rc = make_tmap_qkv_4d(&tmTail, qkv, hd, 3 * H, N, B, ldqkv, 16, kKV, 1);
-    if (rc != DFD_OK) return rc;
-  }
   const float scale_log2 = scale * 1.4426950408889634f;
   const int n_items = (int)items64;
-  const int grid = n_items < 2 * kNumSMs ? n_items : 2 * kNumSMs;
-  static bool attr[2] = {false, false};
+  if (kv_tile == 0) kv_tile = N > 256 ? 128 : 64;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  if (hd == 64) {
-    if (!attr[0]) {
-      DFD_CUDA(cudaFuncSetAttribute(attention_ws_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    WsSmem<64>::kTotal));
-      attr[0] = true;
-    }
-    attention_ws_kernel<64><<<grid, kThreads, WsSmem<64>::kTotal, st>>>(tmMain, tmTail, o, ldo, N, H, n_items,
-                                                                       scale_log2);
-  } else {
-    if (!attr[1]) {
-      DFD_CUDA(cudaFuncSetAttribute(attention_ws_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    WsSmem<72>::kTotal));
-      attr[1] = true;
-    }
-    attention_ws_kernel<72><<<grid, kThreads, WsSmem<72>::kTotal, st>>>(tmMain, tmTail, o, ldo, N, H, n_items,
-                                                                       scale_log2);
-  }
-  DFD_LAUNCH_CHECK();
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return DFD_OK;
+  if (hd == 64)
+    return kv_tile == 64 ? launch_ws<64, 64>(qkv, ldqkv, o, ldo, B, N, H, n_items, scale_log2, st)
+                         : launch_ws<64, 128>(qkv, ldqkv, o, ldo, B, N, H, n_items, scale_log2, st);
+  return kv_tile == 64 ? launch_ws<72, 64>(qkv, ldqkv, o, ldo, B, N, H, n_items, scale_log2, st)
+                       : launch_ws<72, 128>(qkv, ldqkv, o, ldo, B, N, H, n_items, scale_log2, st);
 }
 
 }  // namespace dfd

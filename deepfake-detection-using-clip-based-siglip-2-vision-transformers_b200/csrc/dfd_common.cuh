@@ -61,10 +61,10 @@ int attention_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B
                    float scale, cudaStream_t st);
 int attention_tc_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
                       float scale, cudaStream_t st);
+int attention_auto_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
+                        float scale, cudaStream_t st);
 int attention_ws_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
-                      float scale, cudaStream_t st);
-int attention_pp_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
-                      float scale, cudaStream_t st);
+                      float scale, int kv_tile, cudaStream_t st);
 int map_attention_bf16(const void* kv, int64_t ldkv, const float* q, void* out, int64_t ldo, int B, int N,
                        int H, int hd, float scale, cudaStream_t st);
 

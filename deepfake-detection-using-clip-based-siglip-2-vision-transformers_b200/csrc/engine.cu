@@ -532,7 +532,7 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
       ep.bias = l.b_qkv;
       DFD_OP(0, gemm_bf16_dispatch(e->h, D, l.w_qkv, D, e->qkv, 3 * D, M, 3 * D, D, &ep, 0, st));
     }
-    DFD_OP(1, attention_tc_bf16(e->qkv, 3 * D, e->att, D, B, N, H, hd, scale, st));
+    DFD_OP(1, attention_auto_bf16(e->qkv, 3 * D, e->att, D, B, N, H, hd, scale, st));
     {
       dfd_gemm_epilogue ep{};
       ep.bias = l.b_o;
