@@ -22,7 +22,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int kEpiWarps = 8;                       // two groups of 4 warps (one warp per TMEM lane quadrant)
 constexpr int kGemmThreads = (3 + kEpiWarps) * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 residual TMA
-constexpr int kResSlots = 2;                        // one residual chunk in flight per epilogue group (RES kernels)
+constexpr int kResSlotsMax = 4;                     // residual ring: 2 epilogue groups x up to 2 chunks in flight
 constexpr int kChunkN = 64;                         // epilogue / TMA-store granularity along N
 constexpr int kStageCBytes = BM * kChunkN * 2;      // 16 KB staging tile per epilogue group
 
@@ -48,7 +48,11 @@ struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (BN / CG) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kResBytes = RES ? kResSlots * kStageCBytes : 0;
+  // residual chunks in flight per epilogue group; group g owns slots [g kResDepth, (g + 1) kResDepth).  Measured on
+  // B200 (so400m out-projection, K = 1152): depth 2 costs one of the five 32 KB pipeline stages and is 9 % SLOWER than
+  // depth 1 (1090 vs 1197 TFLOP/s) — the mainloop needs the stages more than the epilogue needs the prefetch.
+  static constexpr int kResDepth = 1;
+  static constexpr int kResBytes = RES ? 2 * kResDepth * kStageCBytes : 0;
   static constexpr int kAvail = 227 * 1024 - 2 * kStageCBytes - kResBytes - 256 - 1024;
   static constexpr int kStages = kAvail / kStageBytes > 8 ? 8 : kAvail / kStageBytes;
   static constexpr int kTileBytes = kStages * kStageBytes;
@@ -89,8 +93,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   uint64_t* tfull_bar = empty_bar + S::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* rfull_bar = tempty_bar + 2;
-  uint64_t* rempty_bar = rfull_bar + kResSlots;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + kResSlots);
+  uint64_t* rempty_bar = rfull_bar + kResSlotsMax;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + kResSlotsMax);
   uint8_t* smem_r = smem_c + 2 * kStageCBytes;
 
   const int warp = threadIdx.x >> 5;
@@ -120,7 +124,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       mbar_init(&tempty_bar[a], kEpiWarps * CG);
     }
 #pragma unroll
-    for (int r = 0; r < kResSlots; ++r) {
+    for (int r = 0; r < kResSlotsMax; ++r) {
       mbar_init(&rfull_bar[r], 1);
       mbar_init(&rempty_bar[r], 4);
     }
@@ -210,16 +214,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     // ------------------------------- residual producer --------------------------
     if (RES && elect_one()) {
       tma_prefetch_desc(&tmR);
-      // slot g belongs to epilogue group g (chunks c ≡ g mod 2): each slot has exactly one consumer, so the parity
-      // waits stay one phase apart whatever the number of chunks per tile (a shared ring broke for odd counts)
-      uint32_t uses[kResSlots] = {0, 0};
+      // epilogue group g (chunks c ≡ g mod 2) owns a ring of kResDepth slots: each slot has exactly one consumer, so
+      // the parity waits stay one phase apart whatever the number of chunks per tile (a shared ring broke for odd
+      // counts)
+      uint32_t uses[2] = {0, 0};
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int m0 = (tile / num_n) * (BM * CG) + (int)cta_rank * BM;
         const int n0 = (tile % num_n) * BN;
         const int nvalid = min(BN / kChunkN, (N - n0 + kChunkN - 1) / kChunkN);
         for (int c = 0; c < nvalid; ++c) {
-          const int slot = c & 1;
-          mbar_wait(&rempty_bar[slot], (uses[slot]++ & 1u) ^ 1u);
+          const uint32_t u = uses[c & 1]++;
+          const int slot = (c & 1) * S::kResDepth + (int)(u % S::kResDepth);
+          mbar_wait(&rempty_bar[slot], ((u / S::kResDepth) & 1u) ^ 1u);
           mbar_expect_tx(&rfull_bar[slot], kStageCBytes);
           tma_load_2d(&tmR, &rfull_bar[slot], smem_r + slot * kStageCBytes, n0 + c * kChunkN, m0);
         }
@@ -240,7 +246,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     constexpr int kChunks = BN / kChunkN;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t res_uses = 0;  // residual chunks this group has consumed from its slot
+    uint32_t res_uses = 0;  // residual chunks this group has consumed from its ring
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       const int m0 = (tile / num_n) * (BM * CG) + (int)cta_rank * BM;
       const int n0 = (tile % num_n) * BN;
@@ -292,8 +298,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         uint4 res[8];
         if (RES) {
           // this chunk's residual tile was prefetched by the residual warp (128B-swizzled, like the C staging)
-          const int slot = grp;
-          mbar_wait(&rfull_bar[slot], res_uses++ & 1u);
+          const int slot = grp * S::kResDepth + (int)(res_uses % S::kResDepth);
+          mbar_wait(&rfull_bar[slot], (res_uses / S::kResDepth) & 1u);
+          ++res_uses;
           const uint32_t rrow = smem_u32(smem_r + slot * kStageCBytes) + static_cast<uint32_t>(row_in_tile * 128);
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
