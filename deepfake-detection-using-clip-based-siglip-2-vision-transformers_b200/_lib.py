@@ -108,6 +108,10 @@ SIGNATURES = {
     "dfd_head_fwd": (_I, [C.POINTER(HeadWeights), _P, _L, _I, _P, _P, _P, _P, _P]),
     "dfd_freq_features": (_I, [_P, _I, _P, _P, _P, _F, _I, _P, _P, _P]),
     "dfd_freq_scratch_bytes": (_L, [_I]),
+    "dfd_resample_ksize": (_I, [_I, _I]),
+    "dfd_resample_coeffs_host": (_I, [_I, _I, _P, _P, _P]),
+    "dfd_gray256_scratch_bytes": (_L, [_I, _I, _I]),
+    "dfd_gray256": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P]),
     "dfd_score_epilogue": (_I, [C.POINTER(ScoreWeights), _P, _P, _P, _I, C.POINTER(Scores), _P]),
     "dfd_fusion_fwd_bwd": (_I, [_P, _P, _P, _P, _I, _F, _P, _P, _P, _P]),
     "dfd_engine_create": (_I, [C.POINTER(EngineConfig), _I, _I, C.POINTER(_P)]),

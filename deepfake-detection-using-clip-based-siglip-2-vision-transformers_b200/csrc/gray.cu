@@ -1,0 +1,297 @@
+// gray256 on the GPU: u8 RGB images -> the 256x256 gray image every frequency feature is computed from.
+//
+// Reference (train_fusion_head_only.py:142-148, deepfake-detector-v2/app.py:736-749):
+//     ImageOps.exif_transpose(pil).convert("L") -> [cv2 CLAHE(2.0, 8x8)] -> resize((256,256), BICUBIC) -> f32 / 255
+// i.e. Pillow's integer luma, OpenCV's CLAHE and Pillow's 22-bit fixed-point antialiased bicubic resample.  All of it
+// is byte / integer work (plus four fp32 multiply-adds per pixel in CLAHE's LUT interpolation, done here in the
+// library's operation order without fused multiply-add), so the result is bit-exact with the libraries; the oracle
+// restatement is oracle/gray_ref.py, pinned against Pillow 12.2.0 / OpenCV 4.13.0.
+//
+//   luma_kernel              RGB u8 NHWC -> L u8                         (Pillow Convert.c rgb2l)
+//   clahe_lut_kernel         per (image, tile): histogram in shared memory, clip + redistribute, prefix sum -> LUT
+//   clahe_apply_kernel       per pixel: bilinear blend of the 4 surrounding tile LUTs        (OpenCV clahe.cpp)
+//   resample_rows_kernel     horizontal pass, u8 -> u8                    (Pillow Resample.c, 8bpc)
+//   resample_cols_kernel     vertical pass, u8 -> f32 / 255
+// HBM-bound streaming kernels; ~1.3 MB of traffic per 384x384 image, < 0.1 % of the detection step.
+#include "dfd_common.cuh"
+
+#include <atomic>
+#include <cmath>
+
+namespace dfd {
+
+extern std::atomic<int64_t> g_launches;
+
+namespace {
+
+constexpr int kOut = 256;
+constexpr int kPrecisionBits = 32 - 8 - 2;  // Resample.c PRECISION_BITS
+constexpr int kTiles = 8;
+
+// ---------------------------------------------------------------------------------------------------------
+// Pillow rgb2l
+// ---------------------------------------------------------------------------------------------------------
+__global__ void luma_kernel(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ L, int64_t npix) {
+  // 4 pixels (12 bytes in, 4 bytes out) per thread
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p0 = q * 4;
+  if (p0 >= npix) return;
+  if (p0 + 4 <= npix) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(rgb + p0 * 3);  // 12-byte groups are 4-byte aligned
+    const uint32_t a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+    const uint32_t px[12] = {a & 255u, (a >> 8) & 255u, (a >> 16) & 255u, a >> 24,
+                             b & 255u, (b >> 8) & 255u, (b >> 16) & 255u, b >> 24,
+                             c & 255u, (c >> 8) & 255u, (c >> 16) & 255u, c >> 24};
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t l = (px[3 * i] * 19595u + px[3 * i + 1] * 38470u + px[3 * i + 2] * 7471u + 0x8000u) >> 16;
+      out |= l << (8 * i);
+    }
+    *reinterpret_cast<uint32_t*>(L + p0) = out;
+  } else {
+    for (int64_t p = p0; p < npix; ++p)
+      L[p] = (uint8_t)((rgb[3 * p] * 19595u + rgb[3 * p + 1] * 38470u + rgb[3 * p + 2] * 7471u + 0x8000u) >> 16);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// OpenCV CLAHE (8-bit, histSize 256)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+  return i;
+}
+
+// grid (64 tiles, B), 256 threads.  tile (tw x th) of the image extended by BORDER_REFLECT_101 to a multiple of 8.
+__global__ void __launch_bounds__(256)
+clahe_lut_kernel(const uint8_t* __restrict__ L, uint8_t* __restrict__ luts, int H, int W, int tw, int th, int clip,
+                 float lut_scale) {
+  __shared__ int hist[256];
+  __shared__ int scan[256];
+  __shared__ int s_clipped;
+  const int tile = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+  const int ty = tile / kTiles, tx = tile % kTiles;
+  const uint8_t* img = L + (int64_t)b * H * W;
+  hist[t] = 0;
+  if (t == 0) s_clipped = 0;
+  __syncthreads();
+  for (int i = t; i < tw * th; i += 256) {
+    const int y = reflect101(ty * th + i / tw, H), x = reflect101(tx * tw + i % tw, W);
+    atomicAdd(&hist[img[(int64_t)y * W + x]], 1);
+  }
+  __syncthreads();
+  int h = hist[t];
+  if (clip > 0) {
+    if (h > clip) {
+      atomicAdd(&s_clipped, h - clip);
+      h = clip;
+    }
+    __syncthreads();
+    const int clipped = s_clipped;
+    const int batch = clipped / 256;
+    const int residual = clipped - batch * 256;
+    h += batch;
+    if (residual != 0) {
+      // for (i = 0; i < 256 && residual > 0; i += step, residual--) hist[i]++
+      const int step = max(256 / residual, 1);
+      if (t % step == 0 && t / step < residual) h += 1;
+    }
+  }
+  // inclusive prefix sum over the 256 bins
+  scan[t] = h;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    const int v = t >= o ? scan[t - o] : 0;
+    __syncthreads();
+    scan[t] += v;
+    __syncthreads();
+  }
+  // saturate_cast<uchar>(sum * lutScale): one fp32 multiply, round half to even, clamp
+  const int r = __float2int_rn(__fmul_rn((float)scan[t], lut_scale));
+  luts[((int64_t)b * kTiles * kTiles + tile) * 256 + t] = (uint8_t)min(max(r, 0), 255);
+}
+
+__global__ void __launch_bounds__(256)
+clahe_apply_kernel(const uint8_t* __restrict__ L, const uint8_t* __restrict__ luts, uint8_t* __restrict__ out, int H,
+                   int W, float inv_tw, float inv_th) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+  if (x >= W) return;
+  const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
+  const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+  int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
+  const float xa = __fsub_rn(txf, (float)tx1), ya = __fsub_rn(tyf, (float)ty1);
+  const float xa1 = __fsub_rn(1.0f, xa), ya1 = __fsub_rn(1.0f, ya);
+  const int tx2 = min(tx1 + 1, kTiles - 1), ty2 = min(ty1 + 1, kTiles - 1);
+  tx1 = max(tx1, 0);
+  ty1 = max(ty1, 0);
+  const int64_t pix = ((int64_t)b * H + y) * W + x;
+  const int v = L[pix];
+  const uint8_t* lb = luts + (int64_t)b * kTiles * kTiles * 256 + v;
+  const float l11 = (float)__ldg(lb + (ty1 * kTiles + tx1) * 256), l12 = (float)__ldg(lb + (ty1 * kTiles + tx2) * 256);
+  const float l21 = (float)__ldg(lb + (ty2 * kTiles + tx1) * 256), l22 = (float)__ldg(lb + (ty2 * kTiles + tx2) * 256);
+  // (l11*xa1 + l12*xa)*ya1 + (l21*xa1 + l22*xa)*ya, every operation rounded separately (no FMA) as in clahe.cpp
+  const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+  const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+  const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+  out[pix] = (uint8_t)min(max(__float2int_rn(res), 0), 255);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Pillow 8bpc resample passes.  Coefficient tables (host: dfd_resample_coeffs_host): xmin[o], count[o], kk[o][ksize].
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int clip8(int acc) { return min(max(acc >> kPrecisionBits, 0), 255); }
+
+// in [B, H, W] u8 -> out [B, H, 256] u8 ; one thread per output pixel, a block covers one row
+__global__ void __launch_bounds__(kOut)
+resample_rows_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int H, int W,
+                     const int* __restrict__ xmin, const int* __restrict__ count, const int* __restrict__ kk,
+                     int ksize) {
+  const int xx = threadIdx.x, y = blockIdx.x, b = blockIdx.y;
+  const uint8_t* row = in + ((int64_t)b * H + y) * W;
+  const int x0 = xmin[xx], n = count[xx];
+  const int* k = kk + xx * ksize;
+  int acc = 1 << (kPrecisionBits - 1);
+  for (int i = 0; i < n; ++i) acc += (int)row[x0 + i] * __ldg(k + i);
+  out[((int64_t)b * H + y) * kOut + xx] = (uint8_t)clip8(acc);
+}
+
+// in [B, H, 256] u8 -> out [B, 256, 256] f32 = u8 / 255 ; a block covers one output row
+__global__ void __launch_bounds__(kOut)
+resample_cols_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int H, const int* __restrict__ ymin,
+                     const int* __restrict__ count, const int* __restrict__ kk, int ksize) {
+  const int x = threadIdx.x, yy = blockIdx.x, b = blockIdx.y;
+  const uint8_t* img = in + (int64_t)b * H * kOut;
+  const int y0 = ymin[yy], n = count[yy];
+  const int* k = kk + yy * ksize;
+  int acc = 1 << (kPrecisionBits - 1);
+  for (int i = 0; i < n; ++i) acc += (int)img[(int64_t)(y0 + i) * kOut + x] * __ldg(k + i);
+  out[((int64_t)b * kOut + yy) * kOut + x] = __fdiv_rn((float)clip8(acc), 255.0f);
+}
+
+double bicubic_filter(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+
+}  // namespace
+
+int resample_ksize(int in_size, int out_size) {
+  double filterscale = (double)in_size / out_size;
+  if (filterscale < 1.0) filterscale = 1.0;
+  return (int)std::ceil(2.0 * filterscale) * 2 + 1;
+}
+
+}  // namespace dfd
+
+// Pillow precompute_coeffs + normalize_coeffs_8bpc for the bicubic filter over the whole axis (host, double
+// precision, the library's operation order).  kk must hold out_size * dfd_resample_ksize(in, out) ints.
+extern "C" DFD_API int dfd_resample_ksize(int in_size, int out_size) {
+  if (in_size <= 0 || out_size <= 0) return 0;
+  return dfd::resample_ksize(in_size, out_size);
+}
+
+extern "C" DFD_API int dfd_resample_coeffs_host(int in_size, int out_size, int32_t* xmin_host, int32_t* count_host,
+                                                int32_t* kk_host) {
+  DFD_REQUIRE(in_size > 0 && out_size > 0 && xmin_host && count_host && kk_host, DFD_ERR_BAD_ARG,
+              "resample_coeffs: bad argument");
+  double scale = (double)in_size / out_size, filterscale = scale;
+  if (filterscale < 1.0) filterscale = 1.0;
+  const double support = 2.0 * filterscale;
+  const int ksize = (int)std::ceil(support) * 2 + 1;
+  const double ss = 1.0 / filterscale;
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    double ww = 0.0;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double k[64];
+    DFD_REQUIRE(ksize <= 64, DFD_ERR_UNSUPPORTED, "resample_coeffs: downscale factor too large (ksize %d)", ksize);
+    for (int x = 0; x < ksize; ++x) k[x] = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      const double w = dfd::bicubic_filter((x + xmin - center + 0.5) * ss);
+      k[x] = w;
+      ww += w;
+    }
+    for (int x = 0; x < xmax; ++x)
+      if (ww != 0.0) k[x] /= ww;
+    for (int x = 0; x < ksize; ++x)
+      kk_host[xx * ksize + x] = k[x] < 0 ? (int)(-0.5 + k[x] * (1 << dfd::kPrecisionBits))
+                                         : (int)(0.5 + k[x] * (1 << dfd::kPrecisionBits));
+    xmin_host[xx] = xmin;
+    count_host[xx] = xmax;
+  }
+  return DFD_OK;
+}
+
+extern "C" DFD_API int64_t dfd_gray256_scratch_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  const int64_t hw = ((int64_t)H * W + 255) / 256 * 256;
+  // L, CLAHE output, tile LUTs, horizontally resampled image
+  return (int64_t)B * (2 * hw + dfd::kTiles * dfd::kTiles * 256 + (int64_t)H * dfd::kOut);
+}
+
+extern "C" DFD_API int dfd_gray256(const void* rgb_u8, int B, int H, int W, int clahe, const int32_t* xmin_w,
+                                   const int32_t* count_w, const int32_t* kk_w, int ksize_w, const int32_t* xmin_h,
+                                   const int32_t* count_h, const int32_t* kk_h, int ksize_h, void* scratch,
+                                   float* gray256, void* stream) {
+  using namespace dfd;
+  DFD_REQUIRE(rgb_u8 && scratch && gray256, DFD_ERR_BAD_ARG, "gray256: null pointer");
+  DFD_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535 && H <= 65535, DFD_ERR_SHAPE, "gray256: bad shape");
+  DFD_REQUIRE(xmin_w && count_w && kk_w && xmin_h && count_h && kk_h, DFD_ERR_BAD_ARG,
+              "gray256: resample tables missing");
+  DFD_REQUIRE(ksize_w == resample_ksize(W, kOut) && ksize_h == resample_ksize(H, kOut), DFD_ERR_BAD_ARG,
+              "gray256: resample tables were built for another size");
+  DFD_REQUIRE((uintptr_t)rgb_u8 % 4 == 0 && (uintptr_t)scratch % 4 == 0, DFD_ERR_BAD_ARG,
+              "gray256: pointers must be 4-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t npix = (int64_t)B * H * W;
+  const int64_t hw = ((int64_t)H * W + 255) / 256 * 256;
+  uint8_t* L = reinterpret_cast<uint8_t*>(scratch);
+  uint8_t* C = L + (int64_t)B * hw;
+  uint8_t* luts = C + (int64_t)B * hw;
+  uint8_t* rows = luts + (int64_t)B * kTiles * kTiles * 256;
+  DFD_REQUIRE((npix + 3) / 4 / 256 + 1 < (1ll << 31), DFD_ERR_SHAPE, "gray256: batch too large");
+  // images are packed back to back in L (B*H*W bytes); the per-image stride hw is only used for sizing
+  luma_kernel<<<(unsigned)(((npix + 3) / 4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(rgb_u8), L,
+                                                                        npix);
+  DFD_LAUNCH_CHECK();
+  int launches = 1;
+  const uint8_t* src = L;
+  if (clahe) {
+    int tw, th;
+    if (W % kTiles == 0 && H % kTiles == 0) {
+      tw = W / kTiles;
+      th = H / kTiles;
+    } else {
+      tw = (W + (kTiles - W % kTiles)) / kTiles;
+      th = (H + (kTiles - H % kTiles)) / kTiles;
+    }
+    const int area = tw * th;
+    const float lut_scale = 255.0f / (float)area;
+    int clip = (int)(2.0 * area / 256);
+    if (clip < 1) clip = 1;
+    clahe_lut_kernel<<<dim3(kTiles * kTiles, B), 256, 0, st>>>(L, luts, H, W, tw, th, clip, lut_scale);
+    DFD_LAUNCH_CHECK();
+    clahe_apply_kernel<<<dim3((W + 255) / 256, H, B), 256, 0, st>>>(L, luts, C, H, W, 1.0f / (float)tw,
+                                                                  1.0f / (float)th);
+    DFD_LAUNCH_CHECK();
+    launches += 2;
+    src = C;
+  }
+  // Pillow skips a pass whose size does not change; here the identity tables (count 1, weight 2^22) reproduce the
+  // input exactly, so both passes always run
+  resample_rows_kernel<<<dim3(H, B), kOut, 0, st>>>(src, rows, H, W, xmin_w, count_w, kk_w, ksize_w);
+  DFD_LAUNCH_CHECK();
+  resample_cols_kernel<<<dim3(kOut, B), kOut, 0, st>>>(rows, gray256, H, xmin_h, count_h, kk_h, ksize_h);
+  DFD_LAUNCH_CHECK();
+  g_launches.fetch_add(launches + 2, std::memory_order_relaxed);
+  return DFD_OK;
+}

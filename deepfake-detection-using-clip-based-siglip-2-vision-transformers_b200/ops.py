@@ -207,6 +207,52 @@ def freq_features(gray256: torch.Tensor, luts, eps: float = 1e-8, zscore: bool =
     return feats
 
 
+def resample_coeffs(in_size: int, out_size: int = 256):
+    """Pillow's 8bpc bicubic resample tables for one axis (host, dfd_resample_coeffs_host): (xmin, count, kk) int32
+    numpy arrays, kk [out_size, ksize].  Works without a GPU."""
+    import numpy as np
+
+    lib = _lib.load()
+    ks = lib.dfd_resample_ksize(in_size, out_size)
+    xmin, cnt = np.zeros(out_size, np.int32), np.zeros(out_size, np.int32)
+    kk = np.zeros((out_size, ks), np.int32)
+    check(lib.dfd_resample_coeffs_host(in_size, out_size, xmin.ctypes.data, cnt.ctypes.data, kk.ctypes.data))
+    return xmin, cnt, kk
+
+
+_RESAMPLE_TABLES: dict = {}
+
+
+def _resample_tables(size: int, device) -> tuple:
+    key = (size, str(device))
+    if key not in _RESAMPLE_TABLES:
+        _RESAMPLE_TABLES[key] = tuple(torch.from_numpy(a).to(device) for a in resample_coeffs(size, 256))
+    return _RESAMPLE_TABLES[key]
+
+
+def gray256_from_rgb(images: torch.Tensor, clahe: bool, scratch: Optional[torch.Tensor] = None,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """u8 RGB images [B,H,W,3] (NHWC, device) -> gray256 f32 [B,256,256] in [0,1] (dfd_gray256): Pillow 'L' luma,
+    optional OpenCV CLAHE(2.0, 8x8), Pillow bicubic resize, /255 — train_fusion_head_only.py:142-148 (clahe=True),
+    deepfake-detector-v2/app.py:736-749.  EXIF orientation is the decoder's business (apply ImageOps.exif_transpose
+    before handing pixels over, as the reference does)."""
+    _need_cuda(images)
+    assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[3] == 3 and images.is_contiguous()
+    B, H, W, _ = images.shape
+    lib = _lib.load()
+    need = lib.dfd_gray256_scratch_bytes(B, H, W)
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty((need,), dtype=torch.uint8, device=images.device)
+    xw, cw, kw = _resample_tables(W, images.device)
+    xh, ch, kh = _resample_tables(H, images.device)
+    if out is None:
+        out = torch.empty((B, 256, 256), dtype=torch.float32, device=images.device)
+    check(lib.dfd_gray256(images.data_ptr(), B, H, W, int(clahe), xw.data_ptr(), cw.data_ptr(), kw.data_ptr(),
+                          kw.shape[1], xh.data_ptr(), ch.data_ptr(), kh.data_ptr(), kh.shape[1], scratch.data_ptr(),
+                          out.data_ptr(), current_stream()))
+    return out
+
+
 class ScoreParams:
     """Device copy of FreqMLP + fusion + CORAL parameters for dfd_score_epilogue (gen 1 or 2)."""
 

@@ -2,7 +2,8 @@
 and of the extraction loops of train_fusion_head_only.py:329-347:
 
     images (u8 NHWC) ──SigLIP engine──> pooled ──classifier head──> z_sig ┐
-    gray256 (f32)    ──freq feature kernels──> 24-d features ─────────────┴─ score epilogue ──> z, CORAL, p_blend
+       └─ gray256 kernels (luma, CLAHE, bicubic 256²) ─ freq feature kernels ─> 24-d features ─┴─ score epilogue ──> z, CORAL
+    (gray256 may also be handed in, e.g. when the caller's images are not at the model resolution)
 
 One call = (7·L + 13) backbone launches + head + 2 freq kernels + 1 score-epilogue kernel, all enqueue-only on the
 current stream; `detect()` adds the pinned H2D copies and one D2H read of the packed scores, which is what the
@@ -65,11 +66,20 @@ class DetectionPipeline:
         zs = (scoring.gen == 1) if freq_zscore is None else freq_zscore
         self.freq = FreqFeatureExtractor(self.device, eps=freq_eps, zscore=zs)
         self._pin: Dict[str, torch.Tensor] = {}
+        self._gray_scratch: Optional[torch.Tensor] = None
 
     # ---- device-resident path ---------------------------------------------------------------------
-    def detect_device(self, images: torch.Tensor, gray256: torch.Tensor, resize_mode: int = 0) -> Dict[str, torch.Tensor]:
+    def detect_device(self, images: torch.Tensor, gray256: Optional[torch.Tensor] = None, resize_mode: int = 0,
+                      clahe: bool = True) -> Dict[str, torch.Tensor]:
+        """images: u8 NHWC on the device.  gray256 None = derive it from the same pixels on the device
+        (train_fusion_head_only.py:142-148 with clahe=True; app.py:736-749 with DETECT_USE_CLAHE for clahe)."""
         pooled, _ = self.engine(images, resize_mode=resize_mode)
         _, z_sig, _ = ops.head_fwd(self.head, pooled)
+        if gray256 is None:
+            need = ops._lib.load().dfd_gray256_scratch_bytes(*images.shape[:3])
+            if self._gray_scratch is None or self._gray_scratch.numel() < need:
+                self._gray_scratch = torch.empty((need,), dtype=torch.uint8, device=self.device)
+            gray256 = ops.gray256_from_rgb(images, clahe, scratch=self._gray_scratch)
         feats = self.freq.from_gray(gray256)
         out = self.scoring(z_sig, feats=feats)
         out["pooled"] = pooled
@@ -134,11 +144,13 @@ class DetectionPipeline:
         return res
 
     # ---- host-buffer path (what a caller of the reference loops sees) -----------------------------------
-    def detect(self, images_host: torch.Tensor, gray256_host: torch.Tensor, resize_mode: int = 0) -> np.ndarray:
-        """Host (ideally pinned) u8 NHWC images + f32 gray256 -> numpy [B,14] score records."""
+    def detect(self, images_host: torch.Tensor, gray256_host: Optional[torch.Tensor] = None, resize_mode: int = 0,
+               clahe: bool = True) -> np.ndarray:
+        """Host (ideally pinned) u8 NHWC images [+ f32 gray256; None = computed on the device from the same
+        pixels] -> numpy [B,14] score records."""
         img = images_host.to(self.device, non_blocking=True)
-        gray = gray256_host.to(self.device, non_blocking=True)
-        packed = self.pack(self.detect_device(img, gray, resize_mode))
+        gray = None if gray256_host is None else gray256_host.to(self.device, non_blocking=True)
+        packed = self.pack(self.detect_device(img, gray, resize_mode, clahe))
         key = f"out{packed.shape[0]}"
         if key not in self._pin:
             self._pin[key] = torch.empty(packed.shape, dtype=torch.float32).pin_memory()

@@ -159,6 +159,23 @@ DFD_API int dfd_freq_features(const float* gray256, int B, const uint8_t* lut_ba
                               void* scratch, float* feats /*[B,24]*/, void* stream);
 DFD_API int64_t dfd_freq_scratch_bytes(int B);
 
+/* gray256: u8 RGB images [B,H,W,3] (NHWC) -> the 256x256 gray image in [0,1] (fp32) the frequency features are
+ * computed from.  Replaces _pil_to_gray256_clahe / _pil_to_gray256 (train_fusion_head_only.py:142-148,
+ * deepfake-detector-v2/app.py:736-749): Pillow convert("L") (integer ITU-R 601-2 luma) -> optional
+ * cv2.createCLAHE(2.0,(8,8)).apply -> Pillow resize((256,256), BICUBIC) (22-bit fixed-point antialiased resample,
+ * horizontal pass then vertical, u8 in between) -> /255.  Bit-exact with Pillow 12.2 / OpenCV 4.13 (oracle/gray_ref.py).
+ * The per-axis coefficient tables are built on the HOST by dfd_resample_coeffs_host (double precision, Pillow's
+ * precompute_coeffs + normalize_coeffs_8bpc; no GPU needed) and passed as device arrays: xmin[256], count[256],
+ * kk[256][ksize] with ksize = dfd_resample_ksize(in_size, 256).  scratch: dfd_gray256_scratch_bytes(B,H,W). */
+DFD_API int dfd_resample_ksize(int in_size, int out_size);
+DFD_API int dfd_resample_coeffs_host(int in_size, int out_size, int32_t* xmin_host, int32_t* count_host,
+                                     int32_t* kk_host);
+DFD_API int64_t dfd_gray256_scratch_bytes(int B, int H, int W);
+DFD_API int dfd_gray256(const void* rgb_u8, int B, int H, int W, int clahe, const int32_t* xmin_w,
+                        const int32_t* count_w, const int32_t* kk_w, int ksize_w, const int32_t* xmin_h,
+                        const int32_t* count_h, const int32_t* kk_h, int ksize_h, void* scratch,
+                        float* gray256 /*[B,256,256]*/, void* stream);
+
 /* Score epilogue: FreqMLP + fusion + temperature + CORAL, one warp per sample.
  *  gen 1 (shipped siglip/ safetensors files; deepfake-detector-v2/app.py:601-628,691-709,1355-1396):
  *     z_freq = FreqMLP_G1(feats)  (SafeLayerNorm eps 1e-5 → Linear(24,64) → GELU(erf) → Linear(64,1); eval noise omitted)

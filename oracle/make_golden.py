@@ -192,6 +192,34 @@ def make_scoring():
     print("scoring_golden.npz:", {k: v.shape for k, v in g.items()})
 
 
+def make_gray():
+    """gray256 through the reference's OWN functions (Pillow + OpenCV as installed here) on the seeded images of
+    oracle/gray_ref.py: pins the restatement and is what the GPU kernels are compared with on the GPU box."""
+    from PIL import Image
+
+    from oracle import gray_ref as G
+
+    tr = extract(f"{REF}/train_fusion_head_only.py", {"_pil_to_gray256_clahe"}, base_namespace())
+    app = base_namespace()
+    app.update({"DETECT_USE_CLAHE": False})
+    extract(f"{REF}/deepfake-detector-v2/app.py", {"_pil_to_gray256"}, app)
+    outs = []
+    for (h, w, kind, seed) in G.GOLDEN_CASES:
+        pil = Image.fromarray(G.synthetic_rgb(h, w, kind, seed), "RGB")
+        for fn in (tr["_pil_to_gray256_clahe"], app["_pil_to_gray256"]):  # CLAHE on, CLAHE off
+            gray = fn(pil).numpy()
+            u8 = np.round(gray * 255.0).astype(np.uint8)
+            assert np.array_equal(u8.astype(np.float32) / np.float32(255.0), gray)
+            outs.append(u8)
+    import PIL
+    import cv2
+
+    np.savez_compressed(os.path.join(OUT, "gray_golden.npz"), gray_u8=np.stack(outs),
+                        cases=np.array([c[:2] + (c[3],) for c in G.GOLDEN_CASES], dtype=np.int32),
+                        versions=np.array([f"Pillow {PIL.__version__}", f"opencv {cv2.__version__}"]))
+    print("gray golden:", len(outs), "images")
+
+
 def make_heads():
     """Classifier heads as the reference defines them (inference_ai_human_images.py:131-138;
     train_fusion_head_only.py:84-99), fed seeded pooled embeddings."""
@@ -284,7 +312,9 @@ def make_backbone():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["scoring", "heads", "backbone"]
+    which = sys.argv[1:] or ["scoring", "heads", "backbone", "gray"]
+    if "gray" in which:
+        make_gray()
     if "scoring" in which:
         make_scoring()
     if "heads" in which:

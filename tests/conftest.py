@@ -47,6 +47,11 @@ def golden_backbone():
 
 
 @pytest.fixture(scope="session")
+def golden_gray():
+    return np.load(os.path.join(GOLDEN, "gray_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def shipped():
     """The reference's shipped G1 artefacts (siglip/*: 7.4 KB of safetensors + 2 JSON + coral_bins.npy)."""
     import json

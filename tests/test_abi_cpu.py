@@ -6,6 +6,7 @@ import os
 import re
 import subprocess
 
+import numpy as np
 import pytest
 import torch
 
@@ -171,3 +172,16 @@ def test_coral_loader_formats(tmp_path, shipped):
     assert c2 == art["cutpoints"] == scoring.fit_coral_cutpoints(lg) and t2 == 1.0
     assert __import__("numpy").load(str(tmp_path / "coral_bins.npy")).sum() == 501
     assert scoring.fit_coral_cutpoints_shipped(shipped["bins"]) == {k: float(shipped["cuts"][k]) for k in ("q25", "q50", "q75", "max")}
+
+
+def test_resample_tables_host_equal_oracle(lib):
+    """dfd_resample_coeffs_host is pure host code (double precision, Pillow's precompute_coeffs): no GPU needed."""
+    from dfd import ops
+    from oracle import gray_ref as G
+
+    for n in (384, 224, 256, 451, 97, 1024, 33, 7, 3000):
+        got, want = ops.resample_coeffs(n, 256), G.resample_coeffs(n, 256)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want)), n
+    # the identity case reproduces the input exactly: one tap of weight 2^22
+    xmin, cnt, kk = ops.resample_coeffs(256, 256)
+    assert np.array_equal(kk.sum(1), np.full(256, 1 << 22)) and int((kk != 0).sum()) == 256

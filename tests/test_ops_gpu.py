@@ -485,3 +485,46 @@ def test_fusion_fwd_bwd(golden_scoring):
     l3, g3, _ = ops.fusion_fwd_bwd(flat, torch.from_numpy(zf2).to(DEV), torch.from_numpy(zs2).to(DEV),
                                    torch.from_numpy(y2).to(DEV))
     assert abs(l3.item() - lo) < 1e-4 and np.abs(g3.cpu().numpy() - go).max() < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------
+# gray256 (Pillow luma + OpenCV CLAHE + Pillow bicubic resize): bit-exact
+# ---------------------------------------------------------------------------------------------------
+def test_gray256_matches_reference_golden(golden_gray):
+    """dfd_gray256 against the outputs of the reference's own _pil_to_gray256[_clahe] on the seeded images."""
+    from dfd import ops
+    from oracle import gray_ref as G
+
+    for i, (h, w, kind, seed) in enumerate(G.GOLDEN_CASES):
+        rgb = torch.from_numpy(G.synthetic_rgb(h, w, kind, seed)).to(DEV)
+        for j, clahe in enumerate((True, False)):
+            got = ops.gray256_from_rgb(rgb[None].contiguous(), clahe)[0].cpu().numpy()
+            want = golden_gray["gray_u8"][2 * i + j].astype(np.float32) / np.float32(255.0)
+            assert np.array_equal(got, want), (h, w, kind, clahe, int((got != want).sum()))
+
+
+@pytest.mark.parametrize("B,H,W", [(5, 384, 384), (3, 224, 224), (2, 100, 37), (1, 1, 1), (2, 600, 9)])
+def test_gray256_batched_matches_oracle(B, H, W):
+    from dfd import ops
+    from oracle import gray_ref as G
+
+    imgs = np.stack([G.synthetic_rgb(H, W, ("noise", "waves", "edges")[b % 3], 100 + b) for b in range(B)])
+    for clahe in (True, False):
+        got = ops.gray256_from_rgb(torch.from_numpy(imgs).to(DEV), clahe).cpu().numpy()
+        for b in range(B):
+            assert np.array_equal(got[b], G.gray256_from_rgb_u8(imgs[b], clahe)), (b, clahe)
+
+
+def test_gray256_full_size_properties():
+    """BASELINE batch (512 x 384 x 384): batch-permutation equivariance and range, no oracle at this size."""
+    from dfd import ops
+
+    g = torch.Generator(device=DEV).manual_seed(7)
+    img = torch.randint(0, 256, (512, 384, 384, 3), dtype=torch.uint8, device=DEV, generator=g)
+    a = ops.gray256_from_rgb(img, True)
+    perm = torch.randperm(512, device=DEV, generator=g)
+    b = ops.gray256_from_rgb(img[perm].contiguous(), True)
+    assert torch.equal(a[perm], b)
+    assert float(a.min()) >= 0.0 and float(a.max()) <= 1.0
+    k = a.double() * 255.0
+    assert float((k - k.round()).abs().max()) < 1e-4   # every value is k/255

@@ -145,3 +145,33 @@ def test_coral_known_answers(golden_scoring, shipped):
     assert np.allclose(tp, [-0.525, 3.968], atol=2e-3)
     assert S.fit_coral_script(golden_scoring["fit_logits"]) == golden_scoring["fit_cuts_script"].tolist()
     assert np.allclose(S.coral_cut_logits(None), [S.logit(v) for v in (0.32, 0.47, 0.61, 0.75)])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# gray256 restatement (Pillow luma + resample, OpenCV CLAHE)
+# ---------------------------------------------------------------------------------------------------------
+def test_gray_oracle_matches_reference_golden(golden_gray):
+    """oracle/gray_ref.py against the outputs of the reference's own _pil_to_gray256[_clahe] (make_golden.py)."""
+    from oracle import gray_ref as G
+
+    for i, (h, w, kind, seed) in enumerate(G.GOLDEN_CASES):
+        assert tuple(golden_gray["cases"][i]) == (h, w, seed)
+        rgb = G.synthetic_rgb(h, w, kind, seed)
+        for j, clahe in enumerate((True, False)):
+            want = golden_gray["gray_u8"][2 * i + j].astype(np.float32) / np.float32(255.0)
+            assert np.array_equal(G.gray256_from_rgb_u8(rgb, clahe), want), (h, w, kind, clahe)
+
+
+def test_gray_oracle_matches_installed_libraries():
+    """Stage by stage against Pillow / OpenCV as installed (skipped where they are missing)."""
+    PIL_Image = pytest.importorskip("PIL.Image")
+    cv2 = pytest.importorskip("cv2")
+    from oracle import gray_ref as G
+
+    for (h, w, kind, seed) in [(120, 200, "noise", 11), (257, 255, "waves", 12), (64, 64, "edges", 13), (8, 9, "noise", 14)]:
+        rgb = G.synthetic_rgb(h, w, kind, seed)
+        L = np.array(PIL_Image.fromarray(rgb, "RGB").convert("L"))
+        assert np.array_equal(L, G.luma_u8(rgb))
+        assert np.array_equal(np.array(PIL_Image.fromarray(L).resize((256, 256), PIL_Image.BICUBIC)),
+                              G.resize_bicubic_u8(L, 256, 256))
+        assert np.array_equal(cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8)).apply(L), G.clahe_u8(L))
