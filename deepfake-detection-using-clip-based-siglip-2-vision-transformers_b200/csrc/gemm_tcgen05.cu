@@ -66,14 +66,17 @@ struct GemmSmem {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
-// gelu_pytorch_tanh with the single-MUFU tanh (abs error ~5e-4 of a value that is rounded to bf16 anyway)
-__device__ __forceinline__ float gelu_tanh_fast(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  const float u = k0 * x * fmaf(k1 * x, x, 1.0f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;\n" : "=f"(t) : "f"(u));
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
+// gelu_pytorch_tanh with the single-MUFU tanh (abs error ~5e-4 of a value that is rounded to bf16 anyway),
+// for a pair: 0.5 x (1 + tanh(x (k0 + k0 k1 x²))) in five packed FP instructions + two MUFU.TANH
+__device__ __forceinline__ float2 gelu_tanh_fast2(float2 x) {
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const float2 w = ffma2(fmul2(x, x), make_float2(k01, k01), make_float2(k0, k0));
+  const float2 u = fmul2(x, w);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;\n" : "=f"(t.x) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;\n" : "=f"(t.y) : "f"(u.y));
+  const float2 hx = fmul2(x, make_float2(0.5f, 0.5f));
+  return ffma2(hx, t, hx);
 }
 
 template <int BN, int CG, int RES>
@@ -316,53 +319,62 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           if (lane == 0) mbar_arrive(&rempty_bar[slot]);
         }
         uint4 o[8];
+        // two fp32 lanes per instruction (FFMA2 / FADD2 / FMUL2): the fused epilogues (LayerNorm fold + bias + GELU)
+        // were issue bound — fc1 held the tensor pipe at 70 % (profiles/r01_gemm_full.md)
+        const float2 nmean2 = make_float2(-ln_mean, -ln_mean), rstd2 = make_float2(ln_rstd, ln_rstd);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const int cc = c0 + g * 8;
-          float v[8];
+          float2 v[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+          for (int j = 0; j < 4; ++j)
+            v[j] = make_float2(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
           if (cc < N) {
             if (epi.ln_colsum != nullptr) {
               const float4 s0 = __ldg(reinterpret_cast<const float4*>(epi.ln_colsum + cc));
               const float4 s1 = __ldg(reinterpret_cast<const float4*>(epi.ln_colsum + cc + 4));
-              const float cs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+              const float2 cs[4] = {{s0.x, s0.y}, {s0.z, s0.w}, {s1.x, s1.y}, {s1.z, s1.w}};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = ln_rstd * (v[j] - ln_mean * cs[j]);
+              for (int j = 0; j < 4; ++j) v[j] = fmul2(rstd2, ffma2(nmean2, cs[j], v[j]));
             }
             if (epi.bias != nullptr) {
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + cc));
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + cc + 4));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              v[0] = fadd2(v[0], make_float2(b0.x, b0.y));
+              v[1] = fadd2(v[1], make_float2(b0.z, b0.w));
+              v[2] = fadd2(v[2], make_float2(b1.x, b1.y));
+              v[3] = fadd2(v[3], make_float2(b1.z, b1.w));
             }
             if (epi.act == 1) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_fast(v[j]);
+              for (int j = 0; j < 4; ++j) v[j] = gelu_tanh_fast2(v[j]);
             }
             if (pos_row != nullptr) {
               const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos_row + cc));
               const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos_row + cc + 4));
-              v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
-              v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+              v[0] = fadd2(v[0], make_float2(p0.x, p0.y));
+              v[1] = fadd2(v[1], make_float2(p0.z, p0.w));
+              v[2] = fadd2(v[2], make_float2(p1.x, p1.y));
+              v[3] = fadd2(v[3], make_float2(p1.z, p1.w));
             }
             if (RES) {
-              const float2 a0 = unpack_bf16x2(res[g].x), a1 = unpack_bf16x2(res[g].y),
-                           a2 = unpack_bf16x2(res[g].z), a3 = unpack_bf16x2(res[g].w);
-              v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
-              v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
+              v[0] = fadd2(v[0], unpack_bf16x2(res[g].x));
+              v[1] = fadd2(v[1], unpack_bf16x2(res[g].y));
+              v[2] = fadd2(v[2], unpack_bf16x2(res[g].z));
+              v[3] = fadd2(v[3], unpack_bf16x2(res[g].w));
             }
           }
-          o[g].x = pack_bf16x2(v[0], v[1]);
-          o[g].y = pack_bf16x2(v[2], v[3]);
-          o[g].z = pack_bf16x2(v[4], v[5]);
-          o[g].w = pack_bf16x2(v[6], v[7]);
+          o[g].x = pack_bf16x2(v[0].x, v[0].y);
+          o[g].y = pack_bf16x2(v[1].x, v[1].y);
+          o[g].z = pack_bf16x2(v[2].x, v[2].y);
+          o[g].w = pack_bf16x2(v[3].x, v[3].y);
           if (epi.stats_out != nullptr && cc < N) {
             const float2 q0 = unpack_bf16x2(o[g].x), q1 = unpack_bf16x2(o[g].y),
                          q2 = unpack_bf16x2(o[g].z), q3 = unpack_bf16x2(o[g].w);
-            st_sum += ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
-            st_sq += ((q0.x * q0.x + q0.y * q0.y) + (q1.x * q1.x + q1.y * q1.y)) +
-                     ((q2.x * q2.x + q2.y * q2.y) + (q3.x * q3.x + q3.y * q3.y));
+            const float2 sm = fadd2(fadd2(q0, q1), fadd2(q2, q3));
+            const float2 sq = ffma2(q0, q0, ffma2(q1, q1, ffma2(q2, q2, fmul2(q3, q3))));
+            st_sum += sm.x + sm.y;
+            st_sq += sq.x + sq.y;
           }
         }
         // staging tile free? (the previous TMA store of this group has finished reading it)
