@@ -53,16 +53,22 @@ struct GemmSmem {
   // depth 1 (1090 vs 1197 TFLOP/s) — the mainloop needs the stages more than the epilogue needs the prefetch.
   static constexpr int kResDepth = 1;
   static constexpr int kResBytes = RES ? 2 * kResDepth * kStageCBytes : 0;
-  static constexpr int kAvail = 227 * 1024 - 2 * kStageCBytes - kResBytes - 256 - 1024;
+  static constexpr int kColTabBytes = 2 * 2 * kChunkN * 4;  // per epilogue group: 64 LayerNorm column sums + 64 biases
+  static constexpr int kAvail = 227 * 1024 - 2 * kStageCBytes - kResBytes - 256 - kColTabBytes - 1024;
   static constexpr int kStages = kAvail / kStageBytes > 8 ? 8 : kAvail / kStageBytes;
   static constexpr int kTileBytes = kStages * kStageBytes;
   static constexpr int kCBytes = 2 * kStageCBytes + kResBytes;  // C staging (2) then the residual ring
   static constexpr int kBarBytes = 256;
-  static constexpr int kTotal = kTileBytes + kCBytes + kBarBytes + 1024;  // +1024 alignment slack
+  static constexpr int kTotal = kTileBytes + kCBytes + kBarBytes + kColTabBytes + 1024;  // +1024 alignment slack
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -99,6 +105,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   uint64_t* rempty_bar = rfull_bar + kResSlotsMax;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + kResSlotsMax);
   uint8_t* smem_r = smem_c + 2 * kStageCBytes;
+  float* col_tab = reinterpret_cast<float*>(smem + S::kTileBytes + S::kCBytes + S::kBarBytes);  // [group][colsum 64 | bias 64]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -250,6 +257,33 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t res_uses = 0;  // residual chunks this group has consumed from its ring
+
+    // Per-column epilogue parameters (LayerNorm column sums, bias) of the group's CURRENT chunk live in a 512-byte
+    // shared table; the values of its NEXT chunk are fetched with one LDG per thread while the current chunk is being
+    // computed and stored into the table between the group's two barriers.  (Reading them with __ldg per 8-column
+    // group left every such group waiting on the long scoreboard: 20 % of all samples of the fc1 GEMM.)
+    float* tab = col_tab + grp * (2 * kChunkN);
+    const int tab_t = (ew & 3) * 32 + lane;           // 0..127 within the group
+    const float* tab_src = (tab_t < kChunkN) ? epi.ln_colsum : epi.bias;
+    const int tab_e = tab_t & (kChunkN - 1);
+    auto next_chunk_col = [&](int tile, int c) -> int {  // first column of the group's chunk after (tile, c); -1: none
+      c += 2;
+      while (tile < num_tiles) {
+        const int n0t = (tile % num_n) * BN;
+        if (c < min(kChunks, (N - n0t + kChunkN - 1) / kChunkN)) return n0t + c * kChunkN;
+        tile += tile_step;
+        c = grp;
+      }
+      return -1;
+    };
+    auto fetch_col = [&](int col0) -> float {
+      const int col = col0 + tab_e;
+      return (tab_src != nullptr && col0 >= 0 && col < N) ? __ldg(tab_src + col) : 0.f;
+    };
+    tab[tab_t] = fetch_col(next_chunk_col(first_tile, grp - 2));
+    named_bar_sync(1 + grp, 128);
+    const uint32_t tab_addr = smem_u32(tab);
+
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       const int m0 = (tile / num_n) * (BM * CG) + (int)cta_rank * BM;
       const int n0 = (tile % num_n) * BN;
@@ -289,6 +323,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * kChunkN + 32),
                            *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
         tmem_ld_wait();
+        const float tab_next = fetch_col(next_chunk_col(tile, c));  // consumed after the first barrier below
         if (c + 2 >= nvalid) {
           // last chunk of this group for this tile: the accumulator stage can go back to the MMA warp
           tc_fence_before();
@@ -331,15 +366,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             v[j] = make_float2(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
           if (cc < N) {
             if (epi.ln_colsum != nullptr) {
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(epi.ln_colsum + cc));
-              const float4 s1 = __ldg(reinterpret_cast<const float4*>(epi.ln_colsum + cc + 4));
+              const float4 s0 = lds_f4(tab_addr + static_cast<uint32_t>(g * 32));
+              const float4 s1 = lds_f4(tab_addr + static_cast<uint32_t>(g * 32 + 16));
               const float2 cs[4] = {{s0.x, s0.y}, {s0.z, s0.w}, {s1.x, s1.y}, {s1.z, s1.w}};
 #pragma unroll
               for (int j = 0; j < 4; ++j) v[j] = fmul2(rstd2, ffma2(nmean2, cs[j], v[j]));
             }
             if (epi.bias != nullptr) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + cc));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + cc + 4));
+              const float4 b0 = lds_f4(tab_addr + static_cast<uint32_t>(kChunkN * 4 + g * 32));
+              const float4 b1 = lds_f4(tab_addr + static_cast<uint32_t>(kChunkN * 4 + g * 32 + 16));
               v[0] = fadd2(v[0], make_float2(b0.x, b0.y));
               v[1] = fadd2(v[1], make_float2(b0.z, b0.w));
               v[2] = fadd2(v[2], make_float2(b1.x, b1.y));
@@ -380,6 +415,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         // staging tile free? (the previous TMA store of this group has finished reading it)
         if (store_warp && elect_one()) tma_store_wait_read<0>();
         named_bar_sync(1 + grp, 128);
+        tab[tab_t] = tab_next;  // every thread of the group is past its reads of the current chunk's parameters
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const uint32_t addr = stage_row + static_cast<uint32_t>((g ^ sw) << 4);
