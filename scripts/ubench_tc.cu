@@ -72,6 +72,75 @@ __global__ void __launch_bounds__(128, 2) mma_bench(MmaCase c, int reps, int nac
   }
 }
 
+// The attention kernel's per-tile MMA mix, issued back to back with no softmax in between:
+//   variant 0: 5 x (SS N=64 -> S)            then 4 x (TS N=64 -> O, TS N=16 -> O tail)      (64-key tile, as shipped)
+//   variant 1: 5 x (SS N=64 -> S)            then 4 x (TS N=80 -> O)                         (single P.V MMA per k-step)
+//   variant 2: 5 x (SS N=128 -> S)           then 8 x (TS N=64, TS N=16)                     (128-key tile)
+//   variant 3: 5 x (TS N=64 -> S, Q in TMEM) then 4 x (TS N=80 -> O)
+template <int mode>
+__global__ void __launch_bounds__(128, 2) seq_bench(int variant, int reps, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < 80 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  if (threadIdx.x < 32) tmem_alloc<256>(&slot);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = slot;
+  bool issuer = (threadIdx.x < 32) ? elect_one() : false;
+  if (issuer) {
+    const uint32_t q = smem_u32(smem), k = smem_u32(smem + 20480), v = smem_u32(smem + 40960);
+    const uint64_t dQ = umma_desc(q, 16, 1024, 2), dQt = umma_desc(q + 16384, 16, 256, 6);
+    const uint64_t dK = umma_desc(k, 16, 1024, 2), dKt = umma_desc(k + 16384, 16, 256, 6);
+    const uint64_t dV = umma_desc(v, 16, 1024, 2), dVt = umma_desc(v + 16384, 16, 256, 6);
+    const uint64_t dV80 = umma_desc(v, 4096, 256, 6);
+    const uint32_t tS = tm, tO = tm + 128, tQ = tm + 216;
+    const int nqk = variant == 2 ? 128 : 64;
+    const uint32_t id_qk = umma_idesc_bf16_major(128, nqk, 0, 0);
+    const uint32_t id_pv = umma_idesc_bf16_major(128, 64, 0, 1), id_pvt = umma_idesc_bf16_major(128, 16, 0, 1);
+    const uint32_t id_pv80 = umma_idesc_bf16_major(128, 80, 0, 1);
+    const int ksteps = variant == 2 ? 8 : 4;
+    auto tile = [&]() {
+      for (int kk = 0; kk < 4; ++kk) {
+        if (variant == 3) umma_bf16_ts(tS, tQ + 8 * kk, dK + 2 * kk, id_qk, kk != 0);
+        else umma_bf16_ss(tS, dQ + 2 * kk, dK + 2 * kk, id_qk, kk != 0);
+      }
+      if (variant == 3) umma_bf16_ts(tS, tQ + 32, dKt, id_qk, 1);
+      else umma_bf16_ss(tS, dQt, dKt, id_qk, 1);
+      for (int kk = 0; kk < ksteps; ++kk) {
+        if (variant == 1 || variant == 3) {
+          umma_bf16_ts(tO, tS + 8 * kk, dV80 + kk * 32, id_pv80, 1);
+        } else {
+          umma_bf16_ts(tO, tS + 8 * kk, dV + kk * 128, id_pv, 1);
+          umma_bf16_ts(tO + 64, tS + 8 * kk, dVt + kk * 32, id_pvt, 1);
+        }
+      }
+    };
+    tile();
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) tile();
+    umma_commit(&bar);
+    mbar_wait(&bar, 1);
+    out[blockIdx.x] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    tmem_dealloc<256>(tm);
+  }
+}
+
 // every warp loads `cols` fp32 columns of its lane quadrant `reps` times
 template <int X>
 __global__ void __launch_bounds__(512, 1) ldtm_bench(int reps, long long* out, uint32_t* sink) {
@@ -166,6 +235,17 @@ int main() {
       }
     }
   }
+  cudaFuncSetAttribute(seq_bench<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  for (int variant = 0; variant < 4; ++variant)
+    for (int ctas : {148, 296}) {
+      seq_bench<1><<<ctas, 128, 100 * 1024>>>(variant, 500, d_out);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("seq variant %d: %s\n", variant, cudaGetErrorString(e)); return 1; }
+      cudaMemcpy(h.data(), d_out, sizeof(long long), cudaMemcpyDeviceToHost);
+      const double keys = variant == 2 ? 128 : 64;
+      printf("attention MMA mix variant %d ctas/SM=%d: %7.1f cycles per tile per CTA = %6.1f cycles per 64 keys per SM\n", variant,
+             ctas / 148, (double)h[0] / 500, (double)h[0] / 500 / (keys / 64) / (296 / ctas == 1 ? 2.0 : 1.0) * (ctas == 296 ? 2.0 : 1.0) / 2.0 * (ctas == 296 ? 1.0 : 2.0));
+    }
   for (int warps : {4, 8, 16}) {
     ldtm_bench<32><<<148, warps * 32>>>(reps, d_out, sink);
     cudaDeviceSynchronize();
