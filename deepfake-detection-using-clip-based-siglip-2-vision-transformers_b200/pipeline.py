@@ -56,7 +56,7 @@ def head_params_from_state(sd: Dict[str, torch.Tensor], dim: int, device) -> "op
 class DetectionPipeline:
     def __init__(self, arch: VisionArch | str, backbone_state: Dict[str, torch.Tensor],
                  head_state: Dict[str, torch.Tensor], scoring: ScoringStack, device: int = 0, max_batch: int = 64,
-                 freq_eps: float = EPS_TRAINER, freq_zscore: Optional[bool] = None, fuse_ln: bool = False):
+                 freq_eps: float = EPS_TRAINER, freq_zscore: Optional[bool] = None, fuse_ln: bool = True):
         self.arch = ARCHS[arch] if isinstance(arch, str) else arch
         self.device = torch.device("cuda", device)
         self.engine = SiglipEngine(self.arch, device, max_batch, fuse_ln=fuse_ln).load_state_dict(backbone_state)

@@ -131,7 +131,8 @@ def test_base_224_vs_hf_golden(golden_backbone):
     assert (last.float().cpu()[:, ::7, ::5] - gl).abs().max() <= 0.04 * gl.abs().max() + 0.05
 
 
-def test_base_224_logits(golden_backbone):
+@pytest.mark.parametrize("fuse_ln", [False, True])  # True = the configuration bench.py measures
+def test_base_224_logits(golden_backbone, fuse_ln):
     """BASELINE gate 'logits within 1e-2 absolute in bf16' at a named architecture: classifier heads H-A / H-B applied
     to the engine's pooled output vs the same heads (oracle, fp32) applied to the HF fp32 golden embedding."""
     from dfd import ops
@@ -139,7 +140,7 @@ def test_base_224_logits(golden_backbone):
     from oracle import siglip_ref as R
 
     name = "siglip2-base-patch16-224"
-    eng, _ = _engine(name, 8)
+    eng, _ = _engine(name, 8, fuse_ln=fuse_ln)
     pooled, _ = eng(R.synthetic_images(2, 224, 0).to(DEV))
     gold = torch.from_numpy(golden_backbone[name + "/pooled"])
     for kind, eps in (("A", 0.0), ("B", 1e-6)):
@@ -149,12 +150,13 @@ def test_base_224_logits(golden_backbone):
         assert (z - z_ref).abs().max() < 1e-2, (kind, z, z_ref)
 
 
-def test_so400m_384_vs_hf_golden(golden_backbone):
+@pytest.mark.parametrize("fuse_ln", [False, True])
+def test_so400m_384_vs_hf_golden(golden_backbone, fuse_ln):
     """SigLIP-2 so400m-patch14-384 (BASELINE config 3: 729 tokens, hd 72, I 4304), B=1, against HF fp32."""
     from oracle import siglip_ref as R
 
     name = "siglip2-so400m-patch14-384"
-    eng, sd = _engine(name, 2)
+    eng, sd = _engine(name, 2, fuse_ln=fuse_ln)
     img = R.synthetic_images(1, 384, 0)
     pooled, last = eng(img.to(DEV), want_last_hidden=True)
     torch.cuda.synchronize()
