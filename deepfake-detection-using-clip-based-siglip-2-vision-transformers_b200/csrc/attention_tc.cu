@@ -122,57 +122,77 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------------ MMA issuer ------------------------------------
+    // One thread issues ~13 MMAs and 3-4 commits per key tile; the first version of this loop spent ~110 scalar /
+    // uniform-datapath instructions per tile on descriptor arithmetic, dynamic stage indexing and a runtime k-step loop
+    // and was ISSUE bound (ncu: the thread was busy ~1450 cycles per tile while the tensor pipe needs ~960).  Now the
+    // key-tile loop is unrolled by the ring depth, so stage / S-buffer indices, descriptors and the full-tile shapes
+    // are compile-time constants.
     if (elect_one()) {
       const uint32_t tO = tmem_base + kColO;
       const uint64_t dQ = umma_desc(smem_u32(sQ), 16, 1024, 2);
       const uint64_t dQt = umma_desc(smem_u32(sQ + S::kQMain), 16, 256, 6);
-      // S_j = Q · K_j^T into S buffer j&1 (runs one tile ahead of the softmax)
-      auto issue_qk = [&](int j) {
-        const int st = j % kStagesKV;
-        const int n16 = (min(kKV, N - j * kKV) + 15) & ~15;
+      const uint64_t dK0 = umma_desc(smem_u32(sK), 16, 1024, 2);
+      const uint64_t dKt0 = umma_desc(smem_u32(sK + S::kMainBytes), 16, 256, 6);
+      const uint64_t dV0 = umma_desc(smem_u32(sV), 16, 1024, 2);  // MN-major, 8-key groups 1024 B apart
+      const uint64_t dVt0 = umma_desc(smem_u32(sV + S::kMainBytes), 16, 256, 6);
+      constexpr uint64_t kStageStep = S::kTileBytes >> 4;        // descriptor start addresses count 16-byte units
+      constexpr uint32_t idesc_qk_full = umma_idesc_bf16_major(kQ, kKV, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16_major(kQ, 64, 0, 1);
+      constexpr uint32_t idesc_pvt = umma_idesc_bf16_major(kQ, 16, 0, 1);
+      // S_j = Q · K_j^T into S buffer sb (runs up to two tiles ahead of the softmax); st, sb are constants after unrolling
+      auto issue_qk = [&](int j, int st, int sb) {
         mbar_wait(&kv_full[st], (j / kStagesKV) & 1u);
         tc_fence_after();
-        const uint32_t tS = tmem_base + kColS + static_cast<uint32_t>((j & 1) * kKV);
-        const uint32_t kaddr = smem_u32(sK + st * S::kTileBytes);
-        const uint64_t dK = umma_desc(kaddr, 16, 1024, 2);
-        const uint32_t idesc_qk = umma_idesc_bf16_major(kQ, n16, 0, 0);
+        const uint32_t tS = tmem_base + kColS + static_cast<uint32_t>(sb * kKV);
+        const uint64_t dK = dK0 + st * kStageStep;
+        const int valid = N - j * kKV;
+        const uint32_t idesc_qk = valid >= kKV ? idesc_qk_full : umma_idesc_bf16_major(kQ, (valid + 15) & ~15, 0, 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16_ss(tS, dQ + static_cast<uint64_t>(2 * k), dK + static_cast<uint64_t>(2 * k), idesc_qk, k != 0);
-        if (kTail) {
-          const uint64_t dKt = umma_desc(kaddr + S::kMainBytes, 16, 256, 6);
-          umma_bf16_ss(tS, dQt, dKt, idesc_qk, 1u);
-        }
-        umma_commit(&s_full[j & 1]);
+        if (kTail) umma_bf16_ss(tS, dQt, dKt0 + st * kStageStep, idesc_qk, 1u);
+        umma_commit(&s_full[sb]);
       };
       mbar_wait(q_full, 0);
-      issue_qk(0);
-      if (T > 1) issue_qk(1);
-      for (int j = 0; j < T; ++j) {
-        const int st = j % kStagesKV;
-        const int n16 = (min(kKV, N - j * kKV) + 15) & ~15;
-        // ---- O += P_j · V_j ----  (P_j written by the softmax warps into the S_j columns)
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1u);
-        tc_fence_after();
-        const uint32_t tP = tmem_base + kColS + static_cast<uint32_t>((j & 1) * kKV);
-        const uint32_t vaddr = smem_u32(sV + st * S::kTileBytes);
-        const uint64_t dV = umma_desc(vaddr, 16, 1024, 2);  // MN-major, 8-key groups 1024 B apart
-        const uint64_t dVt = umma_desc(vaddr + S::kMainBytes, 16, 256, 6);
-        constexpr uint32_t idesc_pv = umma_idesc_bf16_major(kQ, 64, 0, 1);
-        constexpr uint32_t idesc_pvt = umma_idesc_bf16_major(kQ, 16, 0, 1);
-        const int ksteps = n16 >> 4;
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint32_t acc = (j | kk) != 0 ? 1u : 0u;
-          // 16 keys per step: 16 rows x 128 B (main) / 16 rows x 32 B (tail); P: 8 packed columns per step
-          umma_bf16_ts(tO, tP + static_cast<uint32_t>(8 * kk), dV + static_cast<uint64_t>(kk * 128), idesc_pv, acc);
-          if (kTail)
-            umma_bf16_ts(tO + 64, tP + static_cast<uint32_t>(8 * kk), dVt + static_cast<uint64_t>(kk * 32), idesc_pvt,
-                         acc);
+      issue_qk(0, 0, 0);
+      if (T > 1) issue_qk(1, 1, 1);
+      for (int j4 = 0; j4 < T; j4 += kStagesKV) {
+#pragma unroll
+        for (int u = 0; u < kStagesKV; ++u) {
+          const int j = j4 + u;
+          if (j < T) {
+            // ---- O += P_j · V_j ----  (P_j written by the softmax warps into the S_j columns)
+            mbar_wait(&p_full[u & 1], (j >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t tP = tmem_base + kColS + static_cast<uint32_t>((u & 1) * kKV);
+            const uint64_t dV = dV0 + u * kStageStep, dVt = dVt0 + u * kStageStep;
+            const int valid = N - j * kKV;
+            if (valid >= kKV) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                // 16 keys per step: 16 rows x 128 B (main) / 16 rows x 32 B (tail); P: 8 packed columns per step
+                const uint32_t acc = (kk != 0) ? 1u : (j != 0 ? 1u : 0u);
+                umma_bf16_ts(tO, tP + static_cast<uint32_t>(8 * kk), dV + static_cast<uint64_t>(kk * 128), idesc_pv, acc);
+                if (kTail)
+                  umma_bf16_ts(tO + 64, tP + static_cast<uint32_t>(8 * kk), dVt + static_cast<uint64_t>(kk * 32),
+                               idesc_pvt, acc);
+              }
+            } else {
+              const int ksteps = (valid + 15) >> 4;
+              for (int kk = 0; kk < ksteps; ++kk) {
+                const uint32_t acc = (j | kk) != 0 ? 1u : 0u;
+                umma_bf16_ts(tO, tP + static_cast<uint32_t>(8 * kk), dV + static_cast<uint64_t>(kk * 128), idesc_pv, acc);
+                if (kTail)
+                  umma_bf16_ts(tO + 64, tP + static_cast<uint32_t>(8 * kk), dVt + static_cast<uint64_t>(kk * 32),
+                               idesc_pvt, acc);
+              }
+            }
+            umma_commit(&kv_empty[u]);  // K/V stage back to the loader once these MMAs retire
+            umma_commit(o_done);
+            // the tensor pipe executes in issue order, so S_{j&1} / P_j are free for tile j+2 right after P_j·V_j
+            if (j + 2 < T) issue_qk(j + 2, (u + 2) % kStagesKV, u & 1);
+          }
         }
-        umma_commit(&kv_empty[st]);  // K/V stage back to the loader once these MMAs retire
-        umma_commit(o_done);
-        // the tensor pipe executes in issue order, so S_{j&1} / P_j are free for tile j+2 right after P_j·V_j
-        if (j + 2 < T) issue_qk(j + 2);
       }
       umma_commit(o_full);
     }
