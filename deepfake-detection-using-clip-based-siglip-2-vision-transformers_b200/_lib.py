@@ -111,6 +111,9 @@ SIGNATURES = {
     "dfd_resample_ksize": (_I, [_I, _I]),
     "dfd_resample_coeffs_host": (_I, [_I, _I, _P, _P, _P]),
     "dfd_gray256_scratch_bytes": (_L, [_I, _I, _I]),
+    "dfd_resample_ksize_filter": (_I, [_I, _I, _I]),
+    "dfd_resample_coeffs_filter_host": (_I, [_I, _I, _I, _P, _P, _P]),
+    "dfd_resize_u8": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P]),
     "dfd_gray256": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P]),
     "dfd_score_epilogue": (_I, [C.POINTER(ScoreWeights), _P, _P, _P, _I, C.POINTER(Scores), _P]),
     "dfd_fusion_fwd_bwd": (_I, [_P, _P, _P, _P, _I, _F, _P, _P, _P, _P]),

@@ -170,6 +170,42 @@ resample_cols_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, in
   out[((int64_t)b * kOut + yy) * kOut + x] = __fdiv_rn((float)clip8(acc), 255.0f);
 }
 
+// Generic Pillow 8bpc passes for interleaved images (C = 1 or 3 channels): used by dfd_resize_u8
+// in [B, H, W, C] -> out [B, H, OW, C]
+__global__ void __launch_bounds__(256)
+resize_rows_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int H, int W, int OW, int C,
+                   const int* __restrict__ xmin, const int* __restrict__ count, const int* __restrict__ kk, int ksize) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;  // (xx, c) within the output row
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (e >= OW * C) return;
+  const int xx = e / C, c = e - xx * C;
+  const uint8_t* row = in + ((int64_t)b * H + y) * W * C + c;
+  const int x0 = xmin[xx], n = count[xx];
+  const int* k = kk + xx * ksize;
+  int acc = 1 << (kPrecisionBits - 1);
+  for (int i = 0; i < n; ++i) acc += (int)row[(x0 + i) * C] * __ldg(k + i);
+  out[((int64_t)b * H + y) * OW * C + e] = (uint8_t)clip8(acc);
+}
+// in [B, H, OW, C] -> out [B, OH, OW, C]
+__global__ void __launch_bounds__(256)
+resize_cols_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int H, int OH, int OWC,
+                   const int* __restrict__ ymin, const int* __restrict__ count, const int* __restrict__ kk, int ksize) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yy = blockIdx.y, b = blockIdx.z;
+  if (e >= OWC) return;
+  const uint8_t* img = in + (int64_t)b * H * OWC + e;
+  const int y0 = ymin[yy], n = count[yy];
+  const int* k = kk + yy * ksize;
+  int acc = 1 << (kPrecisionBits - 1);
+  for (int i = 0; i < n; ++i) acc += (int)img[(int64_t)(y0 + i) * OWC] * __ldg(k + i);
+  out[((int64_t)b * OH + yy) * OWC + e] = (uint8_t)clip8(acc);
+}
+
+double bilinear_filter(double x) {
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return 1.0 - x;
+  return 0.0;
+}
 double bicubic_filter(double x) {
   const double a = -0.5;
   if (x < 0.0) x = -x;
@@ -180,10 +216,12 @@ double bicubic_filter(double x) {
 
 }  // namespace
 
-int resample_ksize(int in_size, int out_size) {
+// filter: DFD_FILTER_BILINEAR (support 1) or DFD_FILTER_BICUBIC (support 2)
+int resample_ksize(int in_size, int out_size, int filter = DFD_FILTER_BICUBIC) {
   double filterscale = (double)in_size / out_size;
   if (filterscale < 1.0) filterscale = 1.0;
-  return (int)std::ceil(2.0 * filterscale) * 2 + 1;
+  const double support = (filter == DFD_FILTER_BILINEAR ? 1.0 : 2.0) * filterscale;
+  return (int)std::ceil(support) * 2 + 1;
 }
 
 }  // namespace dfd
@@ -195,13 +233,25 @@ extern "C" DFD_API int dfd_resample_ksize(int in_size, int out_size) {
   return dfd::resample_ksize(in_size, out_size);
 }
 
+extern "C" DFD_API int dfd_resample_ksize_filter(int in_size, int out_size, int filter) {
+  if (in_size <= 0 || out_size <= 0 || (filter != DFD_FILTER_BILINEAR && filter != DFD_FILTER_BICUBIC)) return 0;
+  return dfd::resample_ksize(in_size, out_size, filter);
+}
+
 extern "C" DFD_API int dfd_resample_coeffs_host(int in_size, int out_size, int32_t* xmin_host, int32_t* count_host,
                                                 int32_t* kk_host) {
+  return dfd_resample_coeffs_filter_host(in_size, out_size, DFD_FILTER_BICUBIC, xmin_host, count_host, kk_host);
+}
+
+extern "C" DFD_API int dfd_resample_coeffs_filter_host(int in_size, int out_size, int filter, int32_t* xmin_host,
+                                                       int32_t* count_host, int32_t* kk_host) {
   DFD_REQUIRE(in_size > 0 && out_size > 0 && xmin_host && count_host && kk_host, DFD_ERR_BAD_ARG,
               "resample_coeffs: bad argument");
+  DFD_REQUIRE(filter == DFD_FILTER_BILINEAR || filter == DFD_FILTER_BICUBIC, DFD_ERR_UNSUPPORTED,
+              "resample_coeffs: filter %d not supported (bilinear, bicubic)", filter);
   double scale = (double)in_size / out_size, filterscale = scale;
   if (filterscale < 1.0) filterscale = 1.0;
-  const double support = 2.0 * filterscale;
+  const double support = (filter == DFD_FILTER_BILINEAR ? 1.0 : 2.0) * filterscale;
   const int ksize = (int)std::ceil(support) * 2 + 1;
   const double ss = 1.0 / filterscale;
   for (int xx = 0; xx < out_size; ++xx) {
@@ -216,7 +266,8 @@ extern "C" DFD_API int dfd_resample_coeffs_host(int in_size, int out_size, int32
     DFD_REQUIRE(ksize <= 64, DFD_ERR_UNSUPPORTED, "resample_coeffs: downscale factor too large (ksize %d)", ksize);
     for (int x = 0; x < ksize; ++x) k[x] = 0.0;
     for (int x = 0; x < xmax; ++x) {
-      const double w = dfd::bicubic_filter((x + xmin - center + 0.5) * ss);
+      const double arg = (x + xmin - center + 0.5) * ss;
+      const double w = filter == DFD_FILTER_BILINEAR ? dfd::bilinear_filter(arg) : dfd::bicubic_filter(arg);
       k[x] = w;
       ww += w;
     }
@@ -293,5 +344,30 @@ extern "C" DFD_API int dfd_gray256(const void* rgb_u8, int B, int H, int W, int 
   resample_cols_kernel<<<dim3(kOut, B), kOut, 0, st>>>(rows, gray256, H, xmin_h, count_h, kk_h, ksize_h);
   DFD_LAUNCH_CHECK();
   g_launches.fetch_add(launches + 2, std::memory_order_relaxed);
+  return DFD_OK;
+}
+
+// Pillow Image.resize((OW, OH), BILINEAR | BICUBIC) for batches of same-size 8-bit images, 1 or 3 interleaved channels:
+// what torchvision's transforms.Resize does to a PIL image (inference_ai_human_images.py:200-204,
+// train_fusion_head_only.py:67-74) — horizontal pass, u8, vertical pass.  scratch: B*H*OW*C bytes.
+extern "C" DFD_API int dfd_resize_u8(const void* src, int B, int H, int W, int C, int OH, int OW, const int32_t* xmin_w,
+                                     const int32_t* count_w, const int32_t* kk_w, int ksize_w, const int32_t* xmin_h,
+                                     const int32_t* count_h, const int32_t* kk_h, int ksize_h, void* scratch, void* dst,
+                                     void* stream) {
+  using namespace dfd;
+  DFD_REQUIRE(src && dst && scratch, DFD_ERR_BAD_ARG, "resize: null pointer");
+  DFD_REQUIRE(B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && (C == 1 || C == 3), DFD_ERR_SHAPE, "resize: bad shape");
+  DFD_REQUIRE(B <= 65535 && H <= 65535 && OH <= 65535, DFD_ERR_SHAPE, "resize: B, H, OH must be <= 65535");
+  DFD_REQUIRE(xmin_w && count_w && kk_w && xmin_h && count_h && kk_h && ksize_w > 0 && ksize_h > 0, DFD_ERR_BAD_ARG,
+              "resize: resample tables missing");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* rows = reinterpret_cast<uint8_t*>(scratch);
+  resize_rows_kernel<<<dim3((OW * C + 255) / 256, H, B), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(src), rows, H, W,
+                                                                      OW, C, xmin_w, count_w, kk_w, ksize_w);
+  DFD_LAUNCH_CHECK();
+  resize_cols_kernel<<<dim3((OW * C + 255) / 256, OH, B), 256, 0, st>>>(rows, reinterpret_cast<uint8_t*>(dst), H, OH,
+                                                                       OW * C, xmin_h, count_h, kk_h, ksize_h);
+  DFD_LAUNCH_CHECK();
+  g_launches.fetch_add(2, std::memory_order_relaxed);
   return DFD_OK;
 }

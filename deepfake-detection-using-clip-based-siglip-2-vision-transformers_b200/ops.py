@@ -207,27 +207,47 @@ def freq_features(gray256: torch.Tensor, luts, eps: float = 1e-8, zscore: bool =
     return feats
 
 
-def resample_coeffs(in_size: int, out_size: int = 256):
-    """Pillow's 8bpc bicubic resample tables for one axis (host, dfd_resample_coeffs_host): (xmin, count, kk) int32
+FILTERS = {"bilinear": 2, "bicubic": 3}   # PIL.Image.BILINEAR / BICUBIC
+
+
+def resample_coeffs(in_size: int, out_size: int = 256, filter: str = "bicubic"):
+    """Pillow's 8bpc resample tables for one axis (host, dfd_resample_coeffs_filter_host): (xmin, count, kk) int32
     numpy arrays, kk [out_size, ksize].  Works without a GPU."""
     import numpy as np
 
     lib = _lib.load()
-    ks = lib.dfd_resample_ksize(in_size, out_size)
+    f = FILTERS[filter]
+    ks = lib.dfd_resample_ksize_filter(in_size, out_size, f)
     xmin, cnt = np.zeros(out_size, np.int32), np.zeros(out_size, np.int32)
     kk = np.zeros((out_size, ks), np.int32)
-    check(lib.dfd_resample_coeffs_host(in_size, out_size, xmin.ctypes.data, cnt.ctypes.data, kk.ctypes.data))
+    check(lib.dfd_resample_coeffs_filter_host(in_size, out_size, f, xmin.ctypes.data, cnt.ctypes.data, kk.ctypes.data))
     return xmin, cnt, kk
 
 
 _RESAMPLE_TABLES: dict = {}
 
 
-def _resample_tables(size: int, device) -> tuple:
-    key = (size, str(device))
+def _resample_tables(size: int, device, out_size: int = 256, filter: str = "bicubic") -> tuple:
+    key = (size, out_size, filter, str(device))
     if key not in _RESAMPLE_TABLES:
-        _RESAMPLE_TABLES[key] = tuple(torch.from_numpy(a).to(device) for a in resample_coeffs(size, 256))
+        _RESAMPLE_TABLES[key] = tuple(torch.from_numpy(a).to(device) for a in resample_coeffs(size, out_size, filter))
     return _RESAMPLE_TABLES[key]
+
+
+def resize_u8(images: torch.Tensor, out_h: int, out_w: int, filter: str = "bilinear") -> torch.Tensor:
+    """u8 images [B,H,W,C] (C = 1 or 3, device) -> [B,out_h,out_w,C] u8, bit-exact with PIL `Image.resize((out_w, out_h),
+    BILINEAR|BICUBIC)` — torchvision `transforms.Resize` on PIL inputs (inference_ai_human_images.py:200-204)."""
+    _need_cuda(images)
+    assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[3] in (1, 3) and images.is_contiguous()
+    B, H, W, C = images.shape
+    xw, cw, kw = _resample_tables(W, images.device, out_w, filter)
+    xh, ch, kh = _resample_tables(H, images.device, out_h, filter)
+    scratch = torch.empty((B, H, out_w, C), dtype=torch.uint8, device=images.device)
+    out = torch.empty((B, out_h, out_w, C), dtype=torch.uint8, device=images.device)
+    check(_lib.load().dfd_resize_u8(images.data_ptr(), B, H, W, C, out_h, out_w, xw.data_ptr(), cw.data_ptr(), kw.data_ptr(),
+                                    kw.shape[1], xh.data_ptr(), ch.data_ptr(), kh.data_ptr(), kh.shape[1], scratch.data_ptr(),
+                                    out.data_ptr(), current_stream()))
+    return out
 
 
 def gray256_from_rgb(images: torch.Tensor, clahe: bool, scratch: Optional[torch.Tensor] = None,

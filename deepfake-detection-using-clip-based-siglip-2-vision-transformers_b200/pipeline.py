@@ -70,10 +70,16 @@ class DetectionPipeline:
 
     # ---- device-resident path ---------------------------------------------------------------------
     def detect_device(self, images: torch.Tensor, gray256: Optional[torch.Tensor] = None, resize_mode: int = 0,
-                      clahe: bool = True) -> Dict[str, torch.Tensor]:
-        """images: u8 NHWC on the device.  gray256 None = derive it from the same pixels on the device
-        (train_fusion_head_only.py:142-148 with clahe=True; app.py:736-749 with DETECT_USE_CLAHE for clahe)."""
-        pooled, _ = self.engine(images, resize_mode=resize_mode)
+                      clahe: bool = True, pil_resize: Optional[str] = None) -> Dict[str, torch.Tensor]:
+        """images: u8 NHWC on the device.  gray256 None = derive it from the same (original-size) pixels on the device
+        (train_fusion_head_only.py:142-148 with clahe=True; app.py:736-749 with DETECT_USE_CLAHE for clahe).
+        pil_resize "bilinear" / "bicubic": images of another size first go through the PIL-exact `Resize((S,S))` of the
+        reference's transforms (inference_ai_human_images.py:200-204) instead of the in-model resize (resize_mode)."""
+        S = self.arch.image_size
+        model_in = images
+        if pil_resize is not None and tuple(images.shape[1:3]) != (S, S):
+            model_in = ops.resize_u8(images, S, S, pil_resize)
+        pooled, _ = self.engine(model_in, resize_mode=resize_mode)
         _, z_sig, _ = ops.head_fwd(self.head, pooled)
         if gray256 is None:
             need = ops._lib.load().dfd_gray256_scratch_bytes(*images.shape[:3])
@@ -145,12 +151,12 @@ class DetectionPipeline:
 
     # ---- host-buffer path (what a caller of the reference loops sees) -----------------------------------
     def detect(self, images_host: torch.Tensor, gray256_host: Optional[torch.Tensor] = None, resize_mode: int = 0,
-               clahe: bool = True) -> np.ndarray:
+               clahe: bool = True, pil_resize: Optional[str] = None) -> np.ndarray:
         """Host (ideally pinned) u8 NHWC images [+ f32 gray256; None = computed on the device from the same
         pixels] -> numpy [B,14] score records."""
         img = images_host.to(self.device, non_blocking=True)
         gray = None if gray256_host is None else gray256_host.to(self.device, non_blocking=True)
-        packed = self.pack(self.detect_device(img, gray, resize_mode, clahe))
+        packed = self.pack(self.detect_device(img, gray, resize_mode, clahe, pil_resize))
         key = f"out{packed.shape[0]}"
         if key not in self._pin:
             self._pin[key] = torch.empty(packed.shape, dtype=torch.float32).pin_memory()

@@ -171,6 +171,20 @@ DFD_API int dfd_resample_ksize(int in_size, int out_size);
 DFD_API int dfd_resample_coeffs_host(int in_size, int out_size, int32_t* xmin_host, int32_t* count_host,
                                      int32_t* kk_host);
 DFD_API int64_t dfd_gray256_scratch_bytes(int B, int H, int W);
+
+/* Pillow Image.resize((OW,OH), BILINEAR|BICUBIC) for a batch of same-size 8-bit images with 1 or 3 interleaved channels
+ * — what torchvision transforms.Resize((S,S)) does to the PIL image in the reference's preprocess
+ * (inference_ai_human_images.py:200-204, train_fusion_head_only.py:67-74) and what open_clip's preprocess does with
+ * BICUBIC.  Same fixed-point arithmetic as above, bit-exact; tables from dfd_resample_coeffs_filter_host with
+ * ksize = dfd_resample_ksize_filter(in, out, filter).  scratch: B*H*OW*C bytes. */
+enum { DFD_FILTER_BILINEAR = 2, DFD_FILTER_BICUBIC = 3 };   /* PIL.Image.BILINEAR / BICUBIC */
+DFD_API int dfd_resample_ksize_filter(int in_size, int out_size, int filter);
+DFD_API int dfd_resample_coeffs_filter_host(int in_size, int out_size, int filter, int32_t* xmin_host,
+                                            int32_t* count_host, int32_t* kk_host);
+DFD_API int dfd_resize_u8(const void* src, int B, int H, int W, int C, int OH, int OW, const int32_t* xmin_w,
+                          const int32_t* count_w, const int32_t* kk_w, int ksize_w, const int32_t* xmin_h,
+                          const int32_t* count_h, const int32_t* kk_h, int ksize_h, void* scratch, void* dst,
+                          void* stream);
 DFD_API int dfd_gray256(const void* rgb_u8, int B, int H, int W, int clahe, const int32_t* xmin_w,
                         const int32_t* count_w, const int32_t* kk_w, int ksize_w, const int32_t* xmin_h,
                         const int32_t* count_h, const int32_t* kk_h, int ksize_h, void* scratch,

@@ -47,13 +47,22 @@ def _bicubic(x: float) -> float:
     return 0.0
 
 
-def resample_coeffs(in_size: int, out_size: int):
-    """Pillow precompute_coeffs + normalize_coeffs_8bpc for the bicubic filter (support 2) over the full image.
-    Returns (xmin int32[out], count int32[out], kk int32[out, ksize])."""
+def _bilinear(x: float) -> float:
+    if x < 0.0:
+        x = -x
+    if x < 1.0:
+        return 1.0 - x
+    return 0.0
+
+
+def resample_coeffs(in_size: int, out_size: int, filter: str = "bicubic"):
+    """Pillow precompute_coeffs + normalize_coeffs_8bpc for the bicubic (support 2) / bilinear (support 1) filter over the
+    full image.  Returns (xmin int32[out], count int32[out], kk int32[out, ksize])."""
+    filt, supp = (_bicubic, 2.0) if filter == "bicubic" else (_bilinear, 1.0)
     scale = filterscale = in_size / out_size
     if filterscale < 1.0:
         filterscale = 1.0
-    support = 2.0 * filterscale
+    support = supp * filterscale
     ksize = int(math.ceil(support)) * 2 + 1
     xmin_a = np.zeros(out_size, np.int32)
     cnt_a = np.zeros(out_size, np.int32)
@@ -71,7 +80,7 @@ def resample_coeffs(in_size: int, out_size: int):
         xmax -= xmin
         k = [0.0] * ksize
         for x in range(xmax):
-            w = _bicubic((x + xmin - center + 0.5) * ss)
+            w = filt((x + xmin - center + 0.5) * ss)
             k[x] = w
             ww += w
         for x in range(xmax):
@@ -84,10 +93,10 @@ def resample_coeffs(in_size: int, out_size: int):
     return xmin_a, cnt_a, kk
 
 
-def _resample_last_axis(img: np.ndarray, out_size: int) -> np.ndarray:
+def _resample_last_axis(img: np.ndarray, out_size: int, filter: str = "bicubic") -> np.ndarray:
     """One Pillow 8bpc pass along the last axis: u8 [..., n] -> u8 [..., out_size]."""
     n = img.shape[-1]
-    xmin, cnt, kk = resample_coeffs(n, out_size)
+    xmin, cnt, kk = resample_coeffs(n, out_size, filter)
     src = img.astype(np.int64)
     out = np.empty(img.shape[:-1] + (out_size,), np.uint8)
     for xx in range(out_size):
@@ -106,6 +115,19 @@ def resize_bicubic_u8(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
     if h != out_h:
         img = np.ascontiguousarray(_resample_last_axis(np.ascontiguousarray(img.T), out_h).T)
     return img
+
+
+def resize_u8(img: np.ndarray, out_h: int, out_w: int, filter: str = "bilinear") -> np.ndarray:
+    """Pillow Image.resize((out_w, out_h), BILINEAR|BICUBIC) of an 8-bit image [H, W] or [H, W, C]: every band is
+    resampled independently with the same coefficients, horizontal pass first."""
+    a = img if img.ndim == 3 else img[..., None]
+    h, w, _ = a.shape
+    if w != out_w:
+        a = np.moveaxis(_resample_last_axis(np.ascontiguousarray(np.moveaxis(a, 1, -1)), out_w, filter), -1, 1)
+    if h != out_h:
+        a = np.moveaxis(_resample_last_axis(np.ascontiguousarray(np.moveaxis(a, 0, -1)), out_h, filter), -1, 0)
+    a = np.ascontiguousarray(a)
+    return a if img.ndim == 3 else a[..., 0]
 
 
 def _reflect101(i: int, n: int) -> int:

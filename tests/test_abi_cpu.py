@@ -182,6 +182,10 @@ def test_resample_tables_host_equal_oracle(lib):
     for n in (384, 224, 256, 451, 97, 1024, 33, 7, 3000):
         got, want = ops.resample_coeffs(n, 256), G.resample_coeffs(n, 256)
         assert all(np.array_equal(a, b) for a, b in zip(got, want)), n
+    for n, m in ((640, 384), (224, 384), (37, 224), (1920, 384)):
+        for f in ("bilinear", "bicubic"):
+            got, want = ops.resample_coeffs(n, m, f), G.resample_coeffs(n, m, f)
+            assert all(np.array_equal(a, b) for a, b in zip(got, want)), (n, m, f)
     # the identity case reproduces the input exactly: one tap of weight 2^22
     xmin, cnt, kk = ops.resample_coeffs(256, 256)
     assert np.array_equal(kk.sum(1), np.full(256, 1 << 22)) and int((kk != 0).sum()) == 256

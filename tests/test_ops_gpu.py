@@ -528,3 +528,38 @@ def test_gray256_full_size_properties():
     assert float(a.min()) >= 0.0 and float(a.max()) <= 1.0
     k = a.double() * 255.0
     assert float((k - k.round()).abs().max()) < 1e-4   # every value is k/255
+
+
+@pytest.mark.parametrize("B,H,W,OH,OW,C", [(3, 480, 640, 384, 384, 3), (4, 224, 224, 384, 384, 3), (2, 100, 37, 224, 224, 3),
+                                           (1, 1080, 1920, 384, 384, 3), (2, 384, 384, 384, 384, 3), (3, 97, 211, 64, 48, 1)])
+@pytest.mark.parametrize("filt", ["bilinear", "bicubic"])
+def test_resize_u8_matches_pillow_oracle(B, H, W, OH, OW, C, filt):
+    """dfd_resize_u8 = PIL Image.resize (torchvision transforms.Resize on PIL inputs), bit-exact."""
+    from dfd import ops
+    from oracle import gray_ref as G
+
+    rng = np.random.default_rng(H + W + C)
+    imgs = rng.integers(0, 256, (B, H, W, C), dtype=np.uint8)
+    got = ops.resize_u8(torch.from_numpy(imgs).to(DEV), OH, OW, filt).cpu().numpy()
+    for b in range(B):
+        want = G.resize_u8(imgs[b] if C == 3 else imgs[b, ..., 0], OH, OW, filt)
+        assert np.array_equal(got[b] if C == 3 else got[b, ..., 0], want), (b, filt)
+
+
+def test_resize_then_patchify_equals_pil_preprocess():
+    """a1 end to end on the device: PIL Resize((S,S)) + ToTensor + Normalize(.5,.5) == resize_u8 + patchify (bf16)."""
+    from dfd import ops
+    from oracle import gray_ref as G
+
+    S, P = 224, 16
+    rng = np.random.default_rng(5)
+    imgs = rng.integers(0, 256, (2, 300, 451, 3), dtype=np.uint8)
+    dev = ops.resize_u8(torch.from_numpy(imgs).to(DEV), S, S, "bilinear")
+    A = ops.patchify(dev, S, P)
+    ref_u8 = np.stack([G.resize_u8(im, S, S, "bilinear") for im in imgs])
+    x = torch.from_numpy(ref_u8).permute(0, 3, 1, 2).float() / 255.0
+    x = (x - 0.5) / 0.5
+    g = S // P
+    ref = x.reshape(2, 3, g, P, g, P).permute(0, 2, 4, 1, 3, 5).reshape(2 * g * g, 3 * P * P)
+    torch.cuda.synchronize()
+    assert torch.equal(A[:, :3 * P * P].float().cpu(), ref.to(torch.bfloat16).float())

@@ -175,3 +175,17 @@ def test_gray_oracle_matches_installed_libraries():
         assert np.array_equal(np.array(PIL_Image.fromarray(L).resize((256, 256), PIL_Image.BICUBIC)),
                               G.resize_bicubic_u8(L, 256, 256))
         assert np.array_equal(cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8)).apply(L), G.clahe_u8(L))
+
+
+def test_resize_oracle_matches_pillow():
+    """RGB / L, bilinear (torchvision Resize on PIL inputs) and bicubic (open_clip preprocess), up- and down-scaling."""
+    PIL_Image = pytest.importorskip("PIL.Image")
+    from oracle import gray_ref as G
+
+    rng = np.random.default_rng(3)
+    for (h, w, oh, ow) in [(120, 160, 96, 96), (56, 56, 96, 96), (100, 37, 64, 48), (96, 96, 96, 96), (300, 17, 20, 40)]:
+        im = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        for f, pf in (("bilinear", PIL_Image.BILINEAR), ("bicubic", PIL_Image.BICUBIC)):
+            assert np.array_equal(np.array(PIL_Image.fromarray(im, "RGB").resize((ow, oh), pf)), G.resize_u8(im, oh, ow, f))
+            assert np.array_equal(np.array(PIL_Image.fromarray(im[..., 1]).resize((ow, oh), pf)),
+                                  G.resize_u8(im[..., 1], oh, ow, f))
