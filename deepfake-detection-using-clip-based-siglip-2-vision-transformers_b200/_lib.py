@@ -117,6 +117,7 @@ SIGNATURES = {
     "dfd_gray256": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P]),
     "dfd_score_epilogue": (_I, [C.POINTER(ScoreWeights), _P, _P, _P, _I, C.POINTER(Scores), _P]),
     "dfd_fusion_fwd_bwd": (_I, [_P, _P, _P, _P, _I, _F, _P, _P, _P, _P]),
+    "dfd_freqmlp_fwd_bwd": (_I, [_P, _P, _P, _P, _P, _I, _F, _F, C.c_uint32, _P, _P, _P, _P]),
     "dfd_engine_create": (_I, [C.POINTER(EngineConfig), _I, _I, C.POINTER(_P)]),
     "dfd_engine_destroy": (_I, [_P]),
     "dfd_engine_set_tensor": (_I, [_P, C.c_char_p, _P, _I, _I, C.POINTER(_L), _I]),

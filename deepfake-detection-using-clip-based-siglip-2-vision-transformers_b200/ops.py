@@ -348,6 +348,36 @@ def score_epilogue(params: ScoreParams, z_sig: torch.Tensor, feats: Optional[tor
 FUSION_PARAM_ORDER = ("mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias", "temp.T")
 
 
+FREQMLP_PARAM_ORDER = ("contrast.alpha", "contrast.beta", "band.gates") + tuple(
+    f"blocks.{b}.{n}" for b in range(2)
+    for n in ("norm.weight", "norm.bias", "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")) + ("head.weight", "head.bias", "temp.T")
+FREQMLP_PARAM_SHAPES = ((24,), (24,), (4,)) + ((24,), (24,), (64, 24), (64,), (24, 64), (24,)) * 2 + ((1, 24), (1,), ())
+FREQMLP_NUM_PARAMS = 6494
+
+
+def freqmlp_fwd_bwd(params: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, feats: torch.Tensor,
+                    y: Optional[torch.Tensor] = None, inv_global_batch: Optional[float] = None, dropout_p: float = 0.0,
+                    seed: int = 0, want_grads: bool = True, want_logits: bool = False):
+    """FreqMLP G2 forward (+ backward of mean BCE-with-logits).  Returns (loss[1] | None, grads[6494] | None,
+    logits[B] | None); loss / grads are this rank's partial sums (all-reduce-sum them)."""
+    _need_cuda(params, mean, std, feats)
+    for t in (params, mean, std, feats):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert params.numel() == FREQMLP_NUM_PARAMS and mean.numel() == 24 and std.numel() == 24 and feats.shape[1] == 24
+    B, dev = feats.shape[0], feats.device
+    loss = grads = None
+    if want_grads:
+        assert y is not None and y.dtype == torch.float32 and y.is_contiguous() and y.numel() == B
+        loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+        grads = torch.zeros((FREQMLP_NUM_PARAMS,), dtype=torch.float32, device=dev)
+    logits = torch.empty((B,), dtype=torch.float32, device=dev) if (want_logits or not want_grads) else None
+    inv = (1.0 / B) if inv_global_batch is None else inv_global_batch
+    check(_lib.load().dfd_freqmlp_fwd_bwd(params.data_ptr(), mean.data_ptr(), std.data_ptr(), feats.data_ptr(), _p(y), B,
+                                          inv, float(dropout_p), int(seed) & 0xFFFFFFFF, _p(loss), _p(grads), _p(logits),
+                                          current_stream()))
+    return loss, grads, logits
+
+
 def fusion_fwd_bwd(params195: torch.Tensor, z_freq: torch.Tensor, z_sig: torch.Tensor, y: torch.Tensor,
                    inv_global_batch: Optional[float] = None, want_logits: bool = False):
     """AdaptiveFusionHead forward + backward of mean BCE-with-logits. Returns (loss[1], grads[195], logits|None);

@@ -190,6 +190,19 @@ DFD_API int dfd_gray256(const void* rgb_u8, int B, int H, int W, int clahe, cons
                         const int32_t* count_h, const int32_t* kk_h, int ksize_h, void* scratch,
                         float* gray256 /*[B,256,256]*/, void* stream);
 
+/* FreqMLP (generation 2) forward + backward of mean BCE-with-logits: one training step's
+ * `logits = model(xb); loss = criterion(logits, yb); loss.backward()` ("FreqMLP trainer.py":366-369; model :218-301).
+ * params6494 = the state dict without its two buffers, flattened in order: contrast.alpha[24], contrast.beta[24],
+ * band.gates[4], blocks.{0,1}.{norm.weight[24], norm.bias[24], fc1.weight[64,24], fc1.bias[64], fc2.weight[24,64],
+ * fc2.bias[24]}, head.weight[24], head.bias, temp.T.  mean24/std24 = FeatureNormalizer buffers.
+ * loss_sum[1] and grads[6494] are ACCUMULATED partial sums with the factor inv_global_batch applied (zero them, then
+ * all-reduce-sum across ranks).  grads == NULL: forward only (eval; no dropout).  dropout_p: the blocks' nn.Dropout
+ * (0.05 in the reference's train mode; masks come from a counter hash of (seed, sample, element), so they match torch's
+ * only in distribution; 0 = deterministic). */
+DFD_API int dfd_freqmlp_fwd_bwd(const float* params6494, const float* mean24, const float* std24, const float* feats,
+                                const float* y, int B, float inv_global_batch, float dropout_p, uint32_t seed,
+                                float* loss_sum, float* grads, float* logits, void* stream);
+
 /* Score epilogue: FreqMLP + fusion + temperature + CORAL, one warp per sample.
  *  gen 1 (shipped siglip/ safetensors files; deepfake-detector-v2/app.py:601-628,691-709,1355-1396):
  *     z_freq = FreqMLP_G1(feats)  (SafeLayerNorm eps 1e-5 → Linear(24,64) → GELU(erf) → Linear(64,1); eval noise omitted)

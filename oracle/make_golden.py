@@ -220,6 +220,29 @@ def make_gray():
     print("gray golden:", len(outs), "images")
 
 
+def make_freq_train():
+    """Loss and gradients of the reference's OWN FreqMLP class ("FreqMLP trainer.py":218-301) in eval mode (no dropout)
+    under autograd, for seeded weights / features — pins oracle.scoring_ref.freq_mlp_g2_loss_and_grads."""
+    ns = extract(f"{REF}/FreqMLP trainer.py",
+                 {"FeatureNormalizer", "ContrastScaler", "TemperatureScaler", "BandGating", "ResidualMLPBlock", "FreqMLP"},
+                 base_namespace())
+    sd = S.init_freq_mlp_g2(7)
+    m = ns["FreqMLP"]()
+    m.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()}, strict=True)
+    m.eval()
+    g = torch.Generator().manual_seed(11)
+    feats = torch.randn(37, 24, generator=g) * 0.8 + 0.3
+    y = (torch.rand(37, generator=g) > 0.5).float()
+    with torch.enable_grad():
+        out = m(feats)
+        loss = nn.BCEWithLogitsLoss()(out, y)
+        loss.backward()
+    grads = torch.cat([dict(m.named_parameters())[k].grad.reshape(-1) for k in S.FREQMLP_PARAM_ORDER])
+    np.savez_compressed(os.path.join(OUT, "freq_train_golden.npz"), feats=feats.numpy(), y=y.numpy(),
+                        loss=np.float64(loss.item()), grads=grads.numpy(), logits=out.detach().numpy())
+    print("freq train golden: loss", float(loss), "|grad|", float(grads.norm()))
+
+
 def make_heads():
     """Classifier heads as the reference defines them (inference_ai_human_images.py:131-138;
     train_fusion_head_only.py:84-99), fed seeded pooled embeddings."""
@@ -312,9 +335,11 @@ def make_backbone():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["scoring", "heads", "backbone", "gray"]
+    which = sys.argv[1:] or ["scoring", "heads", "backbone", "gray", "freq_train"]
     if "gray" in which:
         make_gray()
+    if "freq_train" in which:
+        make_freq_train()
     if "scoring" in which:
         make_scoring()
     if "heads" in which:

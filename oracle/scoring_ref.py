@@ -333,3 +333,31 @@ def fusion_loss_and_grads(sd: dict, z_freq: np.ndarray, z_sig: np.ndarray, y: np
         loss.backward()
     grads = torch.cat([p[k].grad.reshape(-1) for k in names]).numpy()
     return float(loss.detach()), grads, out.detach().numpy()
+
+
+FREQMLP_PARAM_ORDER = ("contrast.alpha", "contrast.beta", "band.gates") + tuple(
+    f"blocks.{b}.{n}" for b in range(2)
+    for n in ("norm.weight", "norm.bias", "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")) + ("head.weight", "head.bias", "temp.T")
+
+
+def freq_mlp_g2_loss_and_grads(sd: dict, feats: np.ndarray, y: np.ndarray):
+    """mean BCEWithLogits(FreqMLP_G2(feats), y) and d loss / d params (flat 6494, FREQMLP_PARAM_ORDER) via float64
+    autograd: "FreqMLP trainer.py":218-301 (eval-mode dropout, i.e. none) and :366-369."""
+    F = torch.nn.functional
+    with torch.enable_grad():
+        t = lambda v: torch.as_tensor(np.asarray(v.detach().cpu() if hasattr(v, "detach") else v), dtype=torch.float64)
+        p = {k: t(sd[k]).clone().requires_grad_(True) for k in FREQMLP_PARAM_ORDER}
+        x = (t(feats) - t(sd["normer.mean"])) / (t(sd["normer.std"]) + 1e-6)
+        x = torch.tanh(p["contrast.alpha"] * x + p["contrast.beta"])
+        gates = torch.sigmoid(p["band.gates"])
+        x = torch.cat([c * gates[i] for i, c in enumerate(torch.split(x, 6, dim=-1))], dim=-1)
+        for b in range(2):
+            r = x
+            h = F.layer_norm(x, (24,), p[f"blocks.{b}.norm.weight"], p[f"blocks.{b}.norm.bias"], 1e-5)
+            h = F.gelu(h @ p[f"blocks.{b}.fc1.weight"].t() + p[f"blocks.{b}.fc1.bias"])
+            x = h @ p[f"blocks.{b}.fc2.weight"].t() + p[f"blocks.{b}.fc2.bias"] + r
+        out = ((x @ p["head.weight"].t()).squeeze(-1) + p["head.bias"]) / (p["temp.T"] + 1e-6)
+        loss = F.binary_cross_entropy_with_logits(out, t(y))
+        loss.backward()
+    grads = torch.cat([p[k].grad.reshape(-1) for k in FREQMLP_PARAM_ORDER]).numpy()
+    return float(loss.detach()), grads, out.detach().numpy()

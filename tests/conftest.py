@@ -47,6 +47,11 @@ def golden_backbone():
 
 
 @pytest.fixture(scope="session")
+def golden_freq_train():
+    return np.load(os.path.join(GOLDEN, "freq_train_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_gray():
     return np.load(os.path.join(GOLDEN, "gray_golden.npz"))
 

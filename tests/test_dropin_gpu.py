@@ -295,3 +295,79 @@ def test_train_fusion_head_end_to_end(tmp_path):
     assert all(torch.equal(sd[k], best[k]) for k in sd)
     st = scoring.ScoringStack(DEV, load_file(str(tmp_path / "freq_mlp.safetensors")), sd, [-1.0, -0.2, 0.3, 1.5], 1.0)
     assert st.gen == 2
+
+
+def _reference_fit_freq(features, labels, batch_size, epochs, lr, seed):
+    """"FreqMLP trainer.py":330-396 restated with torch autograd, dropout off (the only stochastic part)."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from torch.utils.data import DataLoader, TensorDataset
+
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.norm, self.fc1, self.fc2 = nn.LayerNorm(24), nn.Linear(24, 64), nn.Linear(64, 24)
+
+        def forward(self, x):
+            return self.fc2(F.gelu(self.fc1(self.norm(x)))) + x
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.alpha, self.beta = nn.Parameter(torch.ones(24)), nn.Parameter(torch.zeros(24))
+            self.gates = nn.Parameter(torch.zeros(4))
+            self.blocks = nn.ModuleList([Block(), Block()])
+            self.head = nn.Linear(24, 1)
+            self.T = nn.Parameter(torch.tensor(1.0))
+
+        def forward(self, x, mean, std):
+            x = torch.tanh(self.alpha * ((x - mean) / (std + 1e-6)) + self.beta)
+            g = torch.sigmoid(self.gates)
+            x = torch.cat([c * g[i] for i, c in enumerate(torch.split(x, 6, dim=-1))], dim=-1)
+            for b in self.blocks:
+                x = b(x)
+            return self.head(x).squeeze(-1) / (self.T + 1e-6)
+
+    torch.manual_seed(seed)
+    m = Net()
+    mean, std = features.mean(0), features.std(0) + 1e-6
+    loader = DataLoader(TensorDataset(features, labels), batch_size=batch_size, shuffle=True)
+    opt = torch.optim.AdamW(m.parameters(), lr=lr)
+    with torch.enable_grad():
+        for _ in range(epochs):
+            for xb, yb in loader:
+                opt.zero_grad()
+                nn.BCEWithLogitsLoss()(m(xb, mean, std), yb).backward()
+                nn.utils.clip_grad_norm_(m.parameters(), max_norm=5.0)
+                opt.step()
+    ps = [m.alpha, m.beta, m.gates]
+    for b in m.blocks:
+        ps += [b.norm.weight, b.norm.bias, b.fc1.weight, b.fc1.bias, b.fc2.weight, b.fc2.bias]
+    ps += [m.head.weight, m.head.bias, m.T]
+    return torch.cat([p.detach().reshape(-1) for p in ps])
+
+
+def test_fit_freq_mlp_matches_reference_loop(tmp_path):
+    from safetensors.torch import load_file, save_file
+
+    from dfd import scoring, train_freq
+
+    rng = np.random.default_rng(4)
+    n = 101  # ragged last mini-batch
+    y = torch.from_numpy((rng.random(n) > 0.5).astype(np.float32))
+    feats = torch.from_numpy((rng.normal(0.2, 0.7, (n, 24)) + 0.6 * (y.numpy()[:, None] - 0.5)).astype(np.float32))
+    ref = _reference_fit_freq(feats, y, 8, 3, 1e-3, seed=5)
+    torch.manual_seed(5)
+    model, best, auc = train_freq.fit_freq_mlp(feats, y, epochs=3, batch_size=8, lr=1e-3, device=DEV, dropout=0.0,
+                                               verbose=False)
+    got = model.flat.data.cpu()
+    assert (got - ref).abs().max() < 5e-4, (got - ref).abs().max()
+    assert auc > 0.6
+    # the written file loads, strictly, into the inference-side FreqMLP (the reference's reader: train_fusion_head_only.py:390-392)
+    path = str(tmp_path / "freq_mlp.safetensors")
+    save_file({k: v.contiguous() for k, v in best.items()}, path)
+    fm = scoring.FreqMLP()
+    fm.load_state_dict(load_file(path), strict=True)
+    z = fm(feats.to(DEV))
+    model.load_state_dict(best)
+    assert (z - model(feats.to(DEV))).abs().max() < 1e-4

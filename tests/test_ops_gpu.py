@@ -563,3 +563,57 @@ def test_resize_then_patchify_equals_pil_preprocess():
     ref = x.reshape(2, 3, g, P, g, P).permute(0, 2, 4, 1, 3, 5).reshape(2 * g * g, 3 * P * P)
     torch.cuda.synchronize()
     assert torch.equal(A[:, :3 * P * P].float().cpu(), ref.to(torch.bfloat16).float())
+
+
+# ---------------------------------------------------------------------------------------------------
+# FreqMLP (G2) training step
+# ---------------------------------------------------------------------------------------------------
+def test_freqmlp_fwd_bwd(golden_freq_train):
+    from dfd import ops
+    from oracle import scoring_ref as S
+
+    g = golden_freq_train
+    sd = S.init_freq_mlp_g2(7)
+    flat = torch.cat([torch.as_tensor(sd[k]).reshape(-1).float() for k in ops.FREQMLP_PARAM_ORDER]).to(DEV)
+    mean, std = torch.as_tensor(sd["normer.mean"]).float().to(DEV), torch.as_tensor(sd["normer.std"]).float().to(DEV)
+    feats, y = torch.from_numpy(g["feats"]).to(DEV), torch.from_numpy(g["y"]).to(DEV)
+    loss, grads, logits = ops.freqmlp_fwd_bwd(flat, mean, std, feats, y, want_logits=True)
+    torch.cuda.synchronize()
+    # fp32 kernel vs the reference class's fp32 autograd: a few 1e-6 on O(1) values
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    assert np.abs(grads.cpu().numpy() - g["grads"]).max() < 1e-5 * max(1.0, np.abs(g["grads"]).max())
+    assert np.abs(logits.cpu().numpy() - g["logits"]).max() < 2e-5
+    # eval-mode forward only
+    _, _, lg = ops.freqmlp_fwd_bwd(flat, mean, std, feats, want_grads=False)
+    assert torch.equal(lg, logits)
+    # linearity over shards (what the data-parallel trainer relies on)
+    l1, g1, _ = ops.freqmlp_fwd_bwd(flat, mean, std, feats[:20].contiguous(), y[:20].contiguous(), 1.0 / 37)
+    l2, g2, _ = ops.freqmlp_fwd_bwd(flat, mean, std, feats[20:].contiguous(), y[20:].contiguous(), 1.0 / 37)
+    assert torch.allclose(l1 + l2, loss, atol=1e-6) and torch.allclose(g1 + g2, grads, atol=2e-6)
+    # large ragged batch vs the float64 oracle
+    rng = np.random.default_rng(2)
+    n = 5003
+    f2 = (rng.normal(0.3, 0.8, (n, 24))).astype(np.float32)
+    y2 = (rng.random(n) > 0.5).astype(np.float32)
+    lo, go, _ = S.freq_mlp_g2_loss_and_grads(sd, f2, y2)
+    l3, g3, _ = ops.freqmlp_fwd_bwd(flat, mean, std, torch.from_numpy(f2).to(DEV), torch.from_numpy(y2).to(DEV))
+    assert abs(l3.item() - lo) < 1e-4 and np.abs(g3.cpu().numpy() - go).max() < 1e-4
+
+
+def test_freqmlp_dropout_is_unbiased_and_seeded():
+    from dfd import ops
+    from oracle import scoring_ref as S
+
+    sd = S.init_freq_mlp_g2(7)
+    flat = torch.cat([torch.as_tensor(sd[k]).reshape(-1).float() for k in ops.FREQMLP_PARAM_ORDER]).to(DEV)
+    mean, std = torch.as_tensor(sd["normer.mean"]).float().to(DEV), torch.as_tensor(sd["normer.std"]).float().to(DEV)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    feats = (torch.randn(4096, 24, generator=g) * 0.8 + 0.3).to(DEV)
+    y = (torch.rand(4096, generator=g) > 0.5).float().to(DEV)
+    base = ops.freqmlp_fwd_bwd(flat, mean, std, feats, y)
+    a = ops.freqmlp_fwd_bwd(flat, mean, std, feats, y, dropout_p=0.05, seed=1)
+    b = ops.freqmlp_fwd_bwd(flat, mean, std, feats, y, dropout_p=0.05, seed=1)
+    c = ops.freqmlp_fwd_bwd(flat, mean, std, feats, y, dropout_p=0.05, seed=2)
+    assert torch.allclose(a[1], b[1], atol=1e-6)            # same seed, same masks (up to atomic ordering)
+    assert not torch.allclose(a[1], c[1], atol=1e-6)        # different seed, different masks
+    assert abs(a[0].item() - base[0].item()) < 0.2          # 5 % inverted dropout perturbs the loss only mildly

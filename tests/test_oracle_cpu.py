@@ -189,3 +189,12 @@ def test_resize_oracle_matches_pillow():
             assert np.array_equal(np.array(PIL_Image.fromarray(im, "RGB").resize((ow, oh), pf)), G.resize_u8(im, oh, ow, f))
             assert np.array_equal(np.array(PIL_Image.fromarray(im[..., 1]).resize((ow, oh), pf)),
                                   G.resize_u8(im[..., 1], oh, ow, f))
+
+
+def test_freqmlp_grad_oracle_matches_reference_class(golden_freq_train):
+    """float64 autograd restatement vs loss / gradients of the reference's own FreqMLP class (make_golden.py)."""
+    g = golden_freq_train
+    loss, grads, out = S.freq_mlp_g2_loss_and_grads(S.init_freq_mlp_g2(7), g["feats"], g["y"])
+    assert abs(loss - float(g["loss"])) < 1e-6
+    assert np.abs(grads - g["grads"]).max() < 2e-6 and grads.shape == (6494,)
+    assert np.abs(out - g["logits"]).max() < 1e-5
