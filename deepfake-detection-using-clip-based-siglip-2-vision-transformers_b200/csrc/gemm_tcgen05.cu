@@ -162,7 +162,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         // N fastest: CTAs working at the same time share A row blocks through L2; the weights (<= 10 MB)
         // stay L2 resident for the whole GEMM
         const int m0 = (tile / num_n) * (BM * CG) + (int)cta_rank * BM;
-        const int n0 = (tile % num_n) * BN + (int)cta_rank * (BN / CG) * (CG - 1);
+        // the last N tile is only as wide as it has to be (multiple of 16): a pair MMA of width n_eff takes n_eff / 2
+        // columns of B from each CTA, so CTA 1's rows start at n_eff / 2, not BN / 2
+        const int nt0 = (tile % num_n) * BN;
+        const int n_eff = min(BN, (N - nt0 + 15) & ~15);
+        const int n0 = nt0 + (int)cta_rank * (n_eff / CG) * (CG - 1);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * S::kStageBytes;
@@ -184,7 +188,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
     if (is_leader && elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -193,6 +196,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        // N tail: an MMA of width n_eff (multiple of 16) instead of BN — a half-empty 256-wide tile (N = 1152: the fifth
+        // one) then costs half, not all, of a full tile's tensor-pipe time
+        const int n_eff = min(BN, (N - (tile % num_n) * BN + 15) & ~15);
+        const uint32_t idesc = umma_idesc_bf16(BM * CG, n_eff);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
