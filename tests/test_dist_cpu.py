@@ -51,6 +51,15 @@ def _worker(rank, world, port, q):
     l_full, g_full, _ = S.fusion_loss_and_grads(sd, zf, zs, y)
     res["grad_err"] = float(np.abs(bucket[:195].numpy() - g_full).max())
     res["loss_err"] = abs(float(bucket[195]) - l_full)
+    # 4. the same identity for the FreqMLP trainer's 6 495-float bucket
+    f = rng.normal(0.3, 0.8, (B, 24)).astype(np.float32)
+    fsd = S.init_freq_mlp_g2(7)
+    lf_loc, gf_loc, _ = S.freq_mlp_g2_loss_and_grads(fsd, f[lo:hi], y[lo:hi])
+    fb = torch.cat([torch.from_numpy(gf_loc) * nloc / B, torch.tensor([lf_loc * nloc / B], dtype=torch.float64)])
+    distributed.all_reduce_sum_(fb)
+    lf_full, gf_full, _ = S.freq_mlp_g2_loss_and_grads(fsd, f, y)
+    res["fgrad_err"] = float(np.abs(fb[:-1].numpy() - gf_full).max())
+    res["floss_err"] = abs(float(fb[-1]) - lf_full)
     res["max"] = distributed.max_over_ranks(float(rank + 1), "cpu")
     distributed.barrier()
     q.put((rank, res))
@@ -71,6 +80,7 @@ def test_gloo_world2():
     for r in range(world):
         assert out[r]["gather_ok"] and out[r]["gather_eq_ok"]
         assert out[r]["grad_err"] < 1e-12 and out[r]["loss_err"] < 1e-12
+        assert out[r]["fgrad_err"] < 1e-12 and out[r]["floss_err"] < 1e-12
         assert out[r]["max"] == 2.0
 
 
