@@ -33,6 +33,7 @@ class GemmEpilogue(C.Structure):
         ("ln_dim", C.c_int),
         ("ln_eps", C.c_float),
         ("stats_out", C.c_void_p),
+        ("residual_op", C.c_int),
     ]
 
 
@@ -117,6 +118,9 @@ SIGNATURES = {
     "dfd_gray256": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P]),
     "dfd_score_epilogue": (_I, [C.POINTER(ScoreWeights), _P, _P, _P, _I, C.POINTER(Scores), _P]),
     "dfd_fusion_fwd_bwd": (_I, [_P, _P, _P, _P, _I, _F, _P, _P, _P, _P]),
+    "dfd_dwconv3x3_bf16": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
+    "dfd_seg_head_upsample": (_I, [_P, _L, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "dfd_linear_small": (_I, [_P, _L, _P, _P, _P, _I, _I, _I, _P]),
     "dfd_freqmlp_fwd_bwd": (_I, [_P, _P, _P, _P, _P, _I, _F, _F, C.c_uint32, _P, _P, _P, _P]),
     "dfd_engine_create": (_I, [C.POINTER(EngineConfig), _I, _I, C.POINTER(_P)]),
     "dfd_engine_destroy": (_I, [_P]),

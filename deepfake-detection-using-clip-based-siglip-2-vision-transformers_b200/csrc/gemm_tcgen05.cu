@@ -38,6 +38,7 @@ struct EpiArgs {
   float ln_inv_dim;
   float ln_eps;
   float* stats_out;
+  int residual_op;  // 0: v += residual, 1: v *= residual
 };
 
 // CG = CTAs per MMA (1, or 2 = cta_group::2: a 256 x BN tile shared by an SM pair, each CTA staging its own
@@ -390,6 +391,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             if (epi.act == 1) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) v[j] = gelu_tanh_fast2(v[j]);
+            } else if (epi.act == 2) {  // exact erf GELU (nn.GELU() default: the SegFormer decoder of SigLIP2_MTL)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[j] = make_float2(gelu_erf(v[j].x), gelu_erf(v[j].y));
+            } else if (epi.act == 3) {  // sigmoid
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                v[j] = make_float2(1.f / (1.f + __expf(-v[j].x)), 1.f / (1.f + __expf(-v[j].y)));
             }
             if (pos_row != nullptr) {
               const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos_row + cc));
@@ -400,10 +408,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
               v[3] = fadd2(v[3], make_float2(p1.z, p1.w));
             }
             if (RES) {
-              v[0] = fadd2(v[0], unpack_bf16x2(res[g].x));
-              v[1] = fadd2(v[1], unpack_bf16x2(res[g].y));
-              v[2] = fadd2(v[2], unpack_bf16x2(res[g].z));
-              v[3] = fadd2(v[3], unpack_bf16x2(res[g].w));
+              if (epi.residual_op == 0) {
+                v[0] = fadd2(v[0], unpack_bf16x2(res[g].x));
+                v[1] = fadd2(v[1], unpack_bf16x2(res[g].y));
+                v[2] = fadd2(v[2], unpack_bf16x2(res[g].z));
+                v[3] = fadd2(v[3], unpack_bf16x2(res[g].w));
+              } else {  // gate: sigmoid(conv(x)) * x  (SegFormerStrongDecoder.fuse_attn)
+                v[0] = fmul2(v[0], unpack_bf16x2(res[g].x));
+                v[1] = fmul2(v[1], unpack_bf16x2(res[g].y));
+                v[2] = fmul2(v[2], unpack_bf16x2(res[g].z));
+                v[3] = fmul2(v[3], unpack_bf16x2(res[g].w));
+              }
             }
           }
           o[g].x = pack_bf16x2(v[0].x, v[0].y);
@@ -577,7 +592,9 @@ int gemm_bf16_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, v
     ea.ln_inv_dim = epi->ln_dim > 0 ? 1.0f / (float)epi->ln_dim : 0.f;
     ea.ln_eps = epi->ln_eps;
     ea.stats_out = epi->stats_out;
-    DFD_REQUIRE(ea.act == 0 || ea.act == 1, DFD_ERR_BAD_ARG, "gemm: act must be 0 or 1");
+    ea.residual_op = epi->residual_op;
+    DFD_REQUIRE(ea.act >= 0 && ea.act <= 3, DFD_ERR_BAD_ARG, "gemm: act must be 0 (none), 1 (gelu_tanh), 2 (gelu_erf) or 3 (sigmoid)");
+    DFD_REQUIRE(ea.residual_op == 0 || ea.residual_op == 1, DFD_ERR_BAD_ARG, "gemm: residual_op must be 0 (add) or 1 (multiply)");
     DFD_REQUIRE((ea.ln_colsum == nullptr) == (ea.ln_rowstats == nullptr), DFD_ERR_BAD_ARG,
                 "gemm: ln_rowstats and ln_colsum must be given together");
     DFD_REQUIRE(ea.ln_colsum == nullptr || epi->ln_dim > 0, DFD_ERR_BAD_ARG, "gemm: ln_dim must be > 0");

@@ -28,8 +28,9 @@ def _p(t: Optional[torch.Tensor]):
 
 def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = 0, pos=None, residual=None,
               ln_rowstats=None, ln_colsum=None, ln_dim: int = 0, ln_eps: float = 1e-6, stats_out=None,
-              out: Optional[torch.Tensor] = None, tile_n: int = 0) -> torch.Tensor:
-    """out[M,N] = epilogue(a[M,K] @ w[N,K].T); bf16 in/out, fp32 accumulate in TMEM (dfd_gemm_bf16)."""
+              out: Optional[torch.Tensor] = None, tile_n: int = 0, residual_op: int = 0) -> torch.Tensor:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K].T); bf16 in/out, fp32 accumulate in TMEM (dfd_gemm_bf16).
+    act: 0 none, 1 gelu_tanh, 2 gelu_erf, 3 sigmoid; residual_op: 0 add, 1 multiply."""
     _need_cuda(a, w, bias, pos, residual, out)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
@@ -50,6 +51,7 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = 0, pos=
     epi.ln_dim = ln_dim
     epi.ln_eps = ln_eps
     epi.stats_out = _p(stats_out)
+    epi.residual_op = residual_op
     lib = _lib.load()
     if tile_n:
         rc = lib.dfd_gemm_bf16_tile(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
@@ -346,6 +348,43 @@ def score_epilogue(params: ScoreParams, z_sig: torch.Tensor, feats: Optional[tor
 
 
 FUSION_PARAM_ORDER = ("mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias", "temp.T")
+
+
+def dwconv3x3_bf16(x: torch.Tensor, w9: torch.Tensor, bias: Optional[torch.Tensor], B: int, H: int, W: int,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Depthwise 3x3 convolution (zero padding 1) on token-major bf16 activations x [B*H*W, E]; w9 fp32 [E, 9]."""
+    _need_cuda(x, w9, bias, out)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[0] == B * H * W
+    E = x.shape[1]
+    assert w9.dtype == torch.float32 and w9.shape == (E, 9) and w9.is_contiguous()
+    if out is None:
+        out = torch.empty((B * H * W, E), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().dfd_dwconv3x3_bf16(x.data_ptr(), x.stride(0), w9.data_ptr(), _p(bias), out.data_ptr(), out.stride(0),
+                                         B, H, W, E, current_stream()))
+    return out
+
+
+def seg_head_upsample(x: torch.Tensor, w: torch.Tensor, bias: float, B: int, H: int, W: int, S: int) -> torch.Tensor:
+    """1x1 conv E -> 1 then bilinear (align_corners=False) resize to S x S: x bf16 [B*H*W, E] -> fp32 [B, 1, S, S]."""
+    _need_cuda(x, w)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[0] == B * H * W
+    assert w.dtype == torch.float32 and w.numel() == x.shape[1] and w.is_contiguous()
+    low = torch.empty((B * H * W,), dtype=torch.float32, device=x.device)
+    out = torch.empty((B, 1, S, S), dtype=torch.float32, device=x.device)
+    check(_lib.load().dfd_seg_head_upsample(x.data_ptr(), x.stride(0), w.data_ptr(), float(bias), B, H, W, x.shape[1], S,
+                                            low.data_ptr(), out.data_ptr(), current_stream()))
+    return out
+
+
+def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """x bf16 [B,K] @ w fp32 [N,K].T + bias -> fp32 [B,N] (tiny heads: one warp per output)."""
+    _need_cuda(x, w, bias)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    assert w.dtype == torch.float32 and w.dim() == 2 and w.shape[1] == x.shape[1] and w.is_contiguous()
+    out = torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device)
+    check(_lib.load().dfd_linear_small(x.data_ptr(), x.stride(0), w.data_ptr(), _p(bias), out.data_ptr(), x.shape[0],
+                                       w.shape[0], x.shape[1], current_stream()))
+    return out
 
 
 FREQMLP_PARAM_ORDER = ("contrast.alpha", "contrast.beta", "band.gates") + tuple(

@@ -58,13 +58,15 @@ DFD_API int64_t dfd_launch_count(void);
  *                     mean/rstd from ln_rowstats[m] = (Σx, Σx²) over ln_dim columns, eps ln_eps
  *   if (bias)     v += bias[n]
  *   if (act == 1) v = gelu_tanh(v)             HF:modeling_siglip.py:323-327 (gelu_pytorch_tanh)
+ *      act == 2: exact erf GELU, act == 3: sigmoid   (nn.GELU() / nn.Sigmoid() of SegFormerStrongDecoder,
+ *                                                     Siglip2sidafrozen.py:704-722)
  *   if (pos)      v += pos[(m % pos_rows)·N + n]   HF:modeling_siglip.py:179-185 (position embedding)
  *   if (residual) v += residual[m·ldr + n]     HF:modeling_siglip.py:354,359 (residual adds)
  *   C[m·ldc + n] = bf16(v);  if (stats_out) stats_out[m] += (Σ_n bf16(v), Σ_n bf16(v)²)  (atomics)
  */
 typedef struct dfd_gemm_epilogue {
   const float* bias;         /* [N] fp32 or NULL */
-  int act;                   /* 0 none, 1 gelu_tanh */
+  int act;                   /* 0 none, 1 gelu_tanh, 2 gelu_erf, 3 sigmoid */
   const float* pos;          /* [pos_rows, N] fp32 or NULL */
   int pos_rows;
   const void* residual;      /* bf16 [M, ldr] or NULL; may alias C */
@@ -74,6 +76,7 @@ typedef struct dfd_gemm_epilogue {
   int ln_dim;
   float ln_eps;
   float* stats_out;          /* [M,2] fp32, accumulated atomically, or NULL */
+  int residual_op;           /* 0: v += residual (default), 1: v *= residual (gating: Siglip2sidafrozen.py:737) */
 } dfd_gemm_epilogue;
 
 /* C[M,N] (bf16) = epi(A[M,K] (bf16, lda) · W[N,K]ᵀ (bf16, ldw)), fp32 accumulate in TMEM.
@@ -202,6 +205,20 @@ DFD_API int dfd_gray256(const void* rgb_u8, int B, int H, int W, int clahe, cons
 DFD_API int dfd_freqmlp_fwd_bwd(const float* params6494, const float* mean24, const float* std24, const float* feats,
                                 const float* y, int B, float inv_global_batch, float dropout_p, uint32_t seed,
                                 float* loss_sum, float* grads, float* logits, void* stream);
+
+/* SegFormerStrongDecoder / SigLIP2_MTL (Siglip2sidafrozen.py:698-803), the parts that are not GEMMs.  Activations are
+ * token-major bf16 [B·H·W, C] with a leading dimension; the LinearProj and 1x1-convolution layers are dfd_gemm_bf16 calls
+ * (act 2 = erf GELU, act 3 = sigmoid, residual_op 1 = gating).
+ *   dfd_dwconv3x3_bf16     nn.Conv2d(E, E, 3, padding=1, groups=E) (:711); w9 = weight[E,1,3,3] flattened to [E,9] fp32
+ *   dfd_seg_head_upsample  self.head(F.interpolate(x, (S,S), mode="bilinear", align_corners=False)) (:740-741) computed as
+ *                          upsample(head(x)) — both linear, so they commute; low_scratch: B·H·W floats; out [B,S,S] fp32
+ *   dfd_linear_small       nn.Linear(hidden, 3) on the pooled embedding (:777,789): x bf16 [B,K], w fp32 [N,K] */
+DFD_API int dfd_dwconv3x3_bf16(const void* x, int64_t ldx, const float* w9, const float* bias, void* out, int64_t ldo,
+                               int B, int H, int W, int E, void* stream);
+DFD_API int dfd_seg_head_upsample(const void* x, int64_t ldx, const float* w, float bias, int B, int H, int W, int E,
+                                  int S, float* low_scratch, float* out, void* stream);
+DFD_API int dfd_linear_small(const void* x, int64_t ldx, const float* w, const float* bias, float* out, int B, int N,
+                             int K, void* stream);
 
 /* Score epilogue: FreqMLP + fusion + temperature + CORAL, one warp per sample.
  *  gen 1 (shipped siglip/ safetensors files; deepfake-detector-v2/app.py:601-628,691-709,1355-1396):

@@ -243,6 +243,27 @@ def make_freq_train():
     print("freq train golden: loss", float(loss), "|grad|", float(grads.norm()))
 
 
+def make_decoder():
+    """SegFormerStrongDecoder of the reference (Siglip2sidafrozen.py:698-742), instantiated from its own source text with
+    seeded weights, on seeded hidden states: pins oracle/decoder_ref.py."""
+    from oracle import decoder_ref as D
+
+    ns = base_namespace()
+    ns.update({"List": __import__("typing").List, "Tuple": __import__("typing").Tuple})
+    extract(f"{REF}/Siglip2sidafrozen.py", {"LinearProj", "SegFormerStrongDecoder"}, ns)
+    C, K, E, grid, S, B = 64, 4, 32, 5, 70, 2
+    sd = D.init_decoder_state(C, K, E, seed=3)
+    dec = ns["SegFormerStrongDecoder"]([C] * K, embed_dim=E, dropout_rate=0.0).eval()
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}, strict=True)
+    g = torch.Generator().manual_seed(9)
+    hs = [torch.randn(B, grid * grid, C, generator=g) for _ in range(K)]
+    with torch.no_grad():
+        out = dec(hs, (grid, grid), target_size=S)
+    np.savez_compressed(os.path.join(OUT, "decoder_golden.npz"), hidden=torch.stack(hs).numpy(), seg=out.numpy(),
+                        dims=np.array([C, K, E, grid, S, B], dtype=np.int32))
+    print("decoder golden:", tuple(out.shape), float(out.abs().max()))
+
+
 def make_heads():
     """Classifier heads as the reference defines them (inference_ai_human_images.py:131-138;
     train_fusion_head_only.py:84-99), fed seeded pooled embeddings."""
@@ -335,11 +356,13 @@ def make_backbone():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["scoring", "heads", "backbone", "gray", "freq_train"]
+    which = sys.argv[1:] or ["scoring", "heads", "backbone", "gray", "freq_train", "decoder"]
     if "gray" in which:
         make_gray()
     if "freq_train" in which:
         make_freq_train()
+    if "decoder" in which:
+        make_decoder()
     if "scoring" in which:
         make_scoring()
     if "heads" in which:

@@ -52,6 +52,11 @@ def golden_freq_train():
 
 
 @pytest.fixture(scope="session")
+def golden_decoder():
+    return np.load(os.path.join(GOLDEN, "decoder_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_gray():
     return np.load(os.path.join(GOLDEN, "gray_golden.npz"))
 

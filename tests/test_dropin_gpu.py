@@ -371,3 +371,46 @@ def test_fit_freq_mlp_matches_reference_loop(tmp_path):
     z = fm(feats.to(DEV))
     model.load_state_dict(best)
     assert (z - model(feats.to(DEV))).abs().max() < 1e-4
+
+
+def test_segformer_decoder_matches_reference_golden(golden_decoder):
+    """dfd.mtl.SegFormerStrongDecoder vs the reference's own class (fp32) on its golden inputs: bf16 GEMM chain."""
+    from dfd import mtl
+    from oracle import decoder_ref as D
+
+    g = golden_decoder
+    C, K, E, grid, S, B = (int(v) for v in g["dims"])
+    dec = mtl.SegFormerStrongDecoder(K, E, DEV).load_state_dict(D.init_decoder_state(C, K, E, 3), prefix="decoder.")
+    hs = [torch.from_numpy(h).reshape(B * grid * grid, C).to(DEV, torch.bfloat16) for h in g["hidden"]]
+    out = dec(hs, B, grid, S).cpu().numpy()
+    ref = g["seg"]
+    # five bf16 GEMMs deep; logits of magnitude ~0.35: 1 % of the range
+    assert np.abs(out - ref).max() < 0.01 * max(1.0, float(np.abs(ref).max()) / 0.35), np.abs(out - ref).max()
+    assert np.corrcoef(out.ravel(), ref.ravel())[0, 1] > 0.9995
+
+
+def test_siglip2_mtl_end_to_end():
+    """SigLIP2_MTL (encoder taps + 3-class head + decoder) vs the fp32 oracle chain at a small architecture."""
+    from dfd import mtl
+    from oracle import decoder_ref as D
+    from oracle import siglip_ref as R
+
+    name = "small-hd72"                      # 210 px, 15 x 15 tokens, hidden 288, 3 layers
+    c = R.CONFIGS[name]
+    seg_layers, E = (0, 1, -1), 64
+    sd = {"encoder.vision_model." + k: v for k, v in R.init_state_dict(c, 0).items()}
+    sd.update(D.init_decoder_state(c.hidden_size, len(seg_layers), E, seed=4))
+    model = mtl.SigLIP2_MTL(name, 0, max_batch=2, seg_layers=seg_layers, embed_dim=E).load_state_dict(sd)
+    img = R.synthetic_images(2, c.image_size, 3)
+    cls, seg = model(img.to(DEV))
+    o = R.siglip_vision_forward(R.init_state_dict(c, 0), c, R.preprocess_u8(img), "fp32", output_hidden_states=True)
+    hs = o["hidden_states"]
+    feats = [hs[i + 1 if i >= 0 else len(hs) - 1] for i in seg_layers]
+    seg_ref = D.decoder_forward(sd, feats, 15, c.image_size)
+    cls_ref = D.cls_head(sd, o["pooler_output"])
+    torch.cuda.synchronize()
+    assert tuple(seg.shape) == (2, 1, 210, 210) and tuple(cls.shape) == (2, 3)
+    assert (cls.cpu() - cls_ref).abs().max() < 2e-2 * max(1.0, float(cls_ref.abs().max()))
+    scale = float(seg_ref.abs().max())
+    assert (seg.cpu() - seg_ref).abs().max() < 0.03 * max(scale, 0.3), ((seg.cpu() - seg_ref).abs().max(), scale)
+    assert np.corrcoef(seg.cpu().numpy().ravel(), seg_ref.numpy().ravel())[0, 1] > 0.999

@@ -617,3 +617,72 @@ def test_freqmlp_dropout_is_unbiased_and_seeded():
     assert torch.allclose(a[1], b[1], atol=1e-6)            # same seed, same masks (up to atomic ordering)
     assert not torch.allclose(a[1], c[1], atol=1e-6)        # different seed, different masks
     assert abs(a[0].item() - base[0].item()) < 0.2          # 5 % inverted dropout perturbs the loss only mildly
+
+
+# ---------------------------------------------------------------------------------------------------
+# SegFormer decoder pieces (SigLIP2_MTL)
+# ---------------------------------------------------------------------------------------------------
+def test_gemm_decoder_epilogues():
+    """act 2 (erf GELU), act 3 (sigmoid) and the multiplicative residual (gate)."""
+    from dfd import ops
+
+    M, N, K = 700, 320, 256
+    g = torch.Generator(device="cpu").manual_seed(21)
+    a = _bf(torch.randn(M, K, generator=g)).to(DEV)
+    w = _bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    x = _bf(torch.randn(M, N, generator=g)).to(DEV)
+    acc = a.float() @ w.float().t() + bias
+
+    def close(out, ref, what):
+        err = (out.float() - ref).abs()
+        assert bool((err <= 2.0 ** -8 * ref.abs() + 2e-3).all()), f"{what}: {err.max().item()}"
+
+    close(ops.gemm_bf16(a, w, bias=bias, act=2), torch.nn.functional.gelu(acc), "gelu_erf")
+    close(ops.gemm_bf16(a, w, bias=bias, act=3), torch.sigmoid(acc), "sigmoid")
+    close(ops.gemm_bf16(a, w, bias=bias, act=3, residual=x, residual_op=1), torch.sigmoid(acc) * x.float(), "gate")
+    # output into a column slice of a wider matrix (how the decoder concatenates its branches)
+    wide = torch.zeros(M, 3 * N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm_bf16(a, w, bias=bias, act=2, out=wide[:, N:2 * N])
+    close(wide[:, N:2 * N], torch.nn.functional.gelu(acc), "slice")
+    assert float(wide[:, :N].abs().max()) == 0.0 and float(wide[:, 2 * N:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,H,W,E", [(2, 14, 14, 256), (3, 5, 7, 32), (1, 1, 1, 8), (2, 27, 27, 64)])
+def test_dwconv3x3(B, H, W, E):
+    from dfd import ops
+
+    g = torch.Generator(device="cpu").manual_seed(H * W + E)
+    x = _bf(torch.randn(B * H * W, E, generator=g))
+    w = torch.randn(E, 1, 3, 3, generator=g) / 3
+    b = torch.randn(E, generator=g)
+    out = ops.dwconv3x3_bf16(x.to(DEV), w.reshape(E, 9).contiguous().to(DEV), b.to(DEV), B, H, W)
+    ref = torch.nn.functional.conv2d(x.float().reshape(B, H, W, E).permute(0, 3, 1, 2), w, b, padding=1, groups=E)
+    ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, E)
+    torch.cuda.synchronize()
+    err = (out.float().cpu() - ref).abs()
+    assert bool((err <= 2.0 ** -8 * ref.abs() + 1e-4).all()), err.max().item()
+
+
+@pytest.mark.parametrize("B,H,S,E", [(2, 14, 224, 256), (3, 5, 70, 32), (1, 27, 384, 64), (2, 4, 4, 8)])
+def test_seg_head_upsample(B, H, S, E):
+    from dfd import ops
+
+    g = torch.Generator(device="cpu").manual_seed(H + S)
+    x = _bf(torch.randn(B * H * H, E, generator=g))
+    w = torch.randn(E, generator=g) / math.sqrt(E)
+    out = ops.seg_head_upsample(x.to(DEV), w.to(DEV), 0.25, B, H, H, S).cpu()
+    feat = x.float().reshape(B, H, H, E).permute(0, 3, 1, 2)
+    up = torch.nn.functional.interpolate(feat, size=(S, S), mode="bilinear", align_corners=False)   # reference order:
+    ref = torch.nn.functional.conv2d(up, w.reshape(1, E, 1, 1), torch.tensor([0.25]))              # upsample, then head
+    assert (out - ref).abs().max() < 1e-4
+
+
+def test_linear_small():
+    from dfd import ops
+
+    g = torch.Generator(device="cpu").manual_seed(8)
+    x = _bf(torch.randn(37, 1152, generator=g))
+    w, b = torch.randn(3, 1152, generator=g) / 34, torch.randn(3, generator=g)
+    out = ops.linear_small(x.to(DEV), w.to(DEV), b.to(DEV)).cpu()
+    assert (out - (x.float() @ w.t() + b)).abs().max() < 1e-4

@@ -198,3 +198,13 @@ def test_freqmlp_grad_oracle_matches_reference_class(golden_freq_train):
     assert abs(loss - float(g["loss"])) < 1e-6
     assert np.abs(grads - g["grads"]).max() < 2e-6 and grads.shape == (6494,)
     assert np.abs(out - g["logits"]).max() < 1e-5
+
+
+def test_decoder_oracle_matches_reference_class(golden_decoder):
+    """oracle/decoder_ref.py vs the reference's own SegFormerStrongDecoder (make_golden.py)."""
+    from oracle import decoder_ref as D
+
+    g = golden_decoder
+    C, K, E, grid, S, B = (int(v) for v in g["dims"])
+    out = D.decoder_forward(D.init_decoder_state(C, K, E, 3), [torch.from_numpy(h) for h in g["hidden"]], grid, S)
+    assert np.abs(out.numpy() - g["seg"]).max() < 1e-6
