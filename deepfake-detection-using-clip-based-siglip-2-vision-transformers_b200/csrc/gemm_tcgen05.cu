@@ -86,6 +86,11 @@ __device__ __forceinline__ float2 gelu_tanh_fast2(float2 x) {
   return ffma2(hx, t, hx);
 }
 
+__device__ __noinline__ float2 act_rare(float2 v, int act) {
+  if (act == 2) return make_float2(gelu_erf(v.x), gelu_erf(v.y));   // exact erf GELU (nn.GELU() default)
+  return make_float2(1.f / (1.f + __expf(-v.x)), 1.f / (1.f + __expf(-v.y)));  // act == 3: sigmoid
+}
+
 template <int BN, int CG, int RES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -391,13 +396,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             if (epi.act == 1) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) v[j] = gelu_tanh_fast2(v[j]);
-            } else if (epi.act == 2) {  // exact erf GELU (nn.GELU() default: the SegFormer decoder of SigLIP2_MTL)
+            } else if (epi.act >= 2) {  // erf GELU / sigmoid (SegFormer decoder of SigLIP2_MTL): out of line, so that the
+              // backbone's epilogue keeps its registers and schedule (inlined erff cost the base-224 engine 10 %)
 #pragma unroll
-              for (int j = 0; j < 4; ++j) v[j] = make_float2(gelu_erf(v[j].x), gelu_erf(v[j].y));
-            } else if (epi.act == 3) {  // sigmoid
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                v[j] = make_float2(1.f / (1.f + __expf(-v[j].x)), 1.f / (1.f + __expf(-v[j].y)));
+              for (int j = 0; j < 4; ++j) v[j] = act_rare(v[j], epi.act);
             }
             if (pos_row != nullptr) {
               const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos_row + cc));
