@@ -342,19 +342,13 @@ int attention_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B
   const int smem = (kBQ + 4 * kBKV) * kLds * 2;
   const float scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((N + kBQ - 1) / kBQ, H, B);
-  static bool attr[2] = {false, false};
+  static SmemOptIn smem_once[2];
   if (hd == 64) {
-    if (!attr[0]) {
-      DFD_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr[0] = true;
-    }
+    if (int rc = ensure_dynamic_smem(smem_once[0], attention_fwd_kernel<64>, smem)) return rc;
     attention_fwd_kernel<64><<<grid, kAttnThreads, smem, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(qkv), ldqkv, reinterpret_cast<__nv_bfloat16*>(out), ldo, N, H, scale_log2);
   } else {
-    if (!attr[1]) {
-      DFD_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr[1] = true;
-    }
+    if (int rc = ensure_dynamic_smem(smem_once[1], attention_fwd_kernel<72>, smem)) return rc;
     attention_fwd_kernel<72><<<grid, kAttnThreads, smem, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(qkv), ldqkv, reinterpret_cast<__nv_bfloat16*>(out), ldo, N, H, scale_log2);
   }

@@ -361,21 +361,13 @@ int attention_tc_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, in
   }
   const float scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((N + kQ - 1) / kQ, H, B);
-  static bool attr[2] = {false, false};
+  static SmemOptIn smem_once[2];
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   if (hd == 64) {
-    if (!attr[0]) {
-      DFD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    AttnSmem<64>::kTotal));
-      attr[0] = true;
-    }
+    if (int rc2 = ensure_dynamic_smem(smem_once[0], attention_tc_kernel<64>, AttnSmem<64>::kTotal)) return rc2;
     attention_tc_kernel<64><<<grid, kAttnThreads, AttnSmem<64>::kTotal, st>>>(tmMain, tmTail, o, ldo, N, H, scale_log2);
   } else {
-    if (!attr[1]) {
-      DFD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    AttnSmem<72>::kTotal));
-      attr[1] = true;
-    }
+    if (int rc2 = ensure_dynamic_smem(smem_once[1], attention_tc_kernel<72>, AttnSmem<72>::kTotal)) return rc2;
     attention_tc_kernel<72><<<grid, kAttnThreads, AttnSmem<72>::kTotal, st>>>(tmMain, tmTail, o, ldo, N, H, scale_log2);
   }
   DFD_LAUNCH_CHECK();

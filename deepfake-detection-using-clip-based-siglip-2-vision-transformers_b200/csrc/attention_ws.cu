@@ -362,11 +362,8 @@ static int launch_ws(const void* qkv, int64_t ldqkv, __nv_bfloat16* out, int64_t
     rc = make_tmap_qkv_4d(&tmTail, qkv, HD, 3 * H, N, B, ldqkv, 16, 64, 1);
     if (rc != DFD_OK) return rc;
   }
-  static bool attr = false;
-  if (!attr) {
-    DFD_CUDA(cudaFuncSetAttribute(attention_ws_kernel<HD, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr = true;
-  }
+  static SmemOptIn smem_once;
+  if (int rc2 = ensure_dynamic_smem(smem_once, attention_ws_kernel<HD, KV>, S::kTotal)) return rc2;
   const int slots = S::kCtasPerSm * kNumSMs;
   const int grid = n_items < slots ? n_items : slots;
   attention_ws_kernel<HD, KV><<<grid, S::kThreads, S::kTotal, st>>>(tmMain, tmTail, out, ldo, N, H, n_items, scale_log2);

@@ -47,6 +47,25 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     if (_e != cudaSuccess) return ::dfd::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-(function, DEVICE) setting: remember it per device, so that a
+// process that drives several GPUs (or changes device between calls) still launches correctly.  One instance per kernel
+// instantiation (a function-local static at the launch site).
+struct SmemOptIn {
+  unsigned long long done = 0;  // bit d = set on device d (benign race: at worst the attribute is set twice)
+};
+#if defined(__CUDACC__)
+template <typename F>
+inline int ensure_dynamic_smem(SmemOptIn& once, F func, int bytes) {
+  int dev = 0;
+  DFD_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (once.done & bit) return DFD_OK;
+  DFD_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  once.done |= bit;
+  return DFD_OK;
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // internal (cross translation unit) entry points; the extern "C" wrappers and the engine call these
 // ---------------------------------------------------------------------------------------------

@@ -387,11 +387,8 @@ int freq_features(const float* gray256, int B, const uint8_t* lut_band, const in
   uint8_t* sc = reinterpret_cast<uint8_t*>(scratch);
   // zero the per-image spatial accumulators (they sit behind each image's half spectrum)
   DFD_CUDA(cudaMemset2DAsync(sc + kSpecBytes, kImgScratch, 0, kAccDoubles * 8, B, st));
-  static bool attr_set = false;
-  if (!attr_set) {
-    DFD_CUDA(cudaFuncSetAttribute(freq_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowsSmem));
-    attr_set = true;
-  }
+  static SmemOptIn smem_once;
+  if (int rc = ensure_dynamic_smem(smem_once, freq_rows_kernel, kRowsSmem)) return rc;
   freq_rows_kernel<<<dim3(kN / kBand, B), kThreads, kRowsSmem, st>>>(gray256, sc);
   DFD_LAUNCH_CHECK();
   freq_cols_kernel<<<B, kThreads, 0, st>>>(sc, lut_band, lut_rbin, lut_sector, eps, zscore, feats);

@@ -211,11 +211,8 @@ extern "C" DFD_API int dfd_freqmlp_fwd_bwd(const float* params6494, const float*
   DFD_REQUIRE(grads != nullptr || logits != nullptr, DFD_ERR_BAD_ARG, "freqmlp_fwd_bwd: nothing to compute");
   DFD_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, DFD_ERR_BAD_ARG, "freqmlp_fwd_bwd: dropout_p must be in [0, 1)");
   const int smem = (2 * (kNumParams + 2) + kWarps * kScratch) * (int)sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    DFD_CUDA(cudaFuncSetAttribute(freqmlp_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  static SmemOptIn smem_once;
+  if (int rc = ensure_dynamic_smem(smem_once, freqmlp_fwd_bwd_kernel, smem)) return rc;
   int grid = (B + kWarps - 1) / kWarps;
   if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
   freqmlp_fwd_bwd_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(

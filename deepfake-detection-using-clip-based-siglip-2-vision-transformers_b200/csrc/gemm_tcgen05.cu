@@ -522,12 +522,8 @@ template <int BN, int CG, int RES>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                        const CUtensorMap& tmR, int M, int N, int K, const EpiArgs& ea, cudaStream_t st) {
   using S = GemmSmem<BN, CG, RES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DFD_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CG, RES>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set = true;
-  }
+  static SmemOptIn smem_once;
+  if (int rc = ensure_dynamic_smem(smem_once, gemm_bf16_tcgen05_kernel<BN, CG, RES>, S::kTotal)) return rc;
   const int num_tiles = ((M + BM * CG - 1) / (BM * CG)) * ((N + BN - 1) / BN);
   const int max_units = kNumSMs / CG;
   const int units = num_tiles < max_units ? num_tiles : max_units;
