@@ -7,7 +7,10 @@
 //                      (Σy..Σy⁴, double), (b) the 2-level Haar energies, (c) 256-point row FFTs — two real
 //                      rows packed into one complex Stockham radix-4 FFT per warp — written as the
 //                      129-column half spectrum to scratch.
-//   freq_cols_kernel   grid B.  Each warp runs 256-point column FFTs over the 129 stored columns and folds
+//   freq_cols_kernel   grid (P, B), P = 1..4 CTAs per image so that small batches still fill the SMs (one CTA per
+//                      image left a 256-image batch latency bound at < 2 CTAs per SM); the CTAs interleave the 129
+//                      columns, write their partial accumulators to scratch, and the last one to finish (ticket) adds
+//                      them in a fixed order.  Each warp runs 256-point column FFTs over its stored columns and folds
 //                      |F|, log|F| and angle(F) of every bin AND of its Hermitian mirror into the band /
 //                      log-radius / sector / phase-histogram accumulators through host-built LUTs of the
 //                      (fft-shifted) 256² grid; thread 0 then finishes the 24 features.
@@ -16,6 +19,7 @@
 #include "dfd_common.cuh"
 
 #include <atomic>
+#include <cstddef>
 
 namespace dfd {
 
@@ -29,7 +33,11 @@ constexpr int kBand = 32;
 constexpr int kThreads = 256;
 constexpr int kAccDoubles = 32;  // per-image spatial accumulators: 8 srm moments (2 stencils x 4) + 8 haar + pad
 constexpr int64_t kSpecBytes = (int64_t)kN * kHalf * 8;
-constexpr int64_t kImgScratch = kSpecBytes + kAccDoubles * 8;
+constexpr int kMaxColParts = 4;          // CTAs that may share one image's column pass
+constexpr int kColPartBytes = 2048;      // one CTA's partial accumulators: ColAcc (1928 B) + 3 band energies (double)
+// per image: half spectrum | spatial accumulators (zeroed per call) | ticket counter (zeroed) + pad | column partials
+constexpr int64_t kZeroBytes = kAccDoubles * 8 + 16;
+constexpr int64_t kImgScratch = kSpecBytes + kZeroBytes + kMaxColParts * kColPartBytes;
 constexpr int kRowsBytes = (kBand + 2) * kN * 4;
 constexpr int kFftBytes = (kThreads / 32) * 2 * kN * 8;
 constexpr int kRowsSmem = kRowsBytes + kFftBytes + kN * 8;
@@ -208,6 +216,9 @@ struct ColAcc {
   int hist[50];
 };
 
+static_assert(sizeof(ColAcc) + 24 <= kColPartBytes && sizeof(ColAcc) % 4 == 0, "column-pass partials must fit their slot");
+static_assert(offsetof(ColAcc, logcnt) == (kThreads / 32) * 48 * 4, "float sums first, integer counts after");
+
 __device__ __forceinline__ void fold_bin(float re, float im, int sy, int sx, const uint8_t* __restrict__ lut_band,
                                          const int8_t* __restrict__ lut_rbin, const int8_t* __restrict__ lut_sector,
                                          ColAcc* A, int warp, double (&eb)[3]) {
@@ -235,7 +246,7 @@ __device__ __forceinline__ void fold_bin(float re, float im, int sy, int sx, con
 }
 
 __global__ void __launch_bounds__(kThreads)
-freq_cols_kernel(const uint8_t* __restrict__ scratch, const uint8_t* __restrict__ lut_band,
+freq_cols_kernel(uint8_t* __restrict__ scratch, const uint8_t* __restrict__ lut_band,
                  const int8_t* __restrict__ lut_rbin, const int8_t* __restrict__ lut_sector, float eps, int zscore,
                  float* __restrict__ feats) {
   __shared__ __align__(16) float2 fbuf[kThreads / 32][2][kN];
@@ -243,9 +254,10 @@ freq_cols_kernel(const uint8_t* __restrict__ scratch, const uint8_t* __restrict_
   __shared__ ColAcc A;
   __shared__ double ered[kThreads / 32][3];
 
-  const int b = blockIdx.x;
+  const int part = blockIdx.x, nparts = gridDim.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float2* spec = reinterpret_cast<const float2*>(scratch + (int64_t)b * kImgScratch);
+  uint8_t* img_scratch = scratch + (int64_t)b * kImgScratch;
+  const float2* spec = reinterpret_cast<const float2*>(img_scratch);
 
   fill_twiddles(tw);
   for (int i = threadIdx.x; i < (int)(sizeof(ColAcc) / 4); i += kThreads) reinterpret_cast<int*>(&A)[i] = 0;
@@ -254,7 +266,7 @@ freq_cols_kernel(const uint8_t* __restrict__ scratch, const uint8_t* __restrict_
   double eb[3] = {0.0, 0.0, 0.0};
   float2* fa = fbuf[warp][0];
   float2* fb = fbuf[warp][1];
-  for (int kx = warp; kx < kHalf; kx += kThreads / 32) {
+  for (int kx = part * (kThreads / 32) + warp; kx < kHalf; kx += nparts * (kThreads / 32)) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = lane + 32 * i;
@@ -286,13 +298,48 @@ freq_cols_kernel(const uint8_t* __restrict__ scratch, const uint8_t* __restrict_
     if (lane == 0) ered[warp][i] = v;
   }
   __syncthreads();
-  if (threadIdx.x != 0) return;
+  double E[3] = {0.0, 0.0, 0.0};
+  if (nparts > 1) {
+    // publish this CTA's partials, take a ticket; the last CTA of the image adds all partials in part order
+    __shared__ int s_ticket;
+    uint8_t* parts = img_scratch + kSpecBytes + kZeroBytes;
+    int* mine = reinterpret_cast<int*>(parts + part * kColPartBytes);
+    for (int i = threadIdx.x; i < (int)(sizeof(ColAcc) / 4); i += kThreads) mine[i] = reinterpret_cast<int*>(&A)[i];
+    if (threadIdx.x < 3) {
+      double t = 0.0;
+      for (int w = 0; w < kThreads / 32; ++w) t += ered[w][threadIdx.x];
+      reinterpret_cast<double*>(parts + part * kColPartBytes + 2048 - 24)[threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(reinterpret_cast<int*>(img_scratch + kSpecBytes + kAccDoubles * 8), 1);
+    __syncthreads();
+    if (s_ticket != nparts - 1) return;
+    __threadfence();
+    constexpr int kFloatWords = (kThreads / 32) * 48;  // logsum + secsum are float sums, the rest integer counts
+    for (int i = threadIdx.x; i < (int)(sizeof(ColAcc) / 4); i += kThreads) {
+      if (i < kFloatWords) {
+        float t = 0.f;
+        for (int q = 0; q < nparts; ++q) t += __ldcg(reinterpret_cast<const float*>(parts + q * kColPartBytes) + i);
+        reinterpret_cast<float*>(&A)[i] = t;
+      } else {
+        int t = 0;
+        for (int q = 0; q < nparts; ++q) t += __ldcg(reinterpret_cast<const int*>(parts + q * kColPartBytes) + i);
+        reinterpret_cast<int*>(&A)[i] = t;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    for (int q = 0; q < nparts; ++q)
+      for (int i = 0; i < 3; ++i) E[i] += __ldcg(reinterpret_cast<const double*>(parts + q * kColPartBytes + 2048 - 24) + i);
+  } else {
+    if (threadIdx.x != 0) return;
+    for (int w = 0; w < kThreads / 32; ++w)
+      for (int i = 0; i < 3; ++i) E[i] += ered[w][i];
+  }
 
   // ---- finish the 24 features (double scalars, like the reference's python floats) ----------------
   const double EPS = (double)eps;
-  double E[3] = {0.0, 0.0, 0.0};
-  for (int w = 0; w < kThreads / 32; ++w)
-    for (int i = 0; i < 3; ++i) E[i] += ered[w][i];
   const double Et = E[0] + E[1] + E[2] + EPS;
   double f[24];
   f[0] = E[0] / Et;
@@ -340,7 +387,7 @@ freq_cols_kernel(const uint8_t* __restrict__ scratch, const uint8_t* __restrict_
     }
     f[6] = (double)(-ent);
   }
-  const double* accg = reinterpret_cast<const double*>(scratch + (int64_t)b * kImgScratch + kSpecBytes);
+  const double* accg = reinterpret_cast<const double*>(img_scratch + kSpecBytes);
   for (int i = 0; i < 4; ++i) f[7 + i] = accg[8 + i] / (128.0 * 128.0);
   for (int i = 0; i < 4; ++i) f[11 + i] = accg[12 + i] / (64.0 * 64.0);
   for (int st = 0; st < 2; ++st) {
@@ -386,12 +433,14 @@ int freq_features(const float* gray256, int B, const uint8_t* lut_band, const in
               "freq_features: gray256 and scratch must be 16-byte aligned");
   uint8_t* sc = reinterpret_cast<uint8_t*>(scratch);
   // zero the per-image spatial accumulators (they sit behind each image's half spectrum)
-  DFD_CUDA(cudaMemset2DAsync(sc + kSpecBytes, kImgScratch, 0, kAccDoubles * 8, B, st));
+  DFD_CUDA(cudaMemset2DAsync(sc + kSpecBytes, kImgScratch, 0, kZeroBytes, B, st));
   static SmemOptIn smem_once;
   if (int rc = ensure_dynamic_smem(smem_once, freq_rows_kernel, kRowsSmem)) return rc;
   freq_rows_kernel<<<dim3(kN / kBand, B), kThreads, kRowsSmem, st>>>(gray256, sc);
   DFD_LAUNCH_CHECK();
-  freq_cols_kernel<<<B, kThreads, 0, st>>>(sc, lut_band, lut_rbin, lut_sector, eps, zscore, feats);
+  int parts = (4 * kNumSMs + B - 1) / B;  // aim at >= 4 CTAs per SM
+  parts = parts < 1 ? 1 : (parts > kMaxColParts ? kMaxColParts : parts);
+  freq_cols_kernel<<<dim3(parts, B), kThreads, 0, st>>>(sc, lut_band, lut_rbin, lut_sector, eps, zscore, feats);
   DFD_LAUNCH_CHECK();
   g_launches.fetch_add(2, std::memory_order_relaxed);
   return DFD_OK;
