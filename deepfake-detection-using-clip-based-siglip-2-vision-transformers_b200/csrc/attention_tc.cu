@@ -381,15 +381,20 @@ int attention_tc_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, in
 int attention_auto_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
                         float scale, cudaStream_t st) {
   if (N <= 256) return attention_ws_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, 64, st);
+  // attention_pq.cu (persistent, Q in TMEM) is 3-4 % faster timed alone at N = 729 but not inside the power-capped
+  // detect step (same-box A/B: 1465 / 1449 img/s with this kernel, 1432 / 1443 with pq) - see profiles/r01_attention_full.md
   return attention_tc_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, st);
 }
 
 }  // namespace dfd
 
 // Test / A-B hook: impl 0 = warp-level mma.sync kernel (attention.cu), 1 = tcgen05 kernel (this file),
-// 2 / 3 = persistent tcgen05 kernel (attention_ws.cu) with 64- / 128-key tiles.
+// 2 / 3 = persistent tcgen05 kernel (attention_ws.cu) with 64- / 128-key tiles, 4 = persistent with Q in TMEM
+// (attention_pq.cu).
 extern "C" DFD_API int dfd_attention_bf16_impl(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N,
                                                int H, int hd, float scale, int impl, void* stream) {
+  if (impl == 4)
+    return dfd::attention_pq_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));
   if (impl == 2 || impl == 3)
     return dfd::attention_ws_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, impl == 2 ? 64 : 128,
                                   reinterpret_cast<cudaStream_t>(stream));
