@@ -156,7 +156,8 @@ DFD_API int dfd_head_fwd(const dfd_head_weights* w, const void* pooled_bf16, int
  * energies, 3 SRM stencil moments.  lut = host-precomputed per-pixel LUTs of the 256² grid uploaded with
  * dfd_freq_set_luts (band id, log-radius bin, sector id), built by the host with the reference's own torch
  * ops.  eps: 1e-8 (trainers/app v2) or 1e-6 (appv3.py:570).  zscore!=0 applies the app's per-vector
- * z-scoring (app.py:840-846).  scratch: B·256·129·8 bytes. */
+ * z-scoring (app.py:840-846).  scratch: dfd_freq_scratch_bytes(B) bytes (per image the half spectrum plus the
+ * column-pass partial slots and counters). */
 DFD_API int dfd_freq_features(const float* gray256, int B, const uint8_t* lut_band,
                               const int8_t* lut_rbin, const int8_t* lut_sector, float eps, int zscore,
                               void* scratch, float* feats /*[B,24]*/, void* stream);
