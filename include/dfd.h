@@ -153,9 +153,8 @@ DFD_API int dfd_head_fwd(const dfd_head_weights* w, const void* pooled_bf16, int
 /* 24-d frequency feature vector per gray 256×256 fp32 image in [0,1]
  * (train_fusion_head_only.py:150-226 = FreqMLP trainer.py:91-177; app copy deepfake-detector-v2/app.py:752-846):
  * 2-D FFT magnitude band energies, log-spectrum slope, sector anisotropy, phase entropy, 2-level Haar
- * energies, 3 SRM stencil moments.  lut = host-precomputed per-pixel LUTs of the 256² grid uploaded with
- * dfd_freq_set_luts (band id, log-radius bin, sector id), built by the host with the reference's own torch
- * ops.  eps: 1e-8 (trainers/app v2) or 1e-6 (appv3.py:570).  zscore!=0 applies the app's per-vector
+ * energies, 3 SRM stencil moments.  lut_* = device pointers to per-pixel tables of the 256² grid (band id, log-radius bin, sector
+ * id) that the host builds once with the reference's own torch expressions (scoring.py build_freq_luts) and uploads.  eps: 1e-8 (trainers/app v2) or 1e-6 (appv3.py:570).  zscore!=0 applies the app's per-vector
  * z-scoring (app.py:840-846).  scratch: dfd_freq_scratch_bytes(B) bytes (per image the half spectrum plus the
  * column-pass partial slots and counters). */
 DFD_API int dfd_freq_features(const float* gray256, int B, const uint8_t* lut_band,
