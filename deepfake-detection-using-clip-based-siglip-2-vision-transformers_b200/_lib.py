@@ -107,7 +107,7 @@ SIGNATURES = {
     "dfd_patchify": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
     "dfd_map_attention_bf16": (_I, [_P, _L, _P, _P, _L, _I, _I, _I, _I, _F, _P]),
     "dfd_head_fwd": (_I, [C.POINTER(HeadWeights), _P, _L, _I, _P, _P, _P, _P, _P]),
-    "dfd_freq_features": (_I, [_P, _I, _P, _P, _P, _F, _I, _P, _P, _P]),
+    "dfd_freq_features": (_I, [_P, _I, _P, _F, _I, _P, _P, _P]),
     "dfd_freq_scratch_bytes": (_L, [_I]),
     "dfd_resample_ksize": (_I, [_I, _I]),
     "dfd_resample_coeffs_host": (_I, [_I, _I, _P, _P, _P]),

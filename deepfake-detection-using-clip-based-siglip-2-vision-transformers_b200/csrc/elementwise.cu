@@ -178,6 +178,61 @@ __global__ void __launch_bounds__(256) patchify_kernel(PatchArgs a) {
   }
 }
 
+// Fast path for the case every shipped caller hits (u8 NHWC input already on the patch grid, no resample): one CTA per
+// (image, patch row).  The P image rows of a patch row are one contiguous span of P*Win*3 bytes, and its G output rows
+// one contiguous span of G*lda bf16 — both are moved with 16-byte accesses through shared memory; the k -> (c, ky, kx)
+// index arithmetic becomes a table built once per CTA and the u8 -> normalised fp32 conversion a 256-entry table filled
+// with the same expression as fetch_pixel, so the result is bit-identical to the generic kernel.
+__global__ void __launch_bounds__(256) patchify_u8_rows_kernel(PatchArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int span = a.P * a.Win * 3;
+  float* val = reinterpret_cast<float*>(smem);                         // [256]
+  uint16_t* koff = reinterpret_cast<uint16_t*>(smem + 1024);           // [lda] (0xffff = K padding)
+  uint8_t* pix = smem + 1024 + (((int)a.lda * 2 + 15) & ~15);          // [span + 16]
+  const int b = blockIdx.x / a.G, gy = blockIdx.x - b * a.G;
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(a.pixels) + ((int64_t)b * a.Hin + (int64_t)gy * a.P) * a.Win * 3;
+  const int head = (int)(reinterpret_cast<uintptr_t>(src) & 15);       // pix[head + i] = src[i]
+  const int tid = threadIdx.x;
+  val[tid] = ((float)tid / 255.0f - 0.5f) / 0.5f;
+  const int PP = a.P * a.P;
+  for (int k = tid; k < (int)a.lda; k += 256) {
+    if (k < a.K) {
+      const int c = k / PP, r = k - c * PP;
+      const int ky = r / a.P, kx = r - ky * a.P;
+      koff[k] = (uint16_t)((ky * a.Win + kx) * 3 + c);
+    } else {
+      koff[k] = 0xffffu;
+    }
+  }
+  // aligned body with 16-byte loads, ragged ends byte by byte (never touches memory outside the span)
+  const int lead = head ? 16 - head : 0;
+  const int body = (span - lead) >> 4;
+  for (int i = tid; i < lead && i < span; i += 256) pix[head + i] = __ldg(src + i);
+  const uint4* src16 = reinterpret_cast<const uint4*>(src + lead);
+  uint4* pix16 = reinterpret_cast<uint4*>(pix + head + lead);
+  for (int i = tid; i < body; i += 256) pix16[i] = __ldg(src16 + i);
+  for (int i = lead + (body << 4) + tid; i < span; i += 256) pix[head + i] = __ldg(src + i);
+  __syncthreads();
+  const int vec_per_row = (int)(a.lda >> 3);
+  uint4* dst = reinterpret_cast<uint4*>(a.A + ((int64_t)b * a.G + gy) * a.G * a.lda);
+  for (int idx = tid; idx < a.G * vec_per_row; idx += 256) {
+    const int gx = idx / vec_per_row, vcol = idx - gx * vec_per_row;
+    const uint8_t* base = pix + head + gx * a.P * 3;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t o = koff[vcol * 8 + j];
+      v[j] = o == 0xffffu ? 0.f : val[base[o]];
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    dst[idx] = o;
+  }
+}
+
 }  // namespace
 
 int layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,
@@ -232,6 +287,14 @@ int patchify(const void* pixels, int pix_format, int B, int Hin, int Win, int S,
   a.sx = (float)Win / (float)S;
   a.A = reinterpret_cast<__nv_bfloat16*>(A);
   a.lda = lda;
+  const int64_t fast_smem = 1024 + ((lda * 2 + 15) & ~15ll) + (int64_t)P * Win * 3 + 16;
+  if (a.fmt == 0 && a.mode == 0 && fast_smem <= 48 * 1024 && (int64_t)P * Win * 3 < 0xffff && (int64_t)B * a.G < (1ll << 31) &&
+      (reinterpret_cast<uintptr_t>(A) & 15) == 0) {
+    patchify_u8_rows_kernel<<<B * a.G, 256, (size_t)fast_smem, st>>>(a);
+    DFD_LAUNCH_CHECK();
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return DFD_OK;
+  }
   const int64_t total = (int64_t)B * a.G * a.G * (lda >> 3);
   int64_t blocks = (total + 255) / 256;
   if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;

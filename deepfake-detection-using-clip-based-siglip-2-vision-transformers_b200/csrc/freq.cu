@@ -211,47 +211,60 @@ freq_rows_kernel(const float* __restrict__ gray, uint8_t* __restrict__ scratch) 
 struct ColAcc {
   float logsum[kThreads / 32][40];
   float secsum[kThreads / 32][8];
-  int logcnt[40];
-  int seccnt[8];
   int hist[50];
 };
 
 static_assert(sizeof(ColAcc) + 24 <= kColPartBytes && sizeof(ColAcc) % 4 == 0, "column-pass partials must fit their slot");
-static_assert(offsetof(ColAcc, logcnt) == (kThreads / 32) * 48 * 4, "float sums first, integer counts after");
+static_assert(offsetof(ColAcc, hist) == (kThreads / 32) * 48 * 4, "float sums first, integer counts after");
 
-__device__ __forceinline__ void fold_bin(float re, float im, int sy, int sx, const uint8_t* __restrict__ lut_band,
-                                         const int8_t* __restrict__ lut_rbin, const int8_t* __restrict__ lut_sector,
-                                         ColAcc* A, int warp, double (&eb)[3]) {
-  const int idx = sy * kN + sx;
+// bins[key] += val for every lane with key >= 0, where `bins` belongs to this warp alone: lanes that share a key are summed
+// with shuffles and one lane adds the total (consecutive bins of a column fall into 1-3 distinct log-radius bins / sectors,
+// so this loop runs 1-3 times; shared-memory float atomics would serialise up to 32-way).  Convergent call required.
+__device__ __forceinline__ void warp_bin_add(float* bins, int key, float val, int lane) {
+  unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int k = __shfl_sync(0xffffffffu, key, leader);
+    const bool mine = key == k;
+    float v = mine ? val : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == leader) bins[k] += v;
+    todo &= ~__ballot_sync(0xffffffffu, mine);
+  }
+  __syncwarp();
+}
+
+// lut word of the shifted grid position (sy, sx), stored TRANSPOSED (index sx*256 + sy: the lanes of a warp walk sy, so a
+// warp reads 128 contiguous bytes): bits 0-7 band, 8-15 log-radius bin (int8, -1 = not counted), 16-23 sector (int8).
+__device__ __forceinline__ void fold_bin(float re, float im, int sy, int sx, const int32_t* __restrict__ lut, ColAcc* A,
+                                         int* whist, int warp, int lane, double (&eb)[3]) {
+  const int w = __ldg(lut + sx * kN + sy);
   const float mag = hypotf(re, im);
   const float ph = atan2f(im, re);
-  eb[__ldg(lut_band + idx)] += (double)mag;
-  const int rb = __ldg(lut_rbin + idx);
-  if (rb >= 0) {
-    atomicAdd(&A->logsum[warp][rb], logf(mag + 1e-6f));
-    atomicAdd(&A->logcnt[rb], 1);
-  }
-  const int sc = __ldg(lut_sector + idx);
-  if (sc >= 0) {
-    atomicAdd(&A->secsum[warp][sc], mag);
-    atomicAdd(&A->seccnt[sc], 1);
-  }
+  const int band = w & 0xff;
+  const double dm = (double)mag;
+  eb[0] += band == 0 ? dm : 0.0;
+  eb[1] += band == 1 ? dm : 0.0;
+  eb[2] += band == 2 ? dm : 0.0;
+  warp_bin_add(A->logsum[warp], (int)(int8_t)(w >> 8), logf(mag + 1e-6f), lane);
+  warp_bin_add(A->secsum[warp], (int)(int8_t)(w >> 16), mag, lane);
   // torch.histc(bins=50, min=-pi, max=pi): pos = (int)((x - min) / (max - min) * bins), x == max -> last bin
   const float minv = -3.14159274101257324f, maxv = 3.14159274101257324f;
   if (ph >= minv && ph <= maxv) {
     int pos = (int)((ph - minv) / (maxv - minv) * 50.0f);
     if (pos > 49) pos = 49;
-    atomicAdd(&A->hist[pos], 1);
+    atomicAdd(&whist[pos], 1);
   }
 }
 
 __global__ void __launch_bounds__(kThreads)
-freq_cols_kernel(uint8_t* __restrict__ scratch, const uint8_t* __restrict__ lut_band,
-                 const int8_t* __restrict__ lut_rbin, const int8_t* __restrict__ lut_sector, float eps, int zscore,
+freq_cols_kernel(uint8_t* __restrict__ scratch, const int32_t* __restrict__ lut, float eps, int zscore,
                  float* __restrict__ feats) {
   __shared__ __align__(16) float2 fbuf[kThreads / 32][2][kN];
   __shared__ float2 tw[kN];
   __shared__ ColAcc A;
+  __shared__ int whist[kThreads / 32][50];   // phase histogram, one copy per warp
   __shared__ double ered[kThreads / 32][3];
 
   const int part = blockIdx.x, nparts = gridDim.x, b = blockIdx.y;
@@ -261,18 +274,27 @@ freq_cols_kernel(uint8_t* __restrict__ scratch, const uint8_t* __restrict__ lut_
 
   fill_twiddles(tw);
   for (int i = threadIdx.x; i < (int)(sizeof(ColAcc) / 4); i += kThreads) reinterpret_cast<int*>(&A)[i] = 0;
+  for (int i = threadIdx.x; i < (kThreads / 32) * 50; i += kThreads) (&whist[0][0])[i] = 0;
   __syncthreads();
 
   double eb[3] = {0.0, 0.0, 0.0};
   float2* fa = fbuf[warp][0];
   float2* fb = fbuf[warp][1];
-  for (int kx = part * (kThreads / 32) + warp; kx < kHalf; kx += nparts * (kThreads / 32)) {
+  // the CTA takes 8 adjacent columns at a time (one per warp): loaded together, every row contributes 64 contiguous bytes
+  for (int kx0 = part * (kThreads / 32); kx0 < kHalf; kx0 += nparts * (kThreads / 32)) {
+    {
+      const int c = threadIdx.x & 7, r_in = threadIdx.x >> 3;
+      if (kx0 + c < kHalf) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = lane + 32 * i;
-      fa[r] = __ldg(spec + (int64_t)r * kHalf + kx);
+        for (int i = 0; i < 8; ++i) {
+          const int r = r_in + 32 * i;
+          fbuf[c][0][r] = __ldg(spec + (int64_t)r * kHalf + kx0 + c);
+        }
+      }
     }
-    __syncwarp();
+    __syncthreads();
+    const int kx = kx0 + warp;
+    if (kx < kHalf) {
     fft256_warp(fa, fb, tw, lane);
     const bool self_col = (kx == 0) || (kx == kN / 2);
     const int sx = (kx + kN / 2) & (kN - 1);
@@ -284,13 +306,20 @@ freq_cols_kernel(uint8_t* __restrict__ scratch, const uint8_t* __restrict__ lut_
       // the 4 self-conjugate bins of a real image have an exactly-zero imaginary part (torch yields +0)
       if (self_col && (ky == 0 || ky == kN / 2)) v.y = 0.0f;
       const int sy = (ky + kN / 2) & (kN - 1);
-      fold_bin(v.x, v.y, sy, sx, lut_band, lut_rbin, lut_sector, &A, warp, eb);
+      fold_bin(v.x, v.y, sy, sx, lut, &A, whist[warp], warp, lane, eb);
       if (!self_col) {
         const int sym = ((kN - ky) + kN / 2) & (kN - 1);
-        fold_bin(v.x, -v.y, sym, sxm, lut_band, lut_rbin, lut_sector, &A, warp, eb);
+        fold_bin(v.x, -v.y, sym, sxm, lut, &A, whist[warp], warp, lane, eb);
       }
     }
-    __syncwarp();
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 50) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) t += whist[w][threadIdx.x];
+    A.hist[threadIdx.x] = t;
   }
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -351,7 +380,8 @@ freq_cols_kernel(uint8_t* __restrict__ scratch, const uint8_t* __restrict__ lut_
     for (int i = 0; i < 39; ++i) {
       double s = 0.0;
       for (int w = 0; w < kThreads / 32; ++w) s += (double)A.logsum[w][i];
-      mu[i] = A.logcnt[i] > 0 ? (double)(float)(s / (double)A.logcnt[i]) : 0.0;
+      const int cnt = __ldg(lut + kN * kN + i);  // bins per log-radius ring: geometry only, counted by the host
+      mu[i] = cnt > 0 ? (double)(float)(s / (double)cnt) : 0.0;
       mbar += mu[i];
     }
     mbar /= 39.0;
@@ -368,7 +398,8 @@ freq_cols_kernel(uint8_t* __restrict__ scratch, const uint8_t* __restrict__ lut_
     for (int k = 0; k < 8; ++k) {
       double s = 0.0;
       for (int w = 0; w < kThreads / 32; ++w) s += (double)A.secsum[w][k];
-      sm[k] = A.seccnt[k] > 0 ? (double)(float)(s / (double)A.seccnt[k]) : 0.0;
+      const int cnt = __ldg(lut + kN * kN + 40 + k);
+      sm[k] = cnt > 0 ? (double)(float)(s / (double)cnt) : 0.0;
       mbar += sm[k];
     }
     mbar /= 8.0;
@@ -423,11 +454,9 @@ freq_cols_kernel(uint8_t* __restrict__ scratch, const uint8_t* __restrict__ lut_
 
 int64_t freq_scratch_bytes(int B) { return B > 0 ? (int64_t)B * kImgScratch : 0; }
 
-int freq_features(const float* gray256, int B, const uint8_t* lut_band, const int8_t* lut_rbin,
-                  const int8_t* lut_sector, float eps, int zscore, void* scratch, float* feats,
+int freq_features(const float* gray256, int B, const int32_t* lut, float eps, int zscore, void* scratch, float* feats,
                   cudaStream_t st) {
-  DFD_REQUIRE(gray256 && lut_band && lut_rbin && lut_sector && scratch && feats, DFD_ERR_BAD_ARG,
-              "freq_features: null pointer");
+  DFD_REQUIRE(gray256 && lut && scratch && feats, DFD_ERR_BAD_ARG, "freq_features: null pointer");
   DFD_REQUIRE(B > 0 && B <= 65535, DFD_ERR_SHAPE, "freq_features: B must be in 1..65535");
   DFD_REQUIRE(((uintptr_t)gray256 % 16 == 0) && ((uintptr_t)scratch % 16 == 0), DFD_ERR_BAD_ARG,
               "freq_features: gray256 and scratch must be 16-byte aligned");
@@ -440,7 +469,7 @@ int freq_features(const float* gray256, int B, const uint8_t* lut_band, const in
   DFD_LAUNCH_CHECK();
   int parts = (4 * kNumSMs + B - 1) / B;  // aim at >= 4 CTAs per SM
   parts = parts < 1 ? 1 : (parts > kMaxColParts ? kMaxColParts : parts);
-  freq_cols_kernel<<<dim3(parts, B), kThreads, 0, st>>>(sc, lut_band, lut_rbin, lut_sector, eps, zscore, feats);
+  freq_cols_kernel<<<dim3(parts, B), kThreads, 0, st>>>(sc, lut, eps, zscore, feats);
   DFD_LAUNCH_CHECK();
   g_launches.fetch_add(2, std::memory_order_relaxed);
   return DFD_OK;
@@ -448,10 +477,8 @@ int freq_features(const float* gray256, int B, const uint8_t* lut_band, const in
 
 }  // namespace dfd
 
-extern "C" DFD_API int dfd_freq_features(const float* gray256, int B, const uint8_t* lut_band,
-                                         const int8_t* lut_rbin, const int8_t* lut_sector, float eps,
-                                         int zscore, void* scratch, float* feats, void* stream) {
-  return dfd::freq_features(gray256, B, lut_band, lut_rbin, lut_sector, eps, zscore, scratch, feats,
-                            reinterpret_cast<cudaStream_t>(stream));
+extern "C" DFD_API int dfd_freq_features(const float* gray256, int B, const int32_t* lut, float eps, int zscore,
+                                         void* scratch, float* feats, void* stream) {
+  return dfd::freq_features(gray256, B, lut, eps, zscore, scratch, feats, reinterpret_cast<cudaStream_t>(stream));
 }
 extern "C" DFD_API int64_t dfd_freq_scratch_bytes(int B) { return dfd::freq_scratch_bytes(B); }

@@ -192,7 +192,7 @@ def head_fwd(head: HeadParams, pooled: torch.Tensor, prototypes: Optional[torch.
     return feats, z, pp
 
 
-def freq_features(gray256: torch.Tensor, luts, eps: float = 1e-8, zscore: bool = False,
+def freq_features(gray256: torch.Tensor, luts: torch.Tensor, eps: float = 1e-8, zscore: bool = False,
                   scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
     """gray256 f32 [B,256,256] in [0,1] -> 24-d features f32 [B,24] (dfd_freq_features)."""
     _need_cuda(gray256)
@@ -202,10 +202,10 @@ def freq_features(gray256: torch.Tensor, luts, eps: float = 1e-8, zscore: bool =
     need = lib.dfd_freq_scratch_bytes(B)
     if scratch is None or scratch.numel() < need:
         scratch = torch.empty((need,), dtype=torch.uint8, device=gray256.device)
-    band, rbin, sector = luts
+    assert luts.dtype == torch.int32 and luts.numel() == 256 * 256 + 48 and luts.is_contiguous() and luts.device == gray256.device
     feats = torch.empty((B, 24), dtype=torch.float32, device=gray256.device)
-    check(lib.dfd_freq_features(gray256.data_ptr(), B, band.data_ptr(), rbin.data_ptr(), sector.data_ptr(), eps,
-                                int(zscore), scratch.data_ptr(), feats.data_ptr(), current_stream()))
+    check(lib.dfd_freq_features(gray256.data_ptr(), B, luts.data_ptr(), eps, int(zscore), scratch.data_ptr(),
+                                feats.data_ptr(), current_stream()))
     return feats
 
 

@@ -22,9 +22,9 @@ FREQ_TEMP = 1.25     # deepfake-detector-v2/app.py:280
 _N = 256
 
 
-def build_freq_luts(device) -> tuple:
-    """Per-pixel lookup tables over the fft-SHIFTED 256x256 grid, built with the very torch ops the reference
-    uses so every comparison / bin edge rounds identically (train_fusion_head_only.py:156-169,193-197):
+def build_freq_tables() -> tuple:
+    """Per-pixel lookup tables over the fft-SHIFTED 256x256 grid ([sy, sx], CPU), built with the very torch ops the
+    reference uses so every comparison / bin edge rounds identically (train_fusion_head_only.py:156-169,193-197):
       band   u8  0: r<=r1, 1: r1<r<=r2, 2: r>r2
       rbin   i8  log-radius bin 0..38 (bucketize(r+1, logspace(0, log10(rmax+1), 40)) - 1), -1 = not counted
       sector i8  0..7 for a0 <= atan2(dy,dx) < a0+pi/4, -1 = in no sector (angle == pi)
@@ -44,7 +44,21 @@ def build_freq_luts(device) -> tuple:
     sector = torch.full((_N, _N), -1, dtype=torch.int8)
     for k, a0 in enumerate(np.linspace(-math.pi, math.pi, 8, endpoint=False)):
         sector[(ang >= a0) & (ang < a0 + math.pi / 4)] = k
-    return tuple(t.contiguous().to(device) for t in (band, rbin, sector))
+    return band.contiguous(), rbin.contiguous(), sector.contiguous()
+
+
+def pack_freq_luts(band: torch.Tensor, rbin: torch.Tensor, sector: torch.Tensor) -> torch.Tensor:
+    """The table dfd_freq_features reads (include/dfd.h): int32 [256*256 + 48] — one word per grid position, TRANSPOSED
+    (index sx*256 + sy) = band | (rbin & 0xff) << 8 | (sector & 0xff) << 16, then the populations of the 40 log-radius
+    bins and the 8 sectors (the denominators of the reference's masked `.mean()`s, which depend on geometry only)."""
+    word = band.to(torch.int32) | ((rbin.to(torch.int32) & 0xFF) << 8) | ((sector.to(torch.int32) & 0xFF) << 16)
+    logcnt = torch.bincount(rbin[rbin >= 0].to(torch.int64), minlength=40)[:40]
+    seccnt = torch.bincount(sector[sector >= 0].to(torch.int64), minlength=8)[:8]
+    return torch.cat([word.t().contiguous().flatten(), logcnt.to(torch.int32), seccnt.to(torch.int32)]).contiguous()
+
+
+def build_freq_luts(device) -> torch.Tensor:
+    return pack_freq_luts(*build_freq_tables()).to(device)
 
 
 def pil_to_gray256(pil, clahe: bool) -> np.ndarray:

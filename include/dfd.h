@@ -153,12 +153,14 @@ DFD_API int dfd_head_fwd(const dfd_head_weights* w, const void* pooled_bf16, int
 /* 24-d frequency feature vector per gray 256×256 fp32 image in [0,1]
  * (train_fusion_head_only.py:150-226 = FreqMLP trainer.py:91-177; app copy deepfake-detector-v2/app.py:752-846):
  * 2-D FFT magnitude band energies, log-spectrum slope, sector anisotropy, phase entropy, 2-level Haar
- * energies, 3 SRM stencil moments.  lut_* = device pointers to per-pixel tables of the 256² grid (band id, log-radius bin, sector
- * id) that the host builds once with the reference's own torch expressions (scoring.py build_freq_luts) and uploads.  eps: 1e-8 (trainers/app v2) or 1e-6 (appv3.py:570).  zscore!=0 applies the app's per-vector
+ * energies, 3 SRM stencil moments.  lut = device pointer to the per-pixel table of the fft-shifted 256² grid that the host builds
+ * once with the reference's own torch expressions (scoring.py build_freq_luts) and uploads: word [sx*256 + sy] (transposed, so
+ * a warp walking a spectrum column reads it contiguously) = band id (bits 0-7: 0 low, 1 mid, 2 high) | log-radius bin (bits
+ * 8-15, int8, -1 = not counted) | sector id (bits 16-23, int8, -1 = none); followed by 40 + 8 int32 bin populations (how many
+ * grid positions fall in each log-radius bin / sector — geometry only).  eps: 1e-8 (trainers/app v2) or 1e-6 (appv3.py:570).  zscore!=0 applies the app's per-vector
  * z-scoring (app.py:840-846).  scratch: dfd_freq_scratch_bytes(B) bytes (per image the half spectrum plus the
  * column-pass partial slots and counters). */
-DFD_API int dfd_freq_features(const float* gray256, int B, const uint8_t* lut_band,
-                              const int8_t* lut_rbin, const int8_t* lut_sector, float eps, int zscore,
+DFD_API int dfd_freq_features(const float* gray256, int B, const int32_t* lut /*[256*256 + 48]*/, float eps, int zscore,
                               void* scratch, float* feats /*[B,24]*/, void* stream);
 DFD_API int64_t dfd_freq_scratch_bytes(int B);
 

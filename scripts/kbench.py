@@ -88,6 +88,40 @@ def attention(B, arch):
           f"({by / med / 1e6 / PEAKS['hbm_gbs'] * 100:4.1f}% of measured)", flush=True)
 
 
+def memory_bound(B, arch):
+    """HBM-bound kernels of the detect step: algorithmic bytes / CUDA-event time, L2 flushed."""
+    from dfd import scoring
+
+    S, P, D, N, H = arch.image_size, arch.patch_size, arch.hidden_size, arch.tokens, arch.num_attention_heads
+    peak = PEAKS["hbm_gbs"]
+
+    def line(name, by, fn):
+        med, best = timeit(fn, iters=7)
+        print(f"{name:34s} {med:7.3f} ms  {by / 1e6:9.1f} MB  {by / med / 1e6:7.1f} GB/s ({by / med / 1e6 / peak * 100:4.1f}% of measured HBM)",
+              flush=True)
+
+    img = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8, device=DEV)
+    lda = (3 * P * P + 63) // 64 * 64
+    line(f"patchify B={B} S={S}", B * (3 * S * S + N * lda * 2), lambda: ops.patchify(img, S, P))
+    x = torch.randn(B * N, D, device=DEV).to(torch.bfloat16)
+    g = torch.ones(D, device=DEV)
+    line(f"layernorm M={B * N} D={D}", x.numel() * 4, lambda: ops.layernorm_bf16(x, g, g))
+    line(f"rowstats M={B * N} D={D}", x.numel() * 2, lambda: ops.rowstats_bf16(x))
+    kv = torch.randn(B * N, 2 * D, device=DEV).to(torch.bfloat16)
+    q = torch.randn(D, device=DEV)
+    line(f"map_attention B={B} N={N}", kv.numel() * 2, lambda: ops.map_attention_bf16(kv, q, B, N, H, D // H))
+    scratch = torch.empty(ops._lib.load().dfd_gray256_scratch_bytes(B, S, S), dtype=torch.uint8, device=DEV)
+    out = torch.empty(B, 256, 256, device=DEV)
+    for clahe in (False, True):
+        # RGB in, gray256 out, plus the u8 intermediates written and read once each (luma [, CLAHE], row pass)
+        inter = S * S * (2 if clahe else 1) + 256 * S
+        line(f"gray256 B={B} S={S} clahe={clahe}", B * (3 * S * S + 2 * inter + 256 * 256 * 4),
+             lambda: ops.gray256_from_rgb(img, clahe, scratch, out))
+    luts = scoring.build_freq_luts(torch.device(DEV))
+    fscr = torch.empty(ops._lib.load().dfd_freq_scratch_bytes(B), dtype=torch.uint8, device=DEV)
+    line(f"freq_features B={B}", B * (256 * 256 * 4 + 2 * 256 * 129 * 8 + 96), lambda: ops.freq_features(out, luts, scratch=fscr))
+
+
 def full(name, B, iters=3, fuse_ln=False):
     from oracle import siglip_ref as R
 
@@ -111,6 +145,9 @@ if __name__ == "__main__":
     if "attn" in what:
         attention(64, so)
         attention(256, ba)
+    if "mem" in what:
+        memory_bound(512, so)
+        memory_bound(256, ba)
     if "full" in what:
         for f in (False, True):
             full("siglip2-base-patch16-224", 256, fuse_ln=f)

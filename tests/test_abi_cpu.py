@@ -146,9 +146,17 @@ def test_freq_luts_equal_oracle_tables():
     from dfd import scoring
     from oracle import scoring_ref as S
 
-    band, rbin, sector = scoring.build_freq_luts("cpu")
+    band, rbin, sector = scoring.build_freq_tables()
     b, r, s = S.grid_tables()
     assert np.array_equal(band.numpy(), b) and np.array_equal(rbin.numpy(), r) and np.array_equal(sector.numpy(), s)
+    # the packed device table: transposed words, then the bin populations the kernel divides by
+    lut = scoring.build_freq_luts("cpu").numpy()
+    assert lut.shape == (256 * 256 + 48,) and lut.dtype == np.int32
+    w = lut[: 256 * 256].reshape(256, 256).T
+    assert np.array_equal(w & 0xFF, b) and np.array_equal(((w >> 8) & 0xFF).astype(np.uint8).view(np.int8), r)
+    assert np.array_equal(((w >> 16) & 0xFF).astype(np.uint8).view(np.int8), s)
+    assert [int(v) for v in lut[256 * 256: 256 * 256 + 40]] == [int((r == i).sum()) for i in range(40)]
+    assert [int(v) for v in lut[256 * 256 + 40:]] == [int((s == i).sum()) for i in range(8)]
 
 
 def test_coral_loader_formats(tmp_path, shipped):

@@ -187,6 +187,25 @@ def test_patchify_u8(S, P):
     assert float(A[:, K:].abs().max()) == 0.0 if A.shape[1] > K else True
 
 
+@pytest.mark.parametrize("Hin,Win,skip", [(59, 57, 0), (56, 69, 1), (61, 60, 2)])
+def test_patchify_u8_ragged_sides_and_unaligned_base(Hin, Win, skip):
+    """Inputs anywhere on the 4x4 grid of a 60-pixel / patch-14 model (56..69-pixel sides, conv padding 'valid'), with the
+    first image starting at an odd byte offset: the row-block kernel's 16-byte body + ragged ends must see every byte."""
+    from dfd import ops
+
+    S, P, G = 60, 14, 4
+    g = torch.Generator().manual_seed(Hin * 100 + Win)
+    flat = torch.randint(0, 256, (skip + 3 * Hin * Win * 3,), dtype=torch.uint8, generator=g).to(DEV)
+    img = flat[skip:].view(3, Hin, Win, 3)
+    assert img.data_ptr() % 16 == skip
+    A = ops.patchify(img, S, P)
+    x = (img.cpu().permute(0, 3, 1, 2).float() / 255.0 - 0.5) / 0.5
+    ref = x[:, :, : G * P, : G * P].reshape(3, 3, G, P, G, P).permute(0, 2, 4, 1, 3, 5).reshape(3 * G * G, 3 * P * P)
+    torch.cuda.synchronize()
+    assert torch.equal(A[:, : 3 * P * P].cpu(), ref.to(torch.bfloat16))
+    assert float(A[:, 3 * P * P:].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("mode,name", [(1, "nearest"), (2, "bilinear")])
 @pytest.mark.parametrize("Hin,S,P", [(32, 224, 16), (100, 60, 14), (300, 224, 16)])
 def test_patchify_resize(mode, name, Hin, S, P):
@@ -252,7 +271,8 @@ def test_attention_large_logits():
         assert (out.float() - ref).abs().max().item() < 0.06, impl
 
 
-@pytest.mark.parametrize("B,N,H,hd", [(3, 196, 12, 64), (2, 729, 16, 72), (5, 16, 2, 72), (1, 1024, 16, 72)])
+@pytest.mark.parametrize("B,N,H,hd", [(3, 196, 12, 64), (2, 729, 16, 72), (5, 16, 2, 72), (1, 1024, 16, 72), (2, 1, 2, 72),
+                                     (1, 3, 1, 64), (1, 4096, 2, 72)])
 def test_map_attention(B, N, H, hd):
     from dfd import ops
 
