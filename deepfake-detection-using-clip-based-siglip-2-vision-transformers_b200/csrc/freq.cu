@@ -33,7 +33,7 @@ constexpr int kBand = 32;
 constexpr int kThreads = 256;
 constexpr int kAccDoubles = 32;  // per-image spatial accumulators: 8 srm moments (2 stencils x 4) + 8 haar + pad
 constexpr int64_t kSpecBytes = (int64_t)kN * kHalf * 8;
-constexpr int kMaxColParts = 4;          // CTAs that may share one image's column pass
+constexpr int kMaxColParts = 8;          // CTAs that may share one image's column pass
 constexpr int kColPartBytes = 2048;      // one CTA's partial accumulators: ColAcc (1928 B) + 3 band energies (double)
 // per image: half spectrum | spatial accumulators (zeroed per call) | ticket counter (zeroed) + pad | column partials
 constexpr int64_t kZeroBytes = kAccDoubles * 8 + 16;
@@ -467,8 +467,18 @@ int freq_features(const float* gray256, int B, const int32_t* lut, float eps, in
   if (int rc = ensure_dynamic_smem(smem_once, freq_rows_kernel, kRowsSmem)) return rc;
   freq_rows_kernel<<<dim3(kN / kBand, B), kThreads, kRowsSmem, st>>>(gray256, sc);
   DFD_LAUNCH_CHECK();
-  int parts = (4 * kNumSMs + B - 1) / B;  // aim at >= 4 CTAs per SM
-  parts = parts < 1 ? 1 : (parts > kMaxColParts ? kMaxColParts : parts);
+  // An image's column pass is 17 groups of 8 columns, dealt round-robin to `parts` CTAs; about 6 CTAs fit an SM.  Take the
+  // split with the fewest (waves of CTAs) x (groups per CTA): e.g. 512 images -> 3 parts (2 waves x 6 groups, not 2 x 9).
+  int parts = 1;
+  {
+    const int64_t slots = (int64_t)kNumSMs * 6;
+    const int groups = (kHalf + kThreads / 32 - 1) / (kThreads / 32);
+    int64_t best = -1;
+    for (int p = 1; p <= kMaxColParts; ++p) {
+      const int64_t cost = (((int64_t)B * p + slots - 1) / slots) * ((groups + p - 1) / p);
+      if (best < 0 || cost < best) { best = cost; parts = p; }
+    }
+  }
   freq_cols_kernel<<<dim3(parts, B), kThreads, 0, st>>>(sc, lut, eps, zscore, feats);
   DFD_LAUNCH_CHECK();
   g_launches.fetch_add(2, std::memory_order_relaxed);

@@ -22,7 +22,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // classifier head
 // ------------------------------------------------------------------------------------------------
-constexpr int kHeadThreads = 256;
+constexpr int kHeadThreads = 1024;  // 32 warps: the dense chain is a latency chain per output row, so rows in flight are what count
 constexpr int kHeadS = 4;  // samples per CTA (weights are read once per CTA)
 
 // out[s][j] = act(b[j] + sum_k W[j][k] * in[s][k]); one warp per output row j, lanes stride k.
@@ -35,10 +35,21 @@ __device__ void dense_rows(const float* __restrict__ W, const float* __restrict_
     float acc[kHeadS];
 #pragma unroll
     for (int s = 0; s < kHeadS; ++s) acc[s] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      const float wv = __ldg(w + k);
+    if ((K & 127) == 0 && (in_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+      for (int k = lane * 4; k < K; k += 128) {  // 16-byte weight loads (rows are 16-byte aligned: K % 4 == 0)
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
 #pragma unroll
-      for (int s = 0; s < kHeadS; ++s) acc[s] += wv * in[s * in_stride + k];
+        for (int s = 0; s < kHeadS; ++s) {
+          const float4 x = *reinterpret_cast<const float4*>(in + s * in_stride + k);
+          acc[s] += (wv.x * x.x + wv.y * x.y) + (wv.z * x.z + wv.w * x.w);
+        }
+      }
+    } else {
+      for (int k = lane; k < K; k += 32) {
+        const float wv = __ldg(w + k);
+#pragma unroll
+        for (int s = 0; s < kHeadS; ++s) acc[s] += wv * in[s * in_stride + k];
+      }
     }
 #pragma unroll
     for (int s = 0; s < kHeadS; ++s) acc[s] = warp_sum(acc[s]);
@@ -70,7 +81,7 @@ __global__ void __launch_bounds__(kHeadThreads)
 head_fwd_kernel(dfd_head_weights w, const __nv_bfloat16* __restrict__ pooled, int64_t ldp, int B,
                 const float* __restrict__ protos, float* __restrict__ feat_out, float* __restrict__ z_sig,
                 float* __restrict__ p_proto) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int D = w.dim;
   float* f = sm;                 // [S][D] normalised features
   float* a = f + kHeadS * D;     // [S][D] scratch A

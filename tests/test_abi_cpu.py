@@ -63,7 +63,7 @@ def test_version_and_error_text(lib):
     rc = lib.dfd_gemm_bf16(None, 0, None, 0, None, 0, 1, 1, 1, None, None)
     assert rc == -1 and b"null" in lib.dfd_last_error()
     # per image: half spectrum + counters + 4 column-pass partial slots (freq.cu kImgScratch)
-    assert lib.dfd_freq_scratch_bytes(3) == 3 * (256 * 129 * 8 + 272 + 4 * 2048)
+    assert lib.dfd_freq_scratch_bytes(3) == 3 * (256 * 129 * 8 + 272 + 8 * 2048)
     assert lib.dfd_freq_scratch_bytes(0) == 0
     assert lib.dfd_engine_destroy(None) == 0 and lib.dfd_engine_workspace_bytes(None) == 0
 
