@@ -123,7 +123,7 @@ attention_pq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           tma_load_4d(&tmMain, q_full, sQ + i * S::kMainBytes, 0, h, qt * kQ + i * kKV, b);
-          if (kTail) tma_load_4d(&tmTail, q_full, sQ + S::kQMain + i * S::kTailBytes, 64, h, qt * kQ + i * kKV, b);
+          if (kTail) tma_load_4d(&tmTail, q_full, sQ + S::kQMain + i * S::kTailBytes, HD - 16, h, qt * kQ + i * kKV, b);
         }
         for (int j = 0; j < T; ++j) {
           const int st = j % kStagesKV;
@@ -135,8 +135,9 @@ attention_pq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
           tma_load_4d(&tmMain, &kv_full[st], k, 0, H + h, j * kKV, b);
           tma_load_4d(&tmMain, &kv_full[st], v, 0, 2 * H + h, j * kKV, b);
           if (kTail) {
-            tma_load_4d(&tmTail, &kv_full[st], k + S::kMainBytes, 64, H + h, j * kKV, b);
-            tma_load_4d(&tmTail, &kv_full[st], v + S::kMainBytes, 64, 2 * H + h, j * kKV, b);
+            // tail boxes = columns 56..71, in bounds (boxes crossing the tensor edge are served slowly, see attention_tc.cu)
+            tma_load_4d(&tmTail, &kv_full[st], k + S::kMainBytes, HD - 16, H + h, j * kKV, b);
+            tma_load_4d(&tmTail, &kv_full[st], v + S::kMainBytes, HD - 16, 2 * H + h, j * kKV, b);
           }
         }
       }
@@ -236,12 +237,10 @@ attention_pq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
       }
       tmem_st_32x32b_x32(tQ, qw);
       if (kTail) {
-        uint32_t t8[8];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint4 v = lds_u4(q_tail + static_cast<uint32_t>((c ^ ((row >> 2) & 1)) << 4));
-          t8[4 * c] = v.x; t8[4 * c + 1] = v.y; t8[4 * c + 2] = v.z; t8[4 * c + 3] = v.w;
-        }
+        // tail k-step = columns 56..71; 56..63 already went through the main box: Q contributes zeros there
+        uint32_t t8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        const uint4 v = lds_u4(q_tail + static_cast<uint32_t>((1 ^ ((row >> 2) & 1)) << 4));
+        t8[4] = v.x; t8[5] = v.y; t8[6] = v.z; t8[7] = v.w;
         tmem_st_32x32b_x8(tQ + 32, t8);
       }
       tmem_st_wait();
@@ -329,6 +328,10 @@ attention_pq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
         uint32_t o[16];
         tmem_ld_32x32b_x16(tO + static_cast<uint32_t>(16 * c), o);
         tmem_ld_wait();
+        if (kTail && c == kOChunks - 1) {  // tail accumulator = columns 56..71: its upper half is columns 64..71
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = o[8 + i];
+        }
         if (grow < N) {
           uint4 lo, hi;
           lo.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);

@@ -5,8 +5,13 @@
 // while the softmax warps work on S_j.
 //
 //   warp 0      TMA loader: Q once, then K/V tiles of 64 keys through a 4-stage mbarrier ring.  The operand is
-//               addressed through a 4-D tensor map (head-dim, head, token, image) so that (a) rows past the
-//               image's last token and (b) head-dim columns past hd (72 -> 80) are zero-filled by the TMA unit.
+//               addressed through a 4-D tensor map (head-dim, head, token, image) so that rows past the image's
+//               last token are zero-filled by the TMA unit.  hd = 72 is covered by a 64-column box plus a 16-column
+//               "tail" box over columns 56..71 — IN bounds: a tail box over columns 64..79 (zero-filled past 72) is
+//               the obvious choice but boxes that cross the tensor edge are served far more slowly (handshake-only
+//               pipeline 0.257 ms with them, 0.225 ms in bounds, 0.181 ms without any tail box).  The 8 columns the
+//               two boxes share are cancelled on the Q side (the softmax warps zero columns 56..63 of the Q tail once
+//               per CTA) and, for P·V, land in accumulator columns nobody reads.
 //   warp 1      MMA issuer: S = Q·Kᵀ   (M=128, N<=64, K=64 via SWIZZLE_128B tiles + K=16 tail via SWIZZLE_32B tiles)
 //                           O += P·V   (A = P read from TMEM, B = V tile as an MN-major operand; N=64 + N=16 tail)
 //   warps 2..5  softmax: one thread per query row reads its S row from TMEM (no shuffles), keeps the running
@@ -67,7 +72,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
   uint64_t* p_full = s_full + 2;             // [2]
   uint64_t* o_done = p_full + 2;             // phase k completes when P_k·V_k has retired
   uint64_t* o_full = o_done + 1;             // completes once, when the last P·V has retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* q_fixed = o_full + 1;            // the Q tail's shared columns have been zeroed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_fixed + 1);
+  constexpr int kTailCol = HD - 16;          // first column of the tail boxes
 
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,6 +96,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
     }
     mbar_init(o_done, 1);
     mbar_init(o_full, 1);
+    mbar_init(q_fixed, 4);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -104,7 +112,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         tma_load_4d(&tmMain, q_full, sQ + i * S::kMainBytes, 0, h, qt * kQ + i * kKV, b);
-        if (kTail) tma_load_4d(&tmTail, q_full, sQ + S::kQMain + i * S::kTailBytes, 64, h, qt * kQ + i * kKV, b);
+        if (kTail) tma_load_4d(&tmTail, q_full, sQ + S::kQMain + i * S::kTailBytes, kTailCol, h, qt * kQ + i * kKV, b);
       }
       for (int j = 0; j < T; ++j) {
         const int st = j % kStagesKV;
@@ -115,8 +123,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
         tma_load_4d(&tmMain, &kv_full[st], k, 0, H + h, j * kKV, b);
         tma_load_4d(&tmMain, &kv_full[st], v, 0, 2 * H + h, j * kKV, b);
         if (kTail) {
-          tma_load_4d(&tmTail, &kv_full[st], k + S::kMainBytes, 64, H + h, j * kKV, b);
-          tma_load_4d(&tmTail, &kv_full[st], v + S::kMainBytes, 64, 2 * H + h, j * kKV, b);
+          tma_load_4d(&tmTail, &kv_full[st], k + S::kMainBytes, kTailCol, H + h, j * kKV, b);
+          tma_load_4d(&tmTail, &kv_full[st], v + S::kMainBytes, kTailCol, 2 * H + h, j * kKV, b);
         }
       }
     }
@@ -150,7 +158,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16_ss(tS, dQ + static_cast<uint64_t>(2 * k), dK + static_cast<uint64_t>(2 * k), idesc_qk, k != 0);
-        if (kTail) umma_bf16_ss(tS, dQt, dKt0 + st * kStageStep, idesc_qk, 1u);
+        if (kTail) {
+          if (j == 0) {  // the four main k-steps above do not touch the Q tail; this one needs its zeroed columns
+            mbar_wait(q_fixed, 0);
+            tc_fence_after();
+          }
+          umma_bf16_ss(tS, dQt, dKt0 + st * kStageStep, idesc_qk, 1u);
+        }
         umma_commit(&s_full[sb]);
       };
       mbar_wait(q_full, 0);
@@ -205,6 +219,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
     const uint32_t tO = tmem_base + lane_off + kColO;
     constexpr int kOChunks = (HD + 15) / 16;  // 16-column chunks of O
     float m = -INFINITY, l = 0.f;             // m is kept in log2 units (already multiplied by scale_log2)
+    if (kTail) {
+      // Q tail = columns 56..71; 56..63 are already covered by the main box: zero them (SWIZZLE_32B: the 16-byte chunk
+      // index is XORed with bit 2 of the row), then hand the tile to the async proxy
+      mbar_wait(q_full, 0);
+      sts_zero16(smem_u32(sQ + S::kQMain) + static_cast<uint32_t>(row * 32 + (((row >> 2) & 1) << 4)));
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_fixed);
+    }
     for (int j = 0; j < T; ++j) {
       const int valid = min(kKV, N - j * kKV);
       const uint32_t tS = tmem_base + lane_off + kColS + static_cast<uint32_t>((j & 1) * kKV);
@@ -275,6 +298,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
       uint32_t o[16];
       tmem_ld_32x32b_x16(tO + static_cast<uint32_t>(16 * c), o);
       tmem_ld_wait();
+      if (kTail && c == kOChunks - 1) {  // tail accumulator = columns 56..71: its upper half is columns 64..71
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = o[8 + i];
+      }
       if (grow < N) {
         uint4 lo, hi;
         lo.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
