@@ -119,6 +119,7 @@ struct dfd_engine {
   std::vector<cudaEvent_t> prof_ev;
   std::vector<int> prof_fam;
   int prof_n;
+  int prof_cap;  // launches the current profiling session may record
 };
 
 namespace dfd {
@@ -332,6 +333,7 @@ extern "C" DFD_API int dfd_engine_create(const dfd_config* cfg, int device, int 
   e->staging_bytes = 0;
   e->prof_on = false;
   e->prof_n = 0;
+  e->prof_cap = 0;
   carve_weights(e, nullptr, &e->wbytes);
   carve_acts(e, nullptr, &e->abytes);
   cudaError_t err = cudaMalloc(&e->wslab, e->wbytes);
@@ -438,7 +440,7 @@ extern "C" DFD_API int dfd_engine_finalize(dfd_engine* e) {
 // run one launch, bracketed by events when profiling is on
 #define DFD_OP(fam, expr)                                                                   \
   do {                                                                                      \
-    const bool _p = e->prof_on && (size_t)(2 * e->prof_n + 2) <= e->prof_ev.size();          \
+    const bool _p = e->prof_on && e->prof_n < e->prof_cap;                                       \
     if (_p) DFD_CUDA(cudaEventRecord(e->prof_ev[2 * e->prof_n], st));                        \
     DFD_TRY(expr);                                                                          \
     if (_p) {                                                                               \
@@ -458,19 +460,25 @@ extern "C" DFD_API int dfd_engine_set_hidden_tap(dfd_engine* e, void* buf) {
 extern "C" DFD_API int dfd_engine_profile(dfd_engine* e, int enable) {
   DFD_REQUIRE(e, DFD_ERR_BAD_ARG, "profile: null engine");
   DeviceGuard guard(e->device);
-  if (enable && e->prof_ev.empty()) {
-    const int n = 16 + 8 * e->L;
-    e->prof_ev.resize(2 * n);
-    e->prof_fam.assign(n, 0);
-    for (auto& ev : e->prof_ev) DFD_CUDA(cudaEventCreate(&ev));
+  // enable = how many forwards the event buffer must hold: launches keep being recorded across forwards (no host
+  // synchronisation inside a timed loop) until dfd_engine_profile_read sums and clears them
+  if (enable > 0) {
+    const size_t n = (size_t)(16 + 8 * e->L) * (size_t)enable;
+    const size_t have = e->prof_ev.size();
+    if (have < 2 * n) {
+      e->prof_ev.resize(2 * n);
+      for (size_t i = have; i < 2 * n; ++i) DFD_CUDA(cudaEventCreate(&e->prof_ev[i]));
+      e->prof_fam.resize(n, 0);
+    }
   }
-  e->prof_on = enable != 0;
+  e->prof_on = enable > 0;
+  e->prof_cap = enable > 0 ? (16 + 8 * e->L) * enable : 0;
   e->prof_n = 0;
   return DFD_OK;
 }
 
-// Sums the event-timed durations of the LAST profiled forward per kernel family (ms) and launch counts.
-// Synchronises on the last recorded event.
+// Sums the event-timed durations of every launch recorded since the last read (or since profiling was switched on) per
+// kernel family (ms) and the launch counts, then clears the record.  Synchronises on the last recorded event.
 extern "C" DFD_API int dfd_engine_profile_read(dfd_engine* e, float* ms4, int* count4) {
   DFD_REQUIRE(e && ms4 && count4, DFD_ERR_BAD_ARG, "profile_read: null pointer");
   DeviceGuard guard(e->device);
@@ -483,6 +491,7 @@ extern "C" DFD_API int dfd_engine_profile_read(dfd_engine* e, float* ms4, int* c
     ms4[e->prof_fam[i] & 3] += ms;
     count4[e->prof_fam[i] & 3] += 1;
   }
+  e->prof_n = 0;
   return DFD_OK;
 }
 
@@ -497,7 +506,6 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
   const int M = B * N;
   const float eps = e->cfg.ln_eps;
   const float scale = 1.0f / sqrtf((float)hd);
-  e->prof_n = 0;
 
   DFD_OP(3, patchify(pixels, pix_format, B, Hin, Win, e->S, e->P, resize_mode, e->patches, e->Kpad, st));
   const bool fuse = e->cfg.fuse_ln != 0;

@@ -91,7 +91,14 @@ __device__ __noinline__ float2 act_rare(float2 v, int act) {
   return make_float2(1.f / (1.f + __expf(-v.x)), 1.f / (1.f + __expf(-v.y)));  // act == 3: sigmoid
 }
 
-template <int BN, int CG, int RES>
+// EPI selects a compile-time epilogue: 0 = generic (every fused option is a run-time flag), otherwise exactly one of the
+// combinations the backbone launches, with everything else compiled out:
+//   1 LayerNorm fold + bias (qkv)           2 LayerNorm fold + bias + tanh-GELU (fc1)      5 bias        6 bias + tanh-GELU
+//   3 bias + residual add + row statistics (out-projection / fc2 under fuse_ln)            4 bias + residual add
+// The generic epilogue if-converts its run-time options into predicated code: ~880 issued instructions per 64-column chunk
+// per warp for bias + residual (clock64 trace: 3600 of the 4900 cycles of a chunk), which made every GEMM with a short K
+// loop epilogue bound (K = 768 / 1152 out-projections at 45-75 % of the tensor peak).
+template <int BN, int CG, int RES, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                          const __grid_constant__ CUtensorMap tmB,
@@ -277,6 +284,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     // group left every such group waiting on the long scoreboard: 20 % of all samples of the fc1 GEMM.)
     float* tab = col_tab + grp * (2 * kChunkN);
     const int tab_t = (ew & 3) * 32 + lane;           // 0..127 within the group
+    constexpr bool kSpec = EPI != 0;
+    const bool f_ln = kSpec ? (EPI == 1 || EPI == 2) : (epi.ln_colsum != nullptr);
+    const bool f_bias = kSpec ? true : (epi.bias != nullptr);
+    const int f_act = kSpec ? ((EPI == 2 || EPI == 6) ? 1 : 0) : epi.act;
+    const bool f_pos = kSpec ? false : (epi.pos != nullptr);
+    const bool f_mul = kSpec ? false : (epi.residual_op != 0);
+    const bool f_stats = kSpec ? (EPI == 3) : (epi.stats_out != nullptr);
     const float* tab_src = (tab_t < kChunkN) ? epi.ln_colsum : epi.bias;
     const int tab_e = tab_t & (kChunkN - 1);
     auto next_chunk_col = [&](int tile, int c) -> int {  // first column of the group's chunk after (tile, c); -1: none
@@ -304,14 +318,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const bool row_ok = row < M;
 
       float ln_mean = 0.f, ln_rstd = 1.f;
-      if (epi.ln_colsum != nullptr && row_ok) {
+      if (f_ln && row_ok) {
         const float2 st = *reinterpret_cast<const float2*>(epi.ln_rowstats + 2 * (int64_t)row);
         ln_mean = st.x * epi.ln_inv_dim;
         const float var = fmaxf(st.y * epi.ln_inv_dim - ln_mean * ln_mean, 0.f);
         ln_rstd = rsqrtf(var + epi.ln_eps);
       }
       const float* pos_row =
-          epi.pos != nullptr ? epi.pos + (int64_t)(row_ok ? (row % epi.pos_rows) : 0) * N : nullptr;
+          f_pos ? epi.pos + (int64_t)(row_ok ? (row % epi.pos_rows) : 0) * N : nullptr;
       float st_sum = 0.f, st_sq = 0.f;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -378,14 +392,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           for (int j = 0; j < 4; ++j)
             v[j] = make_float2(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
           if (cc < N) {
-            if (epi.ln_colsum != nullptr) {
+            if (f_ln) {
               const float4 s0 = lds_f4(tab_addr + static_cast<uint32_t>(g * 32));
               const float4 s1 = lds_f4(tab_addr + static_cast<uint32_t>(g * 32 + 16));
               const float2 cs[4] = {{s0.x, s0.y}, {s0.z, s0.w}, {s1.x, s1.y}, {s1.z, s1.w}};
 #pragma unroll
               for (int j = 0; j < 4; ++j) v[j] = fmul2(rstd2, ffma2(nmean2, cs[j], v[j]));
             }
-            if (epi.bias != nullptr) {
+            if (f_bias) {
               const float4 b0 = lds_f4(tab_addr + static_cast<uint32_t>(kChunkN * 4 + g * 32));
               const float4 b1 = lds_f4(tab_addr + static_cast<uint32_t>(kChunkN * 4 + g * 32 + 16));
               v[0] = fadd2(v[0], make_float2(b0.x, b0.y));
@@ -393,15 +407,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
               v[2] = fadd2(v[2], make_float2(b1.x, b1.y));
               v[3] = fadd2(v[3], make_float2(b1.z, b1.w));
             }
-            if (epi.act == 1) {
+            if (f_act == 1) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) v[j] = gelu_tanh_fast2(v[j]);
-            } else if (epi.act >= 2) {  // erf GELU / sigmoid (SegFormer decoder of SigLIP2_MTL): out of line, so that the
+            } else if (f_act >= 2) {  // erf GELU / sigmoid (SegFormer decoder of SigLIP2_MTL): out of line, so that the
               // backbone's epilogue keeps its registers and schedule (inlined erff cost the base-224 engine 10 %)
 #pragma unroll
-              for (int j = 0; j < 4; ++j) v[j] = act_rare(v[j], epi.act);
+              for (int j = 0; j < 4; ++j) v[j] = act_rare(v[j], f_act);
             }
-            if (pos_row != nullptr) {
+            if (f_pos) {
               const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos_row + cc));
               const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos_row + cc + 4));
               v[0] = fadd2(v[0], make_float2(p0.x, p0.y));
@@ -410,7 +424,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
               v[3] = fadd2(v[3], make_float2(p1.z, p1.w));
             }
             if (RES) {
-              if (epi.residual_op == 0) {
+              if (!f_mul) {
                 v[0] = fadd2(v[0], unpack_bf16x2(res[g].x));
                 v[1] = fadd2(v[1], unpack_bf16x2(res[g].y));
                 v[2] = fadd2(v[2], unpack_bf16x2(res[g].z));
@@ -427,7 +441,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           o[g].y = pack_bf16x2(v[1].x, v[1].y);
           o[g].z = pack_bf16x2(v[2].x, v[2].y);
           o[g].w = pack_bf16x2(v[3].x, v[3].y);
-          if (epi.stats_out != nullptr && cc < N) {
+          if (f_stats && cc < N) {
             const float2 q0 = unpack_bf16x2(o[g].x), q1 = unpack_bf16x2(o[g].y),
                          q2 = unpack_bf16x2(o[g].z), q3 = unpack_bf16x2(o[g].w);
             const float2 sm = fadd2(fadd2(q0, q1), fadd2(q2, q3));
@@ -454,7 +468,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           tma_store_commit();
         }
       }
-      if (epi.stats_out != nullptr && row_ok) {
+      if (f_stats && row_ok) {
         atomicAdd(epi.stats_out + 2 * (int64_t)row, st_sum);
         atomicAdd(epi.stats_out + 2 * (int64_t)row + 1, st_sq);
       }
@@ -518,12 +532,12 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t 
   return DFD_OK;
 }
 
-template <int BN, int CG, int RES>
+template <int BN, int CG, int RES, int EPI = 0>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                        const CUtensorMap& tmR, int M, int N, int K, const EpiArgs& ea, cudaStream_t st) {
   using S = GemmSmem<BN, CG, RES>;
   static SmemOptIn smem_once;
-  if (int rc = ensure_dynamic_smem(smem_once, gemm_bf16_tcgen05_kernel<BN, CG, RES>, S::kTotal)) return rc;
+  if (int rc = ensure_dynamic_smem(smem_once, gemm_bf16_tcgen05_kernel<BN, CG, RES, EPI>, S::kTotal)) return rc;
   const int num_tiles = ((M + BM * CG - 1) / (BM * CG)) * ((N + BN - 1) / BN);
   const int max_units = kNumSMs / CG;
   const int units = num_tiles < max_units ? num_tiles : max_units;
@@ -539,7 +553,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DFD_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CG, RES>, tmA, tmB, tmC, tmR, M, N, K, ea));
+  DFD_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CG, RES, EPI>, tmA, tmB, tmC, tmR, M, N, K, ea));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return DFD_OK;
 }
@@ -620,6 +634,19 @@ int gemm_bf16_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, v
   if (has_res) {
     rc = make_tmap_bf16_2d(&tmR, ea.residual, M, N, ea.ldr, BM);
     if (rc != DFD_OK) return rc;
+  }
+  // the backbone's own epilogues on its one large-M tile shape get compile-time specialised kernels (see EPI above)
+  if (bn == 256 && cg == 2 && ea.bias != nullptr && ea.pos == nullptr) {
+    const bool ln = ea.ln_colsum != nullptr, stats = ea.stats_out != nullptr;
+    if (!has_res && !stats) {
+      if (ln && ea.act == 0) return launch_gemm<256, 2, 0, 1>(tmA, tmB, tmC, tmR, M, N, K, ea, st);
+      if (ln && ea.act == 1) return launch_gemm<256, 2, 0, 2>(tmA, tmB, tmC, tmR, M, N, K, ea, st);
+      if (!ln && ea.act == 0) return launch_gemm<256, 2, 0, 5>(tmA, tmB, tmC, tmR, M, N, K, ea, st);
+      if (!ln && ea.act == 1) return launch_gemm<256, 2, 0, 6>(tmA, tmB, tmC, tmR, M, N, K, ea, st);
+    } else if (has_res && !ln && ea.act == 0 && ea.residual_op == 0) {
+      if (stats) return launch_gemm<256, 2, 1, 3>(tmA, tmB, tmC, tmR, M, N, K, ea, st);
+      return launch_gemm<256, 2, 1, 4>(tmA, tmB, tmC, tmR, M, N, K, ea, st);
+    }
   }
 #define DFD_GEMM_CASE(BN_, CG_)                                                                   \
   if (bn == BN_ && cg == CG_)                                                                     \

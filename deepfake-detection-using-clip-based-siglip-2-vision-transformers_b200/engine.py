@@ -241,12 +241,14 @@ class SiglipEngine:
 
     __call__ = forward
 
-    def profile(self, enable: bool = True) -> None:
-        """Bracket every launch of the following forwards with CUDA events (bench.py roofline)."""
-        check(self._lib.dfd_engine_profile(self._h, int(enable)))
+    def profile(self, forwards: int = 1) -> None:
+        """Bracket every launch of the following forwards with CUDA events (bench.py roofline).  `forwards` = how many
+        forwards the event buffer holds before profile_read() must be called; 0 / False switches profiling off."""
+        check(self._lib.dfd_engine_profile(self._h, int(forwards)))
 
     def profile_read(self) -> dict:
-        """Per kernel family of the LAST forward: {'gemm': (ms, launches), 'attention': ..., 'layernorm': ..., 'other': ...}."""
+        """Per kernel family, summed over every forward since the last read: {'gemm': (ms, launches), 'attention': ...,
+        'layernorm': ..., 'other': ...}.  Waits for the last recorded launch."""
         ms, cnt = (C.c_float * 4)(), (C.c_int * 4)()
         check(self._lib.dfd_engine_profile_read(self._h, ms, cnt))
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("gemm", "attention", "layernorm", "other"))}

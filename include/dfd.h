@@ -295,10 +295,11 @@ DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int pix_format
  * batch of that forward).  NULL switches the tap off. */
 DFD_API int dfd_engine_set_hidden_tap(dfd_engine* e, void* buf);
 DFD_API int64_t dfd_engine_workspace_bytes(const dfd_engine* e);
-/* Measurement aid (bench.py roofline): when enabled, dfd_engine_forward brackets every launch with CUDA events
- * on the caller's stream.  dfd_engine_profile_read sums the last forward's durations per kernel family
- * (ms4/count4 index: 0 GEMM, 1 attention, 2 LayerNorm, 3 other) and synchronises on the last event. */
-DFD_API int dfd_engine_profile(dfd_engine* e, int enable);
+/* Measurement aid (bench.py roofline): dfd_engine_profile(e, n) with n > 0 makes dfd_engine_forward bracket every launch
+ * with CUDA events on the caller's stream, with room for n forwards (launches past that are not recorded); n = 0 switches
+ * it off.  dfd_engine_profile_read waits for the last recorded event, sums the durations recorded since the previous read
+ * per kernel family (ms4/count4 index: 0 GEMM, 1 attention, 2 LayerNorm, 3 other) and clears the record. */
+DFD_API int dfd_engine_profile(dfd_engine* e, int forwards);
 DFD_API int dfd_engine_profile_read(dfd_engine* e, float* ms4, int* count4);
 
 #ifdef __cplusplus

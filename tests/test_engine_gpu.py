@@ -208,3 +208,29 @@ def test_hf_bf16_autocast_on_gpu(golden_backbone):
     torch.cuda.synchronize()
     rep = R.cosine_report(pooled.float().cpu(), hf)
     assert rep["cos_min"] >= 0.999 and rep["cos_centered_min"] >= 0.995, rep
+
+
+def test_profile_accumulates_over_forwards_and_clears_on_read():
+    """bench.py's roofline: per-launch CUDA events are kept across the forwards of the timed region and read once."""
+    from oracle import siglip_ref as R
+
+    eng, _ = _engine("tiny-hd64", 4)
+    img = R.synthetic_images(3, R.CONFIGS["tiny-hd64"].image_size, 0).to(DEV)
+    eng.profile(1)
+    eng(img)
+    one = eng.profile_read()
+    assert one["gemm"][1] > 0 and one["attention"][1] > 0 and one["gemm"][0] > 0.0
+    assert sum(v[1] for v in eng.profile_read().values()) == 0, "a read clears the record"
+    eng.profile(3)
+    for _ in range(3):
+        eng(img)
+    three = eng.profile_read()
+    assert {k: v[1] for k, v in three.items()} == {k: 3 * v[1] for k, v in one.items()}
+    eng.profile(1)  # room for one forward (16 + 8 L launches): later launches are dropped, never written out of bounds
+    for _ in range(4):
+        eng(img)
+    assert sum(v[1] for v in eng.profile_read().values()) <= 16 + 8 * R.CONFIGS["tiny-hd64"].num_hidden_layers
+    eng.profile(0)
+    eng(img)
+    assert sum(v[1] for v in eng.profile_read().values()) == 0
+    eng.close()
