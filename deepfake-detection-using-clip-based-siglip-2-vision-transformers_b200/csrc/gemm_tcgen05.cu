@@ -129,8 +129,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + BK - 1) / BK;
+  // Persistent schedule: in round rr the units (CTAs / CTA pairs) take the tiles [rr U, (rr + 1) U) in N-fastest order, so the
+  // units working at the same time share A row blocks through L2.  Within a round the assignment is ROTATED by rr * rot: with a fixed
+  // assignment unit u would see n-tiles (u + rr U) mod num_n only — e.g. 74 units and 14 n-tiles: odd units alone get the
+  // half-width tail tile, run ahead of their row-block peers and turn the shared A reads into DRAM re-reads.
   const int first_tile = blockIdx.x / CG;
   const int tile_step = gridDim.x / CG;
+  // rotation per round: the smallest shift for which a unit's n-tile index advances by a step coprime to num_n, i.e. for which
+  // every unit cycles through ALL n-tiles (74 units: 14 n-tiles -> 1, 5 n-tiles -> 0; a shift of 1 would pin each unit to one
+  // n-tile there)
+  int rot = 0;
+  {
+    auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+    while (rot < num_n && gcd((tile_step + rot) % num_n, num_n) != 1) ++rot;
+    if (rot >= num_n) rot = 0;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -171,7 +184,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      for (int rr = 0; rr * tile_step < num_tiles; ++rr) {
+        const int tile = rr * tile_step + (first_tile + rr * rot) % tile_step;  // rotated within the round, see first_tile
+        if (tile >= num_tiles) break;  // only in the last, partial round
         // N fastest: CTAs working at the same time share A row blocks through L2; the weights (<= 10 MB)
         // stay L2 resident for the whole GEMM
         const int m0 = (tile / num_n) * (BM * CG) + (int)cta_rank * BM;
@@ -205,7 +220,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      for (int rr = 0; rr * tile_step < num_tiles; ++rr) {
+        const int tile = rr * tile_step + (first_tile + rr * rot) % tile_step;  // rotated within the round, see first_tile
+        if (tile >= num_tiles) break;  // only in the last, partial round
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -248,7 +265,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       // the parity waits stay one phase apart whatever the number of chunks per tile (a shared ring broke for odd
       // counts)
       uint32_t uses[2] = {0, 0};
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      for (int rr = 0; rr * tile_step < num_tiles; ++rr) {
+        const int tile = rr * tile_step + (first_tile + rr * rot) % tile_step;  // rotated within the round, see first_tile
+        if (tile >= num_tiles) break;  // only in the last, partial round
         const int m0 = (tile / num_n) * (BM * CG) + (int)cta_rank * BM;
         const int n0 = (tile % num_n) * BN;
         const int nvalid = min(BN / kChunkN, (N - n0 + kChunkN - 1) / kChunkN);
@@ -293,13 +312,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const bool f_stats = kSpec ? (EPI == 3) : (epi.stats_out != nullptr);
     const float* tab_src = (tab_t < kChunkN) ? epi.ln_colsum : epi.bias;
     const int tab_e = tab_t & (kChunkN - 1);
-    auto next_chunk_col = [&](int tile, int c) -> int {  // first column of the group's chunk after (tile, c); -1: none
+    auto next_chunk_col = [&](int rr, int c) -> int {  // first column of the group's chunk after (round rr, c); -1: none
       c += 2;
-      while (tile < num_tiles) {
+      for (; rr * tile_step < num_tiles; ++rr, c = grp) {
+        const int tile = rr * tile_step + (first_tile + rr * rot) % tile_step;
+        if (tile >= num_tiles) break;
         const int n0t = (tile % num_n) * BN;
         if (c < min(kChunks, (N - n0t + kChunkN - 1) / kChunkN)) return n0t + c * kChunkN;
-        tile += tile_step;
-        c = grp;
       }
       return -1;
     };
@@ -307,11 +326,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const int col = col0 + tab_e;
       return (tab_src != nullptr && col0 >= 0 && col < N) ? __ldg(tab_src + col) : 0.f;
     };
-    tab[tab_t] = fetch_col(next_chunk_col(first_tile, grp - 2));
+    tab[tab_t] = fetch_col(next_chunk_col(0, grp - 2));
     named_bar_sync(1 + grp, 128);
     const uint32_t tab_addr = smem_u32(tab);
 
-    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+    for (int rr = 0; rr * tile_step < num_tiles; ++rr) {
+        const int tile = rr * tile_step + (first_tile + rr * rot) % tile_step;  // rotated within the round, see first_tile
+        if (tile >= num_tiles) break;  // only in the last, partial round
       const int m0 = (tile / num_n) * (BM * CG) + (int)cta_rank * BM;
       const int n0 = (tile % num_n) * BN;
       const int row = m0 + row_in_tile;
@@ -350,7 +371,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * kChunkN + 32),
                            *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
         tmem_ld_wait();
-        const float tab_next = fetch_col(next_chunk_col(tile, c));  // consumed after the first barrier below
+        const float tab_next = fetch_col(next_chunk_col(rr, c));  // consumed after the first barrier below
         if (c + 2 >= nvalid) {
           // last chunk of this group for this tile: the accumulator stage can go back to the MMA warp
           tc_fence_before();

@@ -21,3 +21,9 @@ echo "ncu gemm full rc=$?"
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:attention_tc -s 84 -c 1 -o $O/prof_bench_attn -f $BENCH > $O/ncu_a.log 2>&1
 echo "ncu attn full rc=$?"
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > $O/smi.txt
+# configs[1] (base-224, batch 256) bench line and the memory-bound kernels: achieved GB/s (CUDA events), then one ncu capture each
+timeout 300 python bench.py --workload base-224 --steps 20 --warmup 5 --no-cpu-baseline > $O/bench_base224.json 2> $O/bench_base224.err; echo "bench base rc=$?"
+timeout 300 python scripts/kbench.py mem > $O/kbench_mem.txt 2>&1; echo "kbench mem rc=$?"
+timeout 300 python scripts/kbench.py gemm attn > $O/kbench_gemm_attn.txt 2>&1; echo "kbench gemm/attn rc=$?"
+timeout 400 ncu --set full --clock-control none -k regex:"freq_cols|freq_rows|map_attention|patchify_u8|head_fwd" -c 6 -o $O/prof_mem -f python scripts/prof_mem.py > $O/ncu_mem.log 2>&1
+echo "ncu mem rc=$?"

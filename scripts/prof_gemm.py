@@ -10,7 +10,7 @@ from dfd import ops  # noqa: E402
 
 DEV = "cuda:0"
 which = sys.argv[1] if len(sys.argv) > 1 else "outres"
-M, D, I = 46656, 1152, 4304
+M, D, I = int(os.environ.get("DFD_PROF_M", 46656)), 1152, 4304
 torch.manual_seed(0)
 if which in ("outres", "qkv", "fc1", "fc2"):
     n, k = {"outres": (D, D), "qkv": (3 * D, D), "fc1": (I, D), "fc2": (D, I)}[which]
