@@ -99,6 +99,7 @@ SIGNATURES = {
     "dfd_version": (_I, []),
     "dfd_launch_count": (_L, []),
     "dfd_gemm_bf16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, C.POINTER(GemmEpilogue), _P]),
+    "dfd_gemm_schedule": (_I, [_I, _I, _I, _I, _I]),
     "dfd_gemm_bf16_tile": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, C.POINTER(GemmEpilogue), _I, _P]),
     "dfd_layernorm_bf16": (_I, [_P, _L, _P, _L, _P, _P, _I, _I, _F, _P]),
     "dfd_rowstats_bf16": (_I, [_P, _L, _P, _I, _I, _P]),

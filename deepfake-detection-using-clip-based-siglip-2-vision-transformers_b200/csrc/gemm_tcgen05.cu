@@ -44,6 +44,25 @@ struct EpiArgs {
 // CG = CTAs per MMA (1, or 2 = cta_group::2: a 256 x BN tile shared by an SM pair, each CTA staging its own
 // 128 rows of A and HALF of the B tile, which roughly halves shared-memory traffic per MMA)
 // RES = the epilogue adds a bf16 residual tile; it is prefetched chunk by chunk with TMA into its own ring.
+// Persistent schedule (shared by the kernel and by the host-side dfd_gemm_schedule, which tests/test_abi_cpu.py uses to check
+// that every tile is taken exactly once).  In round r the U units (CTAs / CTA pairs) take the tiles [r U, (r + 1) U) in N-fastest
+// order, so the units working at the same time share A row blocks through L2.  Within a round the assignment is rotated by
+// r * rot: with a fixed assignment unit u would only ever see the n-tiles (u + r U) mod num_n — 74 units and 14 n-tiles: odd units
+// alone get the half-width tail tile, run ahead of their row-block peers and turn the shared A reads into DRAM re-reads.
+// rot = the smallest shift for which a unit's n-tile index advances by a step coprime to num_n, i.e. for which every unit cycles
+// through ALL n-tiles (74 units: 14 n-tiles -> 1, 5 n-tiles -> 0; a shift of 1 would pin each unit to one n-tile there).
+__host__ __device__ inline int sched_rotation(int units, int num_n) {
+  for (int rot = 0; rot < num_n; ++rot) {
+    int a = (units + rot) % num_n, b = num_n;
+    while (b) { const int t = a % b; a = b; b = t; }
+    if (a == 1) return rot;
+  }
+  return 0;
+}
+__host__ __device__ inline int sched_tile(int round, int unit, int units, int rot) {
+  return round * units + (unit + round * rot) % units;
+}
+
 template <int BN, int CG, int RES>
 struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;
@@ -129,21 +148,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + BK - 1) / BK;
-  // Persistent schedule: in round rr the units (CTAs / CTA pairs) take the tiles [rr U, (rr + 1) U) in N-fastest order, so the
-  // units working at the same time share A row blocks through L2.  Within a round the assignment is ROTATED by rr * rot: with a fixed
-  // assignment unit u would see n-tiles (u + rr U) mod num_n only — e.g. 74 units and 14 n-tiles: odd units alone get the
-  // half-width tail tile, run ahead of their row-block peers and turn the shared A reads into DRAM re-reads.
-  const int first_tile = blockIdx.x / CG;
-  const int tile_step = gridDim.x / CG;
-  // rotation per round: the smallest shift for which a unit's n-tile index advances by a step coprime to num_n, i.e. for which
-  // every unit cycles through ALL n-tiles (74 units: 14 n-tiles -> 1, 5 n-tiles -> 0; a shift of 1 would pin each unit to one
-  // n-tile there)
-  int rot = 0;
-  {
-    auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
-    while (rot < num_n && gcd((tile_step + rot) % num_n, num_n) != 1) ++rot;
-    if (rot >= num_n) rot = 0;
-  }
+  const int first_tile = blockIdx.x / CG;   // this unit's index
+  const int tile_step = gridDim.x / CG;     // units
+  const int rot = sched_rotation(tile_step, num_n);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -185,7 +192,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       int stage = 0;
       uint32_t phase = 0;
       for (int rr = 0; rr * tile_step < num_tiles; ++rr) {
-        const int tile = rr * tile_step + (first_tile + rr * rot) % tile_step;  // rotated within the round, see first_tile
+        const int tile = sched_tile(rr, first_tile, tile_step, rot);  // rotated within the round, see sched_rotation
         if (tile >= num_tiles) break;  // only in the last, partial round
         // N fastest: CTAs working at the same time share A row blocks through L2; the weights (<= 10 MB)
         // stay L2 resident for the whole GEMM
@@ -221,7 +228,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int rr = 0; rr * tile_step < num_tiles; ++rr) {
-        const int tile = rr * tile_step + (first_tile + rr * rot) % tile_step;  // rotated within the round, see first_tile
+        const int tile = sched_tile(rr, first_tile, tile_step, rot);  // rotated within the round, see sched_rotation
         if (tile >= num_tiles) break;  // only in the last, partial round
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
@@ -266,7 +273,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       // counts)
       uint32_t uses[2] = {0, 0};
       for (int rr = 0; rr * tile_step < num_tiles; ++rr) {
-        const int tile = rr * tile_step + (first_tile + rr * rot) % tile_step;  // rotated within the round, see first_tile
+        const int tile = sched_tile(rr, first_tile, tile_step, rot);  // rotated within the round, see sched_rotation
         if (tile >= num_tiles) break;  // only in the last, partial round
         const int m0 = (tile / num_n) * (BM * CG) + (int)cta_rank * BM;
         const int n0 = (tile % num_n) * BN;
@@ -315,7 +322,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     auto next_chunk_col = [&](int rr, int c) -> int {  // first column of the group's chunk after (round rr, c); -1: none
       c += 2;
       for (; rr * tile_step < num_tiles; ++rr, c = grp) {
-        const int tile = rr * tile_step + (first_tile + rr * rot) % tile_step;
+        const int tile = sched_tile(rr, first_tile, tile_step, rot);
         if (tile >= num_tiles) break;
         const int n0t = (tile % num_n) * BN;
         if (c < min(kChunks, (N - n0t + kChunkN - 1) / kChunkN)) return n0t + c * kChunkN;
@@ -331,7 +338,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const uint32_t tab_addr = smem_u32(tab);
 
     for (int rr = 0; rr * tile_step < num_tiles; ++rr) {
-        const int tile = rr * tile_step + (first_tile + rr * rot) % tile_step;  // rotated within the round, see first_tile
+        const int tile = sched_tile(rr, first_tile, tile_step, rot);  // rotated within the round, see sched_rotation
         if (tile >= num_tiles) break;  // only in the last, partial round
       const int m0 = (tile / num_n) * (BM * CG) + (int)cta_rank * BM;
       const int n0 = (tile % num_n) * BN;
@@ -685,6 +692,14 @@ int gemm_bf16_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, v
 }
 
 }  // namespace dfd
+
+// Host-only view of the persistent schedule: the tile that `unit` (of `units`) processes in `round`, or -1 when it has none.
+extern "C" DFD_API int dfd_gemm_schedule(int num_tiles, int num_n, int units, int unit, int round) {
+  if (num_tiles <= 0 || num_n <= 0 || units <= 0 || unit < 0 || unit >= units || round < 0) return -1;
+  if ((long long)round * units >= num_tiles) return -1;
+  const int tile = dfd::sched_tile(round, unit, units, dfd::sched_rotation(units, num_n));
+  return tile < num_tiles ? tile : -1;
+}
 
 extern "C" DFD_API int dfd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C,
                                      int64_t ldc, int M, int N, int K, const dfd_gemm_epilogue* epi,

@@ -87,6 +87,11 @@ DFD_API int dfd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw
                           int64_t ldc, int M, int N, int K, const dfd_gemm_epilogue* epi,
                           void* stream);
 
+/* Host-only view of the GEMM's persistent schedule (no GPU needed): the tile index (m_block * num_n + n_tile, N fastest) that
+ * work unit `unit` of `units` (CTAs or CTA pairs) processes in round `round`, or -1 if it has none.  Each round covers `units`
+ * consecutive tiles, rotated between rounds so that every unit cycles through all n-tiles (gemm_tcgen05.cu: sched_rotation). */
+DFD_API int dfd_gemm_schedule(int num_tiles, int num_n, int units, int unit, int round);
+
 /* y[M,D] (bf16) = LayerNorm(x[M,D] (bf16)) · gamma + beta, fp32 statistics, eps as given.
  * HF:modeling_siglip.py:348,357 (layer_norm1/2), :618 (post_layernorm). */
 DFD_API int dfd_layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,

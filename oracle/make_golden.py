@@ -12,7 +12,6 @@ only numeric outputs are stored.
 from __future__ import annotations
 
 import ast
-import io
 import json
 import math
 import os

@@ -4,7 +4,6 @@ import json
 import math
 import os
 import sys
-import time
 
 import torch
 

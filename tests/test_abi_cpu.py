@@ -140,6 +140,33 @@ def test_state_dict_canonicalisation_hf_and_timm():
     assert abs(engine.ARCHS["google/siglip2-so400m-patch14-384"].flops_per_image() / 1e9 - 670.346) < 1e-3
 
 
+@pytest.mark.parametrize("num_m,num_n,units", [(1458, 14, 74), (1458, 5, 74), (1458, 17, 74), (196, 3, 74), (196, 9, 74),
+                                               (3, 2, 148), (1, 1, 148), (7, 5, 5), (50, 4, 6), (371, 5, 74)])
+def test_gemm_schedule_takes_every_tile_once_and_balances_the_tail(lib, num_m, num_n, units):
+    """The GEMM kernel's persistent schedule, through the same function the kernel uses: every tile exactly once, each
+    round a contiguous block of tiles (so concurrent units share A row blocks), and the tail n-tile spread over ALL units
+    (a fixed assignment pinned it to the units with (u + r U) mod num_n == num_n - 1: odd units only for 74 / 14)."""
+    num_tiles = num_m * num_n
+    units = min(units, num_tiles)
+    rounds = (num_tiles + units - 1) // units
+    seen, tails = [], [0] * units
+    for r in range(rounds + 1):
+        got = [lib.dfd_gemm_schedule(num_tiles, num_n, units, u, r) for u in range(units)]
+        real = sorted(t for t in got if t >= 0)
+        if r < rounds:
+            assert real == list(range(r * units, min((r + 1) * units, num_tiles))), r
+        else:
+            assert real == []
+        for u, t in enumerate(got):
+            if t >= 0 and t % num_n == num_n - 1:
+                tails[u] += 1
+        seen += real
+    assert sorted(seen) == list(range(num_tiles))
+    if rounds >= 4 * num_n and num_n > 1:  # long enough for the rotation to show: no unit is starved of / pinned to tail tiles
+        assert min(tails) >= 1 and max(tails) <= 2 * (sum(tails) / units) + 1, (min(tails), max(tails))
+    assert lib.dfd_gemm_schedule(num_tiles, num_n, units, units, 0) == -1 and lib.dfd_gemm_schedule(0, 1, 1, 0, 0) == -1
+
+
 def test_freq_luts_equal_oracle_tables():
     import numpy as np
 

@@ -4,7 +4,6 @@ golden vectors, on seeded weights of the named architectures.
 Gates (BASELINE.json): pooled embeddings cosine >= 0.999 against the reference path; additionally the
 batch-mean-removed cosine and relative L2 are checked so a wrong-but-correlated result cannot pass.
 """
-import numpy as np
 import pytest
 import torch
 

@@ -1,6 +1,5 @@
 """CPU tests (no GPU): the oracle restatements against the reference-generated golden vectors and the
 reference's shipped artefacts.  These pin the oracle; the -m gpu tests then compare the CUDA path with it."""
-import json
 import os
 
 import numpy as np
