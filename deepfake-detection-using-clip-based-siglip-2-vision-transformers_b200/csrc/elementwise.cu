@@ -288,7 +288,8 @@ int patchify(const void* pixels, int pix_format, int B, int Hin, int Win, int S,
   a.A = reinterpret_cast<__nv_bfloat16*>(A);
   a.lda = lda;
   const int64_t fast_smem = 1024 + ((lda * 2 + 15) & ~15ll) + (int64_t)P * Win * 3 + 16;
-  if (a.fmt == 0 && a.mode == 0 && fast_smem <= 48 * 1024 && (int64_t)P * Win * 3 < 0xffff && (int64_t)B * a.G < (1ll << 31) &&
+  if (a.fmt == 0 && a.mode == 0 && fast_smem <= 48 * 1024 && (int64_t)P * Win * 3 < 0xffff && (int64_t)P * Win * 3 >= 64 &&
+      (int64_t)B * a.G < (1ll << 31) &&
       (reinterpret_cast<uintptr_t>(A) & 15) == 0) {
     patchify_u8_rows_kernel<<<B * a.G, 256, (size_t)fast_smem, st>>>(a);
     DFD_LAUNCH_CHECK();
