@@ -225,3 +225,21 @@ def test_resample_tables_host_equal_oracle(lib):
     # the identity case reproduces the input exactly: one tap of weight 2^22
     xmin, cnt, kk = ops.resample_coeffs(256, 256)
     assert np.array_equal(kk.sum(1), np.full(256, 1 << 22)) and int((kk != 0).sum()) == 256
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the arm the driver times next to ours) on the CPU-runnable config: one JSON line with the
+    keys of the bench contract; the CPU sample is described and nothing pretends to have run on a GPU."""
+    import json
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "base-224",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "images/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["steps"] == 1 and line["gpu_launches"] == 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and "images per step" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "base-224" in line["config"]["workload"]
