@@ -122,10 +122,10 @@ def memory_bound(B, arch):
 
 
 def full(name, B, iters=3, fuse_ln=False):
-    from oracle import siglip_ref as R
+    from dfd import weights
 
     arch = engine.ARCHS[name]
-    eng = engine.SiglipEngine(arch, 0, max_batch=B, fuse_ln=fuse_ln).load_state_dict(R.init_state_dict(R.CONFIGS[name], 0))
+    eng = engine.SiglipEngine(arch, 0, max_batch=B, fuse_ln=fuse_ln).load_state_dict(weights.random_vision_state_dict(arch, 0, DEV))
     img = torch.randint(0, 256, (B, arch.image_size, arch.image_size, 3), dtype=torch.uint8, device=DEV)
     med, best = timeit(lambda: eng(img), iters=iters, warm=2, flush=False)
     tf = arch.flops_per_image() * B / med / 1e9

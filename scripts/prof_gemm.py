@@ -28,12 +28,11 @@ elif which == "attn":
     for _ in range(4):
         ops.attention_bf16(qkv, B, N, H, hd, impl=impl)
 elif which == "engine":
-    from dfd import engine
-    from oracle import siglip_ref as R
+    from dfd import engine, weights
 
     name = "siglip2-so400m-patch14-384"
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
-    eng = engine.SiglipEngine(engine.ARCHS[name], 0, max_batch=B).load_state_dict(R.init_state_dict(R.CONFIGS[name], 0))
+    eng = engine.SiglipEngine(engine.ARCHS[name], 0, max_batch=B).load_state_dict(weights.random_vision_state_dict(engine.ARCHS[name], 0, DEV))
     img = torch.randint(0, 256, (B, 384, 384, 3), dtype=torch.uint8, device=DEV)
     for _ in range(2):
         eng(img)
