@@ -80,8 +80,18 @@ static bool make_map(CUtensorMap* out, void* base, int hd, int heads3, int N, in
                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static int run(int hd, int tail_col_inb);
+
 int main() {
-  const int B = 64, N = 729, H = 16, hd = 72, QT = (N + 127) / 128;
+  // hd 72 as shipped (144-byte heads, tails over 56..71 in bounds / 64..79 out of bounds), then the same tokens with every head
+  // padded to 80 columns (160-byte heads at 32-byte alignment, tail box over 64..79 in bounds)
+  if (int rc = run(72, 56)) return rc;
+  return run(80, 64);
+}
+
+static int run(int hd, int tail_col_inb) {
+  const int B = 64, N = 729, H = 16, QT = (N + 127) / 128;
+  printf("---- head dim stride %d ----\n", hd);
   const int64_t ld = 3 * H * hd;
   void* qkv = nullptr;
   if (cudaMalloc(&qkv, (size_t)B * N * ld * 2) != cudaSuccess) { printf("no device\n"); return 1; }
@@ -95,9 +105,9 @@ int main() {
       {"K+V main boxes only", 2, 0, 0, 0},
       {"K main only", 1, 0, 0, 0},
       {"main + 32B tails over 64..79 (out of bounds)", 2, 2, 64, 0},
-      {"main + 32B tails over 56..71 (in bounds)", 2, 2, 56, 0},
+      {"main + 32B tails, in bounds", 2, 2, tail_col_inb, 0},
       {"32B tails only, out of bounds", 0, 2, 64, 0},
-      {"32B tails only, in bounds", 0, 2, 56, 0},
+      {"32B tails only, in bounds", 0, 2, tail_col_inb, 0},
       {"main + 128B tails over 16..79 (out of bounds)", 2, 2, 16, 1},
       {"main + 128B tails over 8..71 (in bounds)", 2, 2, 8, 1},
   };
@@ -126,5 +136,7 @@ int main() {
              bytes / ms / 1e9, boxes / ms / 1e3 / 148, ms * 1e6 / (tiles / 148));
     }
   }
+  cudaFree(qkv);
+  cudaFree(cyc);
   return 0;
 }
