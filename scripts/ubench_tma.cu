@@ -13,7 +13,7 @@
 
 using namespace dfd;
 
-constexpr int kKV = 64, kStages = 4, kStageBytes = 2 * (kKV * 128 + kKV * 128);  // room for the widest variant
+constexpr int kMaxStages = 8;
 
 struct Mode {
   const char* name;
@@ -24,11 +24,12 @@ struct Mode {
 };
 
 __global__ void __launch_bounds__(64) tma_bench(const __grid_constant__ CUtensorMap tmMain, const __grid_constant__ CUtensorMap tmTail,
-                                                Mode m, int N, int H, int n_items, int QT, long long* cycles) {
+                                                Mode m, int N, int H, int n_items, int QT, int kKV, int kStages, int kStageBytes,
+                                                long long* cycles) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  __shared__ uint64_t full[kStages];
+  __shared__ uint64_t full[kMaxStages];
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(64) tma_bench(const __grid_constant__ CUtensor
     const int T = (N + kKV - 1) / kKV;
     const uint32_t tail_bytes = m.tail_wide ? kKV * 128 : kKV * 32;
     const uint32_t tx = m.main_boxes * kKV * 128 + m.tail_boxes * tail_bytes;
-    uint32_t uses[kStages] = {0, 0, 0, 0};
+    uint32_t uses[kMaxStages] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t0 = clock64();
     int step = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(64) tma_bench(const __grid_constant__ CUtensor
         if (m.main_boxes >= 2) tma_load_4d(&tmMain, &full[st], base + kKV * 128, 0, 2 * H + h, j * kKV, b);
         const CUtensorMap* tt = m.tail_wide ? &tmMain : &tmTail;
         if (m.tail_boxes >= 1) tma_load_4d(tt, &full[st], base + 2 * kKV * 128, m.tail_col, H + h, j * kKV, b);
-        if (m.tail_boxes >= 2) tma_load_4d(tt, &full[st], base + 3 * kKV * 128, m.tail_col, 2 * H + h, j * kKV, b);
+        if (m.tail_boxes >= 2) tma_load_4d(tt, &full[st], base + 2 * kKV * 128 + tail_bytes, m.tail_col, 2 * H + h, j * kKV, b);
       }
     }
     for (int s = 0; s < kStages; ++s)
@@ -66,7 +67,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static bool make_map(CUtensorMap* out, void* base, int hd, int heads3, int N, int B, int64_t ld, int box_cols, CUtensorMapSwizzle sw) {
+static bool make_map(CUtensorMap* out, void* base, int hd, int heads3, int N, int B, int64_t ld, int box_cols, CUtensorMapSwizzle sw, int kKV) {
   void* p = nullptr;
   cudaDriverEntryPointQueryResult q;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
@@ -80,18 +81,23 @@ static bool make_map(CUtensorMap* out, void* base, int hd, int heads3, int N, in
                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int run(int hd, int tail_col_inb);
+static int run(int hd, int tail_col_inb, int kKV, int kStages);
 
 int main() {
   // hd 72 as shipped (144-byte heads, tails over 56..71 in bounds / 64..79 out of bounds), then the same tokens with every head
   // padded to 80 columns (160-byte heads at 32-byte alignment, tail box over 64..79 in bounds)
-  if (int rc = run(72, 56)) return rc;
-  return run(80, 64);
+  for (int hd : {72, 80}) {
+    const int col = hd == 72 ? 56 : 64;
+    if (int rc = run(hd, col, 64, 4)) return rc;
+    if (int rc = run(hd, col, 64, 8)) return rc;    // deeper ring: latency or throughput?
+    if (int rc = run(hd, col, 128, 4)) return rc;   // 128-key tiles: half as many, twice as tall boxes
+  }
+  return 0;
 }
 
-static int run(int hd, int tail_col_inb) {
+static int run(int hd, int tail_col_inb, int kKV, int kStages) {
   const int B = 64, N = 729, H = 16, QT = (N + 127) / 128;
-  printf("---- head dim stride %d ----\n", hd);
+  printf("---- head dim stride %d, %d-key tiles, %d stages ----\n", hd, kKV, kStages);
   const int64_t ld = 3 * H * hd;
   void* qkv = nullptr;
   if (cudaMalloc(&qkv, (size_t)B * N * ld * 2) != cudaSuccess) { printf("no device\n"); return 1; }
@@ -99,8 +105,8 @@ static int run(int hd, int tail_col_inb) {
   long long* cyc = nullptr;
   cudaMalloc(&cyc, 4096 * sizeof(long long));
   CUtensorMap tmMain, tmTail;
-  if (!make_map(&tmMain, qkv, hd, 3 * H, N, B, ld, 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
-      !make_map(&tmTail, qkv, hd, 3 * H, N, B, ld, 16, CU_TENSOR_MAP_SWIZZLE_32B)) { printf("tensor map failed\n"); return 1; }
+  if (!make_map(&tmMain, qkv, hd, 3 * H, N, B, ld, 64, CU_TENSOR_MAP_SWIZZLE_128B, kKV) ||
+      !make_map(&tmTail, qkv, hd, 3 * H, N, B, ld, 16, CU_TENSOR_MAP_SWIZZLE_32B, kKV)) { printf("tensor map failed\n"); return 1; }
   const Mode modes[] = {
       {"K+V main boxes only", 2, 0, 0, 0},
       {"K main only", 1, 0, 0, 0},
@@ -111,19 +117,25 @@ static int run(int hd, int tail_col_inb) {
       {"main + 128B tails over 16..79 (out of bounds)", 2, 2, 16, 1},
       {"main + 128B tails over 8..71 (in bounds)", 2, 2, 8, 1},
   };
-  const int n_items = QT * H * B, smem = kStages * kStageBytes + 1024;
-  cudaFuncSetAttribute(tma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int n_items = QT * H * B;
+  cudaFuncSetAttribute(tma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   int dev_clock_khz = 0;
   cudaDeviceGetAttribute(&dev_clock_khz, cudaDevAttrClockRate, 0);
   for (int per_sm = 1; per_sm <= 2; ++per_sm) {
     for (const Mode& m : modes) {
+      const int kStageBytes = (2 * kKV * 128 + 2 * (m.tail_wide ? kKV * 128 : kKV * 32) + 1023) & ~1023;
+      const int smem = kStages * kStageBytes + 1024;
+      if (smem * per_sm > 220 * 1024 || smem > 200 * 1024) continue;
+      if ((kKV != 64 || kStages != 4) &&
+          !(m.main_boxes == 2 && !m.tail_wide && (m.tail_boxes == 0 || m.tail_col == tail_col_inb)))
+        continue;  // the ring-depth / tile-height variants only run the two mixes that matter
       const int grid = 148 * per_sm;
       cudaEvent_t e0, e1;
       cudaEventCreate(&e0);
       cudaEventCreate(&e1);
-      tma_bench<<<grid, 64, smem>>>(tmMain, tmTail, m, N, H, n_items, QT, cyc);  // warm-up
+      tma_bench<<<grid, 64, smem>>>(tmMain, tmTail, m, N, H, n_items, QT, kKV, kStages, kStageBytes, cyc);  // warm-up
       cudaEventRecord(e0);
-      tma_bench<<<grid, 64, smem>>>(tmMain, tmTail, m, N, H, n_items, QT, cyc);
+      tma_bench<<<grid, 64, smem>>>(tmMain, tmTail, m, N, H, n_items, QT, kKV, kStages, kStageBytes, cyc);
       cudaEventRecord(e1);
       if (cudaEventSynchronize(e1) != cudaSuccess) { printf("%s: launch failed: %s\n", m.name, cudaGetErrorString(cudaGetLastError())); return 1; }
       float ms = 0.f;
