@@ -243,3 +243,28 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and "images per step" in cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "base-224" in line["config"]["workload"]
+
+
+def test_pipeline_host_helpers_without_a_device():
+    """Host-side pieces of DetectionPipeline that need no GPU: the packed score record layout that is all-gathered across
+    ranks, and the six multicrop views / weights of detect_core (deepfake-detector-v2/app.py:1418-1430)."""
+    from PIL import Image
+
+    from dfd import pipeline
+    from dfd.engine import ARCHS
+
+    B = 5
+    out = {k: torch.arange(B, dtype=torch.float32) + 10 * i for i, k in enumerate(pipeline.PACKED_FIELDS[:8])}
+    out["risk_idx"] = torch.arange(B, dtype=torch.int32) % 5
+    out["risk_probs"] = torch.rand(B, 5)
+    rec = pipeline.DetectionPipeline.pack(out)
+    assert rec.shape == (B, 14) and rec.dtype == torch.float32
+    for i, k in enumerate(pipeline.PACKED_FIELDS[:8]):
+        assert torch.equal(rec[:, i], out[k]), k
+    assert torch.equal(rec[:, 8], out["risk_idx"].float()) and torch.equal(rec[:, 9:], out["risk_probs"])
+
+    p = object.__new__(pipeline.DetectionPipeline)  # no engine: make_multicrops only needs the architecture
+    p.arch = ARCHS["siglip2-base-patch16-224"]
+    views = p.make_multicrops(Image.new("RGB", (301, 200), (10, 20, 30)))
+    assert [v.size for v in views] == [(301, 200), (224, 224), (150, 100), (151, 100), (150, 100), (151, 100)]
+    assert len(pipeline.DetectionPipeline.MULTICROP_WEIGHTS) == 6 and abs(sum(pipeline.DetectionPipeline.MULTICROP_WEIGHTS) - 1.0) < 1e-12
