@@ -34,6 +34,7 @@ class GemmEpilogue(C.Structure):
         ("ln_eps", C.c_float),
         ("stats_out", C.c_void_p),
         ("residual_op", C.c_int),
+        ("ln_parts", C.c_int),
     ]
 
 
@@ -100,6 +101,8 @@ SIGNATURES = {
     "dfd_launch_count": (_L, []),
     "dfd_gemm_bf16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, C.POINTER(GemmEpilogue), _P]),
     "dfd_gemm_schedule": (_I, [_I, _I, _I, _I, _I]),
+    "dfd_gemm_last_variant": (_I, []),
+    "dfd_gemm_variant_launches": (_L, [_I]),
     "dfd_gemm_bf16_tile": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, C.POINTER(GemmEpilogue), _I, _P]),
     "dfd_layernorm_bf16": (_I, [_P, _L, _P, _L, _P, _P, _I, _I, _F, _P]),
     "dfd_rowstats_bf16": (_I, [_P, _L, _P, _I, _I, _P]),

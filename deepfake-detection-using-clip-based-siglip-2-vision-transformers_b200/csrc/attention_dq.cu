@@ -1,0 +1,576 @@
+// Non-causal attention on tcgen05 + TMEM, two query tiles per CTA ("dq"): the product kernel for the 729..1024-token
+// SigLIP sequences.
+//
+// What round 1 measured (profiles/r01_attention_full.md, r01_ubench_tma.txt, r01_ubench_tc.txt): with one 128-row query tile
+// per CTA every K/V tile is fetched from L2 once per 128 query rows; at so400m shapes that is 7.6 TB/s of L2 -> SM traffic
+// and the K/V ring, not the tensor pipe (33 % busy) or the MUFU unit, bounded the kernel.  Here
+//   * one persistent CTA per SM owns 256 query rows (two 128-row tiles) of an (image, head): each K/V tile is read from
+//     L2 once per 256 rows (half the traffic per FLOP), in 128-key boxes (half the TMA instructions per byte);
+//   * Q lives in TMEM (bf16 pairs, A operand of S = Q·Kᵀ): an M128 N64 K16 MMA then takes ~42 cycles instead of ~75
+//     (the SS form re-reads the 128-row Q operand from shared memory for every key tile);
+//   * each query tile has its own softmax warpgroup (one thread per row, no shuffles), its own double-buffered S in
+//     TMEM and its own O accumulator, so the two tiles ping-pong on the tensor pipe while both warpgroups keep the MUFU
+//     unit busy; P (bf16) aliases S and is the TMEM A operand of O += P·V;
+//   * O leaves through a shared-memory staging tile and ONE TMA store per tile (the per-lane 16-byte global stores of the
+//     round-1 kernels cost 2.05x the output bytes in SM -> L2 traffic).
+//
+//   warp 0       TMA loader: next item's Q (prefetched while the current item runs), K/V in 128-key stages (3-deep ring)
+//   warps 1, 2   MMA issuers (one elected thread each): S_t,j = Q_t·K_jᵀ, O_t += P_t,j·V_j for query tile t = warp - 1
+//   warps 3-10   softmax / output of query tile 0 (two warps per 32 rows: each handles 32 of the 64 key columns)
+//   warps 11-18  softmax / output of query tile 1
+//
+// TMEM (512 columns):  S[t][buf] fp32 128x64 at (2t+buf)·64 | O[t] fp32 128x80 at 256+80t | Q[t] bf16x2 128x40 at 416+40t
+//
+// Reference semantics: HF:modeling_siglip.py:229-249,293-306 (softmax(q·kᵀ/sqrt(hd)) v, fp32 softmax, no mask).
+#include "dfd_common.cuh"
+
+#include <atomic>
+#include <cstdlib>
+#include <mutex>
+
+namespace dfd {
+
+extern std::atomic<int64_t> g_launches;
+
+namespace {
+
+constexpr int kQ = 128;          // query rows per tile
+constexpr int kKV = 64;          // keys per S tile
+constexpr int kStageKeys = 128;  // keys per ring stage (two S tiles)
+constexpr int kStages = 3;
+constexpr int kThreads = 608;    // loader, 2 MMA warps, 2 x 8 softmax warps
+constexpr int kTmemCols = 512;
+constexpr int kColO = 256;
+constexpr int kColQ = 416;
+
+__device__ long long g_dq_trace[64 * 16];   // DFD_ATTN_DBG & 128: clock64 stamps of CTA 0's first 64 tiles (see dfd_debug_read_trace)
+
+template <int HD>
+struct DqSmem {
+  static constexpr bool kTail = (HD % 64) != 0;
+  static constexpr int kQMainTile = kQ * 128;                        // 128 rows x 128 B, SWIZZLE_128B
+  static constexpr int kQTailTile = kTail ? kQ * 32 : 0;             // 128 rows x 32 B, SWIZZLE_32B
+  static constexpr int kQMain = 2 * kQMainTile, kQBytes = kQMain + 2 * kQTailTile;
+  static constexpr int kMain = kStageKeys * 128;                     // K or V main box of one stage
+  static constexpr int kTailB = kTail ? kStageKeys * 32 : 0;
+  static constexpr int kStageBytes = 2 * kMain + 2 * kTailB;         // K main | V main | K tail | V tail
+  static constexpr int kOutTile = kQ * HD * 2;                       // output staging of one query tile
+  static constexpr int kBarBytes = 256;
+  static constexpr int kOffKV = kQBytes;
+  static constexpr int kOffOut = kOffKV + kStages * kStageBytes;
+  static constexpr int kOffL = kOffOut + 2 * kOutTile;             // partial row sums exchanged between a row's two warps
+  static constexpr int kOffBar = kOffL + 2 * 2 * kQ * 4;
+  static constexpr int kTotal = kOffBar + kBarBytes + 1024;
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
+  static_assert(kQBytes % 1024 == 0 && kStageBytes % 1024 == 0 && kOutTile % 1024 == 0, "swizzle alignment");
+};
+
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+// 4-D tiled store shared -> global (bulk async group); rows past the tensor's extent are clipped by the TMA unit
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+template <int HD>
+__global__ void __launch_bounds__(kThreads, 1)
+attention_dq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_constant__ CUtensorMap tmTail,
+                    const __grid_constant__ CUtensorMap tmOut, int N, int H, int n_items, float scale_log2, int dbg) {
+  using S = DqSmem<HD>;
+  constexpr bool kTail = S::kTail;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + S::kOffKV;
+  uint8_t* sOut = smem + S::kOffOut;
+  float* l_ex = reinterpret_cast<float*>(smem + S::kOffL);   // [2 tiles][2 halves][128 rows] partial row sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
+  uint64_t* q_full = bars;                    // TMA: the item's two Q tiles are in shared memory
+  uint64_t* q_copied = bars + 1;              // [2] tile t's Q is in TMEM (8 warps)
+  uint64_t* kv_full = q_copied + 2;           // [kStages]
+  uint64_t* kv_empty = kv_full + kStages;     // [kStages] both MMA warps are done with the stage
+  uint64_t* s_full = kv_empty + kStages;      // [2 tiles][2 buffers]
+  uint64_t* p_full = s_full + 4;              // [2][2] (8 warps)
+  uint64_t* o_done = p_full + 4;              // [2] phase g: the g-th P·V of tile t (of this CTA) has retired
+  uint64_t* o_full = o_done + 2;              // [2] phase i: the last P·V of tile t of this CTA's i-th active item has retired
+  uint64_t* ld_done = o_full + 2;             // [2 tiles][4 quadrants] both warps of a row group hold their copy of the S tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_done + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = (N + kKV - 1) / kKV;                  // S tiles (64 keys) per item
+  const int TS = (N + kStageKeys - 1) / kStageKeys;   // ring stages per item
+  const int QP = (N + 2 * kQ - 1) / (2 * kQ);         // 256-row query pairs per (image, head)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmMain);
+    if (kTail) tma_prefetch_desc(&tmTail);
+    tma_prefetch_desc(&tmOut);
+    mbar_init(q_full, 1);
+    mbar_init(&q_copied[0], 8);
+    mbar_init(&q_copied[1], 8);
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 2);
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 8);
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&o_done[s], 1);
+      mbar_init(&o_full[s], 1);
+    }
+#pragma unroll
+    for (int s = 0; s < 8; ++s) mbar_init(&ld_done[s], 2);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------ TMA loader ------------------------------------
+    if (elect_one()) {
+      uint32_t ku0 = 0, ku1 = 0, ku2 = 0;   // uses of each ring stage so far (stages restart at 0 with every item)
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int qp = item % QP, h = (item / QP) % H, b = item / (QP * H);
+        mbar_wait(&q_copied[0], (it & 1u) ^ 1u);  // the previous item's Q tiles have been copied out of shared memory
+        mbar_wait(&q_copied[1], (it & 1u) ^ 1u);
+        mbar_expect_tx(q_full, S::kQBytes);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          tma_load_4d(&tmMain, q_full, sQ + t * S::kQMainTile, 0, h, qp * 2 * kQ + t * kQ, b);
+          if (kTail)
+            tma_load_4d(&tmTail, q_full, sQ + S::kQMain + t * S::kQTailTile, HD - 16, h, qp * 2 * kQ + t * kQ, b);
+        }
+        int st = 0;
+        for (int jj = 0; jj < TS; ++jj) {
+          const uint32_t n = st == 0 ? ku0++ : (st == 1 ? ku1++ : ku2++);
+          mbar_wait(&kv_empty[st], (n & 1u) ^ 1u);
+          if ((dbg & 2) && n > 0) { mbar_arrive(&kv_full[st]); st = (st + 1 == kStages) ? 0 : st + 1; continue; }
+          mbar_expect_tx(&kv_full[st], (dbg & 32) ? 2 * S::kMain : S::kStageBytes);
+          uint8_t* base = sKV + st * S::kStageBytes;
+          tma_load_4d(&tmMain, &kv_full[st], base, 0, H + h, jj * kStageKeys, b);
+          tma_load_4d(&tmMain, &kv_full[st], base + S::kMain, 0, 2 * H + h, jj * kStageKeys, b);
+          if (kTail && !(dbg & 32)) {
+            // tail boxes = columns HD-16..HD-1, in bounds (boxes that cross the tensor edge are served slowly); the 8
+            // columns they share with the main box meet zeros on the Q side and unread accumulator columns in P·V
+            tma_load_4d(&tmTail, &kv_full[st], base + 2 * S::kMain, HD - 16, H + h, jj * kStageKeys, b);
+            tma_load_4d(&tmTail, &kv_full[st], base + 2 * S::kMain + S::kTailB, HD - 16, 2 * H + h, jj * kStageKeys, b);
+          }
+          st = (st + 1 == kStages) ? 0 : st + 1;
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------ MMA issuers ------------------------------------
+    // One issuing thread per query tile: with a single thread walking both tiles in a fixed order a late P of one tile
+    // held back the other tile's P·V and next S (head-of-line blocking); the tensor pipe itself still runs in issue order.
+    if (elect_one()) {
+      const int t = warp - 1;
+      const uint64_t dK0 = umma_desc(smem_u32(sKV), 16, 1024, 2);
+      const uint64_t dV0 = umma_desc(smem_u32(sKV + S::kMain), 16, 1024, 2);  // MN-major, 8-key groups 1024 B apart
+      const uint64_t dKt0 = umma_desc(smem_u32(sKV + 2 * S::kMain), 16, 256, 6);
+      const uint64_t dVt0 = umma_desc(smem_u32(sKV + 2 * S::kMain + S::kTailB), 16, 256, 6);
+      constexpr uint64_t kStageStep = S::kStageBytes >> 4;       // descriptor start addresses count 16-byte units
+      constexpr uint64_t kHalfMain = (kKV * 128) >> 4;           // second 64 keys of a stage
+      constexpr uint64_t kHalfTail = (kKV * 32) >> 4;
+      constexpr uint32_t idesc_qk_full = umma_idesc_bf16_major(kQ, kKV, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16_major(kQ, 64, 0, 1);
+      constexpr uint32_t idesc_pvt = umma_idesc_bf16_major(kQ, 16, 0, 1);
+      const uint32_t tQ = tmem_base + kColQ + static_cast<uint32_t>(40 * t);
+      const uint32_t tO = tmem_base + kColO + static_cast<uint32_t>(80 * t);
+      uint32_t ku[kStages] = {0, 0, 0};   // kv_full uses per stage      (constant indices after unrolling)
+      uint32_t pu[2] = {0, 0};            // p_full uses per S buffer
+      // S_j = Q_t · K_jᵀ into S buffer j & 1.  u = j mod 6 (stage = u / 2, half = u % 2) is a constant after unrolling.
+      auto issue_qk = [&](int j, int u) {
+        const int st = u >> 1, hf = u & 1, sb = u & 1;
+        if (hf == 0) {  // first use of the stage by this item
+          mbar_wait(&kv_full[st], ku[st]++ & 1u);
+          tc_fence_after();
+        }
+        const uint32_t tS = tmem_base + static_cast<uint32_t>((2 * t + sb) * kKV);
+        const uint64_t dK = dK0 + st * kStageStep + hf * kHalfMain;
+        const int valid = N - j * kKV;
+        const uint32_t idesc_qk = valid >= kKV ? idesc_qk_full : umma_idesc_bf16_major(kQ, (valid + 15) & ~15, 0, 0);
+        if (!(dbg & 16)) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ts(tS, tQ + static_cast<uint32_t>(8 * k), dK + static_cast<uint64_t>(2 * k), idesc_qk, k != 0);
+        if (kTail && !(dbg & 4)) umma_bf16_ts(tS, tQ + 32, dKt0 + st * kStageStep + hf * kHalfTail, idesc_qk, 1u);
+        }
+        umma_commit(&s_full[2 * t + sb]);
+      };
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int qp = item % QP;
+        if (qp * 2 * kQ + t * kQ >= N) {
+          // (only tile 1) no real query rows: just hand the K/V stages back
+          for (int j6 = 0; j6 < TS; j6 += kStages) {
+#pragma unroll
+            for (int st = 0; st < kStages; ++st) {
+              if (j6 + st < TS) {
+                mbar_wait(&kv_full[st], ku[st]++ & 1u);
+                mbar_arrive(&kv_empty[st]);
+              }
+            }
+          }
+          continue;
+        }
+        mbar_wait(&q_copied[t], it & 1u);
+        tc_fence_after();
+        issue_qk(0, 0);
+        if (T > 1) issue_qk(1, 1);
+        for (int j6 = 0; j6 < T; j6 += 2 * kStages) {
+#pragma unroll
+          for (int u = 0; u < 2 * kStages; ++u) {
+            const int j = j6 + u;
+            if (j < T) {
+              const int st = u >> 1, hf = u & 1, sb = u & 1;
+              const uint64_t dV = dV0 + st * kStageStep + hf * kHalfMain;
+              const uint64_t dVt = dVt0 + st * kStageStep + hf * kHalfTail;
+              const int valid = N - j * kKV;
+              // ---- O (+)= P_j · V_j ----  (P written by the tile's softmax warps into the S columns)
+              const bool tr = (dbg & 128) && blockIdx.x == 0 && t == 0 && it == 0 && j < 64;
+              if (tr) g_dq_trace[j * 16 + 8] = clock64();
+              mbar_wait(&p_full[2 * t + sb], pu[sb]++ & 1u);
+              tc_fence_after();
+              if (tr) g_dq_trace[j * 16 + 9] = clock64();
+              const uint32_t tP = tmem_base + static_cast<uint32_t>((2 * t + sb) * kKV);
+              if (dbg & 8) {
+              } else if (valid >= kKV) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  // 16 keys per step: 16 rows x 128 B (main) / 16 rows x 32 B (tail); P: 8 packed columns per step
+                  const uint32_t acc = (kk != 0) ? 1u : (j != 0 ? 1u : 0u);
+                  umma_bf16_ts(tO, tP + static_cast<uint32_t>(8 * kk), dV + static_cast<uint64_t>(kk * 128), idesc_pv, acc);
+                  if (kTail && !(dbg & 4))
+                    umma_bf16_ts(tO + 64, tP + static_cast<uint32_t>(8 * kk), dVt + static_cast<uint64_t>(kk * 32),
+                                 idesc_pvt, acc);
+                }
+              } else {
+                const int ksteps = (valid + 15) >> 4;
+                for (int kk = 0; kk < ksteps; ++kk) {
+                  const uint32_t acc = (j | kk) != 0 ? 1u : 0u;
+                  umma_bf16_ts(tO, tP + static_cast<uint32_t>(8 * kk), dV + static_cast<uint64_t>(kk * 128), idesc_pv, acc);
+                  if (kTail)
+                    umma_bf16_ts(tO + 64, tP + static_cast<uint32_t>(8 * kk), dVt + static_cast<uint64_t>(kk * 32),
+                                 idesc_pvt, acc);
+                }
+              }
+              umma_commit(&o_done[t]);
+              if (j == T - 1) umma_commit(&o_full[t]);
+              // this tile is done with the stage after its second half (or the item's last tile)
+              if (hf == 1 || j == T - 1) umma_commit(&kv_empty[st]);
+              if (tr) g_dq_trace[j * 16 + 10] = clock64();
+              // the tensor pipe executes in issue order, so S buffer sb / P_j are free for tile j+2 right here
+              if (j + 2 < T) issue_qk(j + 2, (u + 2) % (2 * kStages));
+              if (tr) g_dq_trace[j * 16 + 11] = clock64();
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------ softmax / output ------------------------------------
+    // 16 warps: query tile t = (warp - 3) / 8; within a tile two warps share each TMEM lane quadrant (32 rows): both
+    // read the whole 64-column S row for the row maximum, then each exponentiates, sums and packs ITS 32 columns.  Four
+    // warps per scheduler (instead of two with one thread per row) keep the MUFU unit fed while others wait on TMEM
+    // round trips; the redundant maximum costs 22 FMNMX3 per tile.
+    const int sw = warp - 3;
+    const int t = sw >> 3;                    // query tile of this warp
+    const int hf = (sw >> 2) & 1;             // which 32 of the tile's 64 key columns this warp exponentiates
+    const int quad = warp & 3;                // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tO = tmem_base + lane_off + kColO + static_cast<uint32_t>(80 * t);
+    const uint32_t tQ = tmem_base + lane_off + kColQ + static_cast<uint32_t>(40 * t);
+    constexpr int kOChunks = (HD + 15) / 16;  // 16-column chunks of O
+    constexpr int kOSplit = (kOChunks + 1) / 2;  // chunks [0, kOSplit) belong to half 0, the rest to half 1
+    const int oc0 = hf ? kOSplit : 0, oc1 = hf ? kOChunks : kOSplit;
+    const uint32_t q_row = smem_u32(sQ + t * S::kQMainTile) + static_cast<uint32_t>(row * 128);
+    const uint32_t q_tail = smem_u32(sQ + S::kQMain + t * S::kQTailTile) + static_cast<uint32_t>(row * 32);
+    uint8_t* out_tile = sOut + t * S::kOutTile;
+    const uint32_t out_row = smem_u32(out_tile) + static_cast<uint32_t>(row * HD * 2);
+    float* l_mine = l_ex + (t * 2 + hf) * kQ + row;
+    const float* l_other = l_ex + (t * 2 + (hf ^ 1)) * kQ + row;
+    const bool store_thread = (sw & 7) == 0 && lane == 0;   // issues (and waits for) the tile's TMA stores
+    // Q row of item `it_q`: shared memory (TMA, swizzled) -> registers -> TMEM as bf16 pairs; each half moves 32 columns
+    auto copy_q = [&](uint32_t it_q) {
+      mbar_wait(q_full, it_q & 1u);
+      uint32_t qw[16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 v = lds_u4(q_row + static_cast<uint32_t>(((4 * hf + c) ^ (row & 7)) << 4));
+        qw[4 * c] = v.x; qw[4 * c + 1] = v.y; qw[4 * c + 2] = v.z; qw[4 * c + 3] = v.w;
+      }
+      tmem_st_32x32b_x16(tQ + static_cast<uint32_t>(16 * hf), qw);
+      if (kTail && hf == 1) {
+        // tail k-step = columns 56..71; 56..63 already went through the main box: Q contributes zeros there
+        uint32_t t8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        const uint4 v = lds_u4(q_tail + static_cast<uint32_t>((1 ^ ((row >> 2) & 1)) << 4));
+        t8[4] = v.x; t8[5] = v.y; t8[6] = v.z; t8[7] = v.w;
+        tmem_st_32x32b_x8(tQ + 32, t8);
+      }
+      tmem_st_wait();
+      // generic-proxy reads of the Q tile precede its TMA refill: proxy fence before the release (see gemm_tcgen05.cu)
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_copied[t]);
+    };
+    uint32_t su0 = 0, su1 = 0;   // s_full uses per S buffer
+    uint32_t g = 0, it = 0;      // running count of this tile's P·V products (o_done phases), item count
+    uint32_t act_items = 0;      // items in which this tile was active (o_full phases)
+    if (blockIdx.x < n_items) copy_q(0);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int qp = item % QP, h = (item / QP) % H, b = item / (QP * H);
+      const int row0 = qp * 2 * kQ + t * kQ;   // first query row of this tile
+      const bool has_next = item + (int)gridDim.x < n_items;
+      if (row0 >= N) {  // (only tile 1) nothing to do for this item; keep the Q hand-shake going
+        if (has_next) copy_q(it + 1);
+        continue;
+      }
+      float m = -INFINITY, l = 0.f;             // m is kept in log2 units (already multiplied by scale_log2)
+      for (int j = 0; j < T; ++j, ++g) {
+        const int sb = j & 1;
+        const int valid = min(kKV, N - j * kKV);
+        const uint32_t tS = tmem_base + lane_off + static_cast<uint32_t>((2 * t + sb) * kKV);
+        const uint32_t par = sb ? su1 : su0;
+        if (sb) ++su1; else ++su0;
+        const bool tr = (dbg & 128) && blockIdx.x == 0 && sw == 0 && lane == 0 && it == 0 && j < 64;
+        if (tr) g_dq_trace[j * 16 + 0] = clock64();
+        mbar_wait(&s_full[2 * t + sb], par & 1u);
+        tc_fence_after();
+        if (tr) g_dq_trace[j * 16 + 1] = clock64();
+        uint32_t s[32], o32[32];   // s: this warp's 32 columns, o32: the partner's (for the row maximum only)
+        tmem_ld_32x32b_x32(tS + static_cast<uint32_t>(32 * hf), s);
+        tmem_ld_32x32b_x32(tS + static_cast<uint32_t>(32 * (hf ^ 1)), o32);
+        tmem_ld_wait();
+        if (tr) g_dq_trace[j * 16 + 2] = clock64();
+        // P aliases the S columns BOTH warps of the row group have just read: neither may write its P before the other
+        // holds its copy (arrive here, wait just before the store - hundreds of cycles later, so it never blocks)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ld_done[4 * t + quad]);
+        if (valid < kKV) {  // last tile: keys past the sequence end (zero-filled K rows) never win
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (32 * hf + c >= valid) s[c] = __float_as_uint(-INFINITY);
+            if (32 * (hf ^ 1) + c >= valid) o32[c] = __float_as_uint(-INFINITY);
+          }
+        }
+        // 8 independent chains (a single running max would be a 64-deep dependent chain)
+        float mx8[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mx8[c] = fmaxf(__uint_as_float(s[c]), __uint_as_float(o32[c]));
+#pragma unroll
+        for (int c = 8; c < 32; ++c)
+          mx8[c & 7] = fmaxf(mx8[c & 7], fmaxf(__uint_as_float(s[c]), __uint_as_float(o32[c])));
+        float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                         fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+        mx *= scale_log2;  // scale > 0
+        // lazy rescale: keep the old reference max unless the new one is more than 2^8 larger.  Both warps of a row see
+        // the same 64 values, so they take the same decision and keep the same m.
+        const float m_new = (mx > m + 8.0f) ? mx : m;
+        const bool moved = m_new != m;
+        const float alpha = (j == 0) ? 0.f : fast_exp2(m - m_new);
+        if (j > 0 && __any_sync(0xffffffffu, moved)) {
+          mbar_wait(&o_done[t], (g - 1) & 1u);  // the previous P·V has retired: O is stable
+          tc_fence_after();
+          for (int c = oc0; c < oc1; ++c) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(tO + static_cast<uint32_t>(16 * c), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x16(tO + static_cast<uint32_t>(16 * c), o);
+          }
+        }
+        m = m_new;
+        float sum8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const float neg_m = -m;
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          float p0 = fmaf(__uint_as_float(s[2 * c]), scale_log2, neg_m);
+          float p1 = fmaf(__uint_as_float(s[2 * c + 1]), scale_log2, neg_m);
+          if (!(dbg & 1)) { p0 = fast_exp2(p0); p1 = fast_exp2(p1); }
+          sum8[(2 * c) & 7] += p0;
+          sum8[(2 * c + 1) & 7] += p1;
+          pk[c] = pack_bf16x2(p0, p1);
+        }
+        l = l * alpha + (((sum8[0] + sum8[1]) + (sum8[2] + sum8[3])) + ((sum8[4] + sum8[5]) + (sum8[6] + sum8[7])));
+        if (tr) g_dq_trace[j * 16 + 3] = clock64();
+        mbar_wait(&ld_done[4 * t + quad], g & 1u);
+        tc_fence_after();
+        tmem_st_32x32b_x16(tS + static_cast<uint32_t>(16 * hf), pk);   // P (bf16 pairs) aliases the S buffer's first 32 columns
+        tmem_st_wait();
+        if (tr) g_dq_trace[j * 16 + 4] = clock64();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[2 * t + sb]);
+        if (tr) g_dq_trace[j * 16 + 5] = clock64();
+      }
+      // every Q_t·Kᵀ of this item has retired (its last S tile has been consumed): the next item's Q may replace it in
+      // TMEM now, so that the MMA warp can start the next item's S tiles while this item's output is written
+      if (has_next) copy_q(it + 1);
+      // ---- O / l -> bf16 -> staging tile -> one TMA store ----
+      *l_mine = l;
+      mbar_wait(&o_full[t], act_items++ & 1u);
+      tc_fence_after();
+      if (store_thread) tma_store_wait_read<0>();   // the previous store of this tile has finished reading the staging tile
+      bar_sync_named(1 + t, 256);
+      const float inv = 1.0f / (hf ? (*l_other + l) : (l + *l_other));   // same order of the two partial sums in both warps
+      for (int c = oc0; c < oc1; ++c) {
+        uint32_t o[16];
+        tmem_ld_32x32b_x16(tO + static_cast<uint32_t>(16 * c), o);
+        tmem_ld_wait();
+        if (kTail && c == kOChunks - 1) {  // tail accumulator = columns 56..71: its upper half is columns 64..71
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = o[8 + i];
+        }
+        uint4 lo, hi;
+        lo.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+        lo.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+        lo.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+        lo.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+        hi.x = pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+        hi.y = pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+        hi.z = pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+        hi.w = pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+        if (HD == 64) {   // 128-byte rows: SWIZZLE_128B staging (16-byte chunk index XOR row mod 8), conflict free
+          sts_u4(out_row + static_cast<uint32_t>(((2 * c) ^ (row & 7)) << 4), lo);
+          sts_u4(out_row + static_cast<uint32_t>(((2 * c + 1) ^ (row & 7)) << 4), hi);
+        } else {          // 144-byte rows, no swizzle: consecutive rows are 9 chunks apart, conflict free as they are
+          sts_u4(out_row + static_cast<uint32_t>(32 * c), lo);
+          if (16 * c + 8 < HD) sts_u4(out_row + static_cast<uint32_t>(32 * c + 16), hi);
+        }
+      }
+      fence_proxy_async_smem();
+      // order this item's TMEM reads before the p_full arrive that lets the next item's first P·V overwrite O
+      tc_fence_before();
+      bar_sync_named(1 + t, 256);
+      if (store_thread && !(dbg & 64)) {
+        tma_store_4d(&tmOut, out_tile, 0, h, row0, b);   // rows >= N are clipped
+        tma_store_commit();
+      }
+    }
+    if (store_thread) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled dq_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// [B*N, ld] bf16 viewed as (hd, heads, N, B); box = box_cols x 1 x box_rows x 1
+int make_tmap_heads(CUtensorMap* out, const void* base, int hd, int heads, int N, int B, int64_t ld, int box_cols,
+                    int box_rows, CUtensorMapSwizzle sw, bool store) {
+  PFN_encodeTiled fn = dq_encode_fn();
+  DFD_REQUIRE(fn != nullptr, DFD_ERR_NO_DEVICE, "cuTensorMapEncodeTiled unavailable (no CUDA driver on this host)");
+  cuuint64_t gdim[4] = {(cuuint64_t)hd, (cuuint64_t)heads, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)hd * 2, (cuuint64_t)ld * 2, (cuuint64_t)N * (cuuint64_t)ld * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_cols, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  store ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DFD_REQUIRE(r == CUDA_SUCCESS, DFD_ERR_CUDA, "cuTensorMapEncodeTiled(heads 4-D) failed (%d)", (int)r);
+  return DFD_OK;
+}
+
+}  // namespace
+
+int attention_dq_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
+                      float scale, cudaStream_t st) {
+  DFD_REQUIRE(qkv && out, DFD_ERR_BAD_ARG, "attention: null pointer");
+  DFD_REQUIRE(B > 0 && N > 0 && H > 0, DFD_ERR_SHAPE, "attention: B, N, H must be positive");
+  DFD_REQUIRE(hd == 64 || hd == 72, DFD_ERR_UNSUPPORTED, "attention: head dim %d not supported (64, 72)", hd);
+  DFD_REQUIRE(ldqkv % 8 == 0 && ldqkv >= 3 * H * hd && ldo % 8 == 0 && ldo >= H * hd, DFD_ERR_SHAPE,
+              "attention: bad leading dimensions");
+  DFD_REQUIRE(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0), DFD_ERR_BAD_ARG,
+              "attention: pointers must be 16-byte aligned");
+  const int64_t items64 = (int64_t)((N + 2 * kQ - 1) / (2 * kQ)) * H * B;
+  DFD_REQUIRE(items64 < (1ll << 31), DFD_ERR_SHAPE, "attention: too many work items");
+  CUtensorMap tmMain, tmTail, tmOut;
+  int rc = make_tmap_heads(&tmMain, qkv, hd, 3 * H, N, B, ldqkv, 64, kStageKeys, CU_TENSOR_MAP_SWIZZLE_128B, false);
+  if (rc != DFD_OK) return rc;
+  tmTail = tmMain;
+  if (hd == 72) {
+    rc = make_tmap_heads(&tmTail, qkv, hd, 3 * H, N, B, ldqkv, 16, kStageKeys, CU_TENSOR_MAP_SWIZZLE_32B, false);
+    if (rc != DFD_OK) return rc;
+  }
+  rc = make_tmap_heads(&tmOut, out, hd, H, N, B, ldo, hd, kQ,
+                       hd == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, true);
+  if (rc != DFD_OK) return rc;
+  const float scale_log2 = scale * 1.4426950408889634f;
+  const int n_items = (int)items64;
+  const int grid = n_items < kNumSMs ? n_items : kNumSMs;
+  static SmemOptIn smem_once[2];
+  const char* dbg_env = getenv("DFD_ATTN_DBG");
+  const int dbg = dbg_env ? atoi(dbg_env) : 0;
+  if (hd == 64) {
+    if (int rc2 = ensure_dynamic_smem(smem_once[0], attention_dq_kernel<64>, DqSmem<64>::kTotal)) return rc2;
+    attention_dq_kernel<64><<<grid, kThreads, DqSmem<64>::kTotal, st>>>(tmMain, tmTail, tmOut, N, H, n_items, scale_log2, dbg);
+  } else {
+    if (int rc2 = ensure_dynamic_smem(smem_once[1], attention_dq_kernel<72>, DqSmem<72>::kTotal)) return rc2;
+    attention_dq_kernel<72><<<grid, kThreads, DqSmem<72>::kTotal, st>>>(tmMain, tmTail, tmOut, N, H, n_items, scale_log2, dbg);
+  }
+  DFD_LAUNCH_CHECK();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return DFD_OK;
+}
+
+}  // namespace dfd
+
+// Development hook: the clock64 stamps of the last attention_dq launch that ran with DFD_ATTN_DBG & 128.
+extern "C" DFD_API int dfd_debug_read_trace(long long* host, int n) {
+  if (n > 64 * 16) n = 64 * 16;
+  return cudaMemcpyFromSymbol(host, dfd::g_dq_trace, sizeof(long long) * n) == cudaSuccess ? 0 : -4;
+}

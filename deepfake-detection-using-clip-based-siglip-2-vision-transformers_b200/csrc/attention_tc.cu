@@ -420,6 +420,8 @@ int attention_auto_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, 
 // (attention_pq.cu).
 extern "C" DFD_API int dfd_attention_bf16_impl(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N,
                                                int H, int hd, float scale, int impl, void* stream) {
+  if (impl == 5)
+    return dfd::attention_dq_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));
   if (impl == 4)
     return dfd::attention_pq_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));
   if (impl == 2 || impl == 3)

@@ -109,12 +109,14 @@ struct PatchArgs {
   const void* pixels;
   int fmt;  // 0 u8 NHWC, 1 f32 NCHW
   int B, Hin, Win, S, P, G, K, mode;
+  int flip;  // 1: every image is read mirrored left-right (the TTA "H-Flip" view, inference_ai_human_images.py:207-214)
   float sy, sx;  // Hin/S, Win/S (fp32, as ATen computes them)
   __nv_bfloat16* A;
   int64_t lda;
 };
 
 __device__ __forceinline__ float fetch_pixel(const PatchArgs& a, int b, int c, int y, int x) {
+  if (a.flip) x = a.Win - 1 - x;  // the flip acts on the SOURCE image, i.e. before any in-model resample, as the transform does
   if (a.fmt == 0) {
     const uint8_t* p = reinterpret_cast<const uint8_t*>(a.pixels);
     const float u = (float)__ldg(p + (((int64_t)b * a.Hin + y) * a.Win + x) * 3 + c);
@@ -199,7 +201,8 @@ __global__ void __launch_bounds__(256) patchify_u8_rows_kernel(PatchArgs a) {
     if (k < a.K) {
       const int c = k / PP, r = k - c * PP;
       const int ky = r / a.P, kx = r - ky * a.P;
-      koff[k] = (uint16_t)((ky * a.Win + kx) * 3 + c);
+      // mirrored: patch gx, column kx reads source pixel Win-1-(gx P + kx); the gx part moves into `base` below
+      koff[k] = (uint16_t)((ky * a.Win + (a.flip ? a.Win - 1 - kx : kx)) * 3 + c);
     } else {
       koff[k] = 0xffffu;
     }
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(256) patchify_u8_rows_kernel(PatchArgs a) {
   uint4* dst = reinterpret_cast<uint4*>(a.A + ((int64_t)b * a.G + gy) * a.G * a.lda);
   for (int idx = tid; idx < a.G * vec_per_row; idx += 256) {
     const int gx = idx / vec_per_row, vcol = idx - gx * vec_per_row;
-    const uint8_t* base = pix + head + gx * a.P * 3;
+    const uint8_t* base = a.flip ? pix + head - gx * a.P * 3 : pix + head + gx * a.P * 3;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -268,7 +271,9 @@ int patchify(const void* pixels, int pix_format, int B, int Hin, int Win, int S,
              void* A, int64_t lda, cudaStream_t st) {
   DFD_REQUIRE(pixels && A, DFD_ERR_BAD_ARG, "patchify: null pointer");
   DFD_REQUIRE(pix_format == 0 || pix_format == 1, DFD_ERR_BAD_ARG, "patchify: pix_format must be 0 or 1");
-  DFD_REQUIRE(resize_mode >= 0 && resize_mode <= 2, DFD_ERR_BAD_ARG, "patchify: resize_mode must be 0..2");
+  const int flip = (resize_mode >> 4) & 1;   // DFD_FLIP_H
+  resize_mode &= 0xF;
+  DFD_REQUIRE(resize_mode >= 0 && resize_mode <= 2, DFD_ERR_BAD_ARG, "patchify: resize_mode must be 0..2 (| DFD_FLIP_H)");
   DFD_REQUIRE(B > 0 && Hin > 0 && Win > 0 && S > 0 && P > 0 && P <= S, DFD_ERR_SHAPE,
               "patchify: bad shape");
   // mode 0 reads the top-left G*P x G*P pixels only (conv padding='valid'), so any input on the same patch grid
@@ -283,6 +288,7 @@ int patchify(const void* pixels, int pix_format, int B, int Hin, int Win, int S,
   a.fmt = pix_format;
   a.B = B; a.Hin = Hin; a.Win = Win; a.S = S; a.P = P; a.G = S / P; a.K = K;
   a.mode = (Hin >= GP && Hin < GP + P && Win >= GP && Win < GP + P) ? 0 : resize_mode;
+  a.flip = flip;
   a.sy = (float)Hin / (float)S;
   a.sx = (float)Win / (float)S;
   a.A = reinterpret_cast<__nv_bfloat16*>(A);

@@ -175,8 +175,10 @@ void carve_acts(dfd_engine* e, uint8_t* base, int64_t* total) {
   e->r = c.take<__nv_bfloat16>(B * D);
   e->h2 = c.take<__nv_bfloat16>(B * D);
   e->m2 = c.take<__nv_bfloat16>(B * I);
-  e->stats_a = c.take<float>(M * 2);
-  e->stats_b = c.take<float>(M * 2);
+  // row statistics of the residual stream: one (Σx, Σx²) pair per 64-column chunk and row, [ceil(D/64)][M][2]
+  const int64_t parts = (D + 63) / 64;
+  e->stats_a = c.take<float>(parts * M * 2);
+  e->stats_b = c.take<float>(parts * M * 2);
   *total = c.off;
 }
 
@@ -394,9 +396,11 @@ extern "C" DFD_API int dfd_engine_set_tensor(dfd_engine* e, const char* name, co
   const int64_t total = s.rows * s.dst_cols;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4096) blocks = 4096;
+  // Stream ordered on the legacy default stream: the H2D copy into the staging buffer (which returns once the pageable
+  // source has been consumed), this kernel, and the next tensor's copy into the same buffer run in order, so no device
+  // synchronisation is needed per tensor — dfd_engine_finalize synchronises once (448 tensors for so400m).
   convert_rows_kernel<<<blocks, 256>>>(src, dtype, s.rows, s.cols, s.dst, s.dst_bf16, s.dst_ld, s.dst_cols);
   DFD_LAUNCH_CHECK();
-  DFD_CUDA(cudaDeviceSynchronize());  // weight loading is not a hot path; keeps staging reuse simple
   mark_set(e, name);
   e->finalized = false;
   if (e->folded) {  // weights were folded in place: a partial reload would mix folded and raw tensors
@@ -501,6 +505,15 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
   DFD_REQUIRE(e && pixels && pooled, DFD_ERR_BAD_ARG, "forward: null pointer");
   DFD_REQUIRE(e->finalized, DFD_ERR_STATE, "forward: engine not finalized");
   DFD_REQUIRE(B > 0 && B <= e->max_batch, DFD_ERR_SHAPE, "forward: batch %d outside 1..%d", B, e->max_batch);
+  {
+    // kernels are launched on the CURRENT device: refuse to run against another device's pointers (the stream handed in
+    // belongs to the caller's device as well)
+    int cur = -1;
+    DFD_CUDA(cudaGetDevice(&cur));
+    DFD_REQUIRE(cur == e->device, DFD_ERR_STATE,
+                "forward: the engine lives on device %d but device %d is current (cudaSetDevice / torch.cuda.device first)",
+                e->device, cur);
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int N = e->N, D = e->D, I = e->I, H = e->H, hd = e->hd;
   const int M = B * N;
@@ -509,16 +522,13 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
 
   DFD_OP(3, patchify(pixels, pix_format, B, Hin, Win, e->S, e->P, resize_mode, e->patches, e->Kpad, st));
   const bool fuse = e->cfg.fuse_ln != 0;
-  const size_t stats_bytes = (size_t)M * 2 * sizeof(float);
+  const int ln_parts = (D + 63) / 64;  // partial statistics per row written by the GEMM that produced the residual stream
   {
     dfd_gemm_epilogue ep{};
     ep.bias = e->b_pe;
     ep.pos = e->pos;
     ep.pos_rows = N;
-    if (fuse) {
-      DFD_CUDA(cudaMemsetAsync(e->stats_a, 0, stats_bytes, st));
-      ep.stats_out = e->stats_a;
-    }
+    if (fuse) ep.stats_out = e->stats_a;
     DFD_OP(0, gemm_bf16_dispatch(e->patches, e->Kpad, e->w_pe, e->Kpad, e->x, D, M, D, e->Kpad, &ep, 0, st));
   }
   const size_t hid_bytes = (size_t)M * D * sizeof(__nv_bfloat16);
@@ -530,6 +540,7 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
       dfd_gemm_epilogue ep{};
       ep.bias = l.b_qkv;
       ep.ln_rowstats = e->stats_a;
+      ep.ln_parts = ln_parts;
       ep.ln_colsum = l.cs_qkv;
       ep.ln_dim = D;
       ep.ln_eps = eps;
@@ -546,10 +557,7 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
       ep.bias = l.b_o;
       ep.residual = e->x;
       ep.ldr = D;
-      if (fuse) {
-        DFD_CUDA(cudaMemsetAsync(e->stats_b, 0, stats_bytes, st));
-        ep.stats_out = e->stats_b;
-      }
+      if (fuse) ep.stats_out = e->stats_b;
       DFD_OP(0, gemm_bf16_dispatch(e->att, D, l.w_o, D, e->x, D, M, D, D, &ep, 0, st));
     }
     if (fuse) {
@@ -557,6 +565,7 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
       ep.bias = l.b_fc1;
       ep.act = 1;
       ep.ln_rowstats = e->stats_b;
+      ep.ln_parts = ln_parts;
       ep.ln_colsum = l.cs_fc1;
       ep.ln_dim = D;
       ep.ln_eps = eps;
@@ -573,10 +582,7 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
       ep.bias = l.b_fc2;
       ep.residual = e->x;
       ep.ldr = D;
-      if (fuse && li + 1 < e->L) {  // statistics for the next layer's LN1 (the post-LN runs as a kernel)
-        DFD_CUDA(cudaMemsetAsync(e->stats_a, 0, stats_bytes, st));
-        ep.stats_out = e->stats_a;
-      }
+      if (fuse && li + 1 < e->L) ep.stats_out = e->stats_a;  // for the next layer's LN1 (the post-LN runs as a kernel)
       DFD_OP(0, gemm_bf16_dispatch(e->mlp, I, l.w_fc2, I, e->x, D, M, D, I, &ep, 0, st));
     }
     if (e->hidden_tap)

@@ -15,6 +15,12 @@
 namespace dfd {
 
 extern std::atomic<int64_t> g_launches;
+static std::atomic<int> g_last_variant{0};  // BN + 1000·CG + 10000·RES + 100000·EPI of the last GEMM launch (tests)
+static std::atomic<int64_t> g_variant_launches[3 * 2 * 2 * 7];  // launches per instantiation since load (tests)
+static int variant_slot(int bn, int cg, int res, int epi) {
+  const int b = bn == 256 ? 2 : (bn == 192 ? 1 : 0);
+  return ((b * 2 + (cg - 1)) * 2 + res) * 7 + epi;
+}
 
 namespace {
 
@@ -39,6 +45,7 @@ struct EpiArgs {
   float ln_eps;
   float* stats_out;
   int residual_op;  // 0: v += residual, 1: v *= residual
+  int ln_parts;     // ln_rowstats holds this many partial (Σx, Σx²) pairs per row: [ln_parts][M][2]
 };
 
 // CG = CTAs per MMA (1, or 2 = cta_group::2: a 256 x BN tile shared by an SM pair, each CTA staging its own
@@ -347,14 +354,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 
       float ln_mean = 0.f, ln_rstd = 1.f;
       if (f_ln && row_ok) {
-        const float2 st = *reinterpret_cast<const float2*>(epi.ln_rowstats + 2 * (int64_t)row);
-        ln_mean = st.x * epi.ln_inv_dim;
-        const float var = fmaxf(st.y * epi.ln_inv_dim - ln_mean * ln_mean, 0.f);
+        // the producer GEMM left one (Σx, Σx²) pair per 64-column chunk of the row; they are added here in a fixed
+        // order (no atomics anywhere: results are bit-reproducible run to run)
+        const float2* rs = reinterpret_cast<const float2*>(epi.ln_rowstats) + row;
+        float s_sum = 0.f, s_sq = 0.f;
+        for (int p = 0; p < epi.ln_parts; ++p) {
+          const float2 st = __ldg(rs + (int64_t)p * M);
+          s_sum += st.x;
+          s_sq += st.y;
+        }
+        ln_mean = s_sum * epi.ln_inv_dim;
+        const float var = fmaxf(s_sq * epi.ln_inv_dim - ln_mean * ln_mean, 0.f);
         ln_rstd = rsqrtf(var + epi.ln_eps);
       }
       const float* pos_row =
           f_pos ? epi.pos + (int64_t)(row_ok ? (row % epi.pos_rows) : 0) * N : nullptr;
-      float st_sum = 0.f, st_sq = 0.f;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -409,6 +423,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           if (lane == 0) mbar_arrive(&rempty_bar[slot]);
         }
         uint4 o[8];
+        float st_sum = 0.f, st_sq = 0.f;
         // two fp32 lanes per instruction (FFMA2 / FADD2 / FMUL2): the fused epilogues (LayerNorm fold + bias + GELU)
         // were issue bound — fc1 held the tensor pipe at 70 % (profiles/r01_gemm_full.md)
         const float2 nmean2 = make_float2(-ln_mean, -ln_mean), rstd2 = make_float2(ln_rstd, ln_rstd);
@@ -495,10 +510,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           tma_store_2d(&tmC, stage_c, c0, m0);  // rows >= M and columns >= N are clipped by the TMA unit
           tma_store_commit();
         }
-      }
-      if (f_stats && row_ok) {
-        atomicAdd(epi.stats_out + 2 * (int64_t)row, st_sum);
-        atomicAdd(epi.stats_out + 2 * (int64_t)row + 1, st_sq);
+        // row statistics of the bf16 output, one partial per (64-column chunk, row): every slot is written exactly once
+        // per GEMM, 32 consecutive rows per warp store (coalesced), and summed in chunk order by the consumer
+        if (f_stats && row_ok)
+          reinterpret_cast<float2*>(epi.stats_out)[(int64_t)(c0 / kChunkN) * M + row] = make_float2(st_sum, st_sq);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -583,6 +598,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   cfg.numAttrs = 1;
   DFD_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CG, RES, EPI>, tmA, tmB, tmC, tmR, M, N, K, ea));
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  g_last_variant.store(BN + 1000 * CG + 10000 * RES + 100000 * EPI, std::memory_order_relaxed);
+  g_variant_launches[variant_slot(BN, CG, RES, EPI)].fetch_add(1, std::memory_order_relaxed);
   return DFD_OK;
 }
 
@@ -633,6 +650,7 @@ int gemm_bf16_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, v
     ea.ln_eps = epi->ln_eps;
     ea.stats_out = epi->stats_out;
     ea.residual_op = epi->residual_op;
+    ea.ln_parts = epi->ln_parts > 0 ? epi->ln_parts : 1;
     DFD_REQUIRE(ea.act >= 0 && ea.act <= 3, DFD_ERR_BAD_ARG, "gemm: act must be 0 (none), 1 (gelu_tanh), 2 (gelu_erf) or 3 (sigmoid)");
     DFD_REQUIRE(ea.residual_op == 0 || ea.residual_op == 1, DFD_ERR_BAD_ARG, "gemm: residual_op must be 0 (add) or 1 (multiply)");
     DFD_REQUIRE((ea.ln_colsum == nullptr) == (ea.ln_rowstats == nullptr), DFD_ERR_BAD_ARG,
@@ -692,6 +710,16 @@ int gemm_bf16_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, v
 }
 
 }  // namespace dfd
+
+// Which kernel instantiation the last dfd_gemm_bf16[_tile] call of this process launched:
+// BN + 1000·CG + 10000·RES + 100000·EPI (tests assert that the specialised epilogues are the ones being checked).
+extern "C" DFD_API int dfd_gemm_last_variant(void) { return dfd::g_last_variant.load(std::memory_order_relaxed); }
+// Launches of one instantiation (same encoding) by this process since load; -1 for an encoding that names no kernel.
+extern "C" DFD_API int64_t dfd_gemm_variant_launches(int variant) {
+  const int bn = variant % 1000, cg = variant / 1000 % 10, res = variant / 10000 % 10, epi = variant / 100000;
+  if ((bn != 128 && bn != 192 && bn != 256) || cg < 1 || cg > 2 || res < 0 || res > 1 || epi < 0 || epi > 6) return -1;
+  return dfd::g_variant_launches[dfd::variant_slot(bn, cg, res, epi)].load(std::memory_order_relaxed);
+}
 
 // Host-only view of the persistent schedule: the tile that `unit` (of `units`) processes in `round`, or -1 when it has none.
 extern "C" DFD_API int dfd_gemm_schedule(int num_tiles, int num_n, int units, int unit, int round) {

@@ -36,6 +36,10 @@ def init_from_env(backend: str | None = None) -> Tuple[int, int, int]:
     return rank, world, local
 
 
+def rank() -> int:
+    return dist.get_rank() if dist.is_initialized() else 0
+
+
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous split of n units: rank r gets [lo, hi); the first n % world ranks get one extra."""
     base, rem = divmod(n, world)

@@ -15,12 +15,16 @@ imported unmodified on a box without those packages.
 """
 from __future__ import annotations
 
+import os
 import sys
 import types
+import warnings
 from typing import Dict, Iterable, Optional
 
 import numpy as np
 import torch
+import torch.nn as nn
+from torch.nn.modules.module import _IncompatibleKeys
 
 from . import ops
 from .engine import ARCHS, SiglipEngine, VisionArch, arch_from_state_dict, canonicalize_state_dict
@@ -50,68 +54,272 @@ def make_preprocess(resolution: int, interpolation: str = "bicubic"):
     ])
 
 
-class VisionTower:
-    """The object `open_clip.create_model_and_transforms` returns, reduced to what the reference touches:
-    `encode_image`, `embed_dim`, `eval`, `to`, `load_state_dict`, `parameters`."""
+# ---------------------------------------------------------------------------------------------------------------------
+# open_clip-shaped vision tower: a real nn.Module whose registered parameters carry the timm names of open_clip's SigLIP
+# models (visual.trunk.blocks.i.attn.qkv.weight, visual.trunk.attn_pool.*, visual.trunk.pos_embed, ...), so that the
+# reference's OWN classes - BinaryClassifier(nn.Module) of inference_ai_human_images.py:111-152 and
+# train_fusion_head_only.py:78-109 - register it as a submodule and their load_state_dict(strict=True) /
+# _filter_state_for_model route the checkpoint's `backbone.*` tensors into it.  The parameters are the source of truth;
+# the dfd engine keeps a packed bf16 copy that is refreshed whenever they change (load_state_dict, in-place updates).
+# ---------------------------------------------------------------------------------------------------------------------
+class _Holder(nn.Module):
+    """Parameter container with the reference model's attribute names; never called (the dfd engine runs the math)."""
 
-    def __init__(self, arch: VisionArch, device, max_batch: int = 64, state_dict: Optional[dict] = None, seed: int = 0):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("dfd: this module only holds parameters; call the tower's encode_image()")
+
+
+def _linear(out_f: int, in_f: int) -> nn.Module:
+    m = _Holder()
+    m.weight = nn.Parameter(torch.empty(out_f, in_f), requires_grad=False)
+    m.bias = nn.Parameter(torch.empty(out_f), requires_grad=False)
+    return m
+
+
+def _norm(dim: int) -> nn.Module:
+    m = _Holder()
+    m.weight = nn.Parameter(torch.empty(dim), requires_grad=False)
+    m.bias = nn.Parameter(torch.empty(dim), requires_grad=False)
+    return m
+
+
+def _timm_trunk(a: VisionArch) -> nn.Module:
+    """Skeleton of timm's VisionTransformer(global_pool='map') as open_clip builds it for SigLIP."""
+    D, I, P, N = a.hidden_size, a.intermediate_size, a.patch_size, a.tokens
+    trunk = _Holder()
+    trunk.patch_embed = _Holder()
+    trunk.patch_embed.proj = _Holder()
+    trunk.patch_embed.proj.weight = nn.Parameter(torch.empty(D, 3, P, P), requires_grad=False)
+    trunk.patch_embed.proj.bias = nn.Parameter(torch.empty(D), requires_grad=False)
+    trunk.pos_embed = nn.Parameter(torch.empty(1, N, D), requires_grad=False)
+    blocks = []
+    for _ in range(a.num_hidden_layers):
+        b = _Holder()
+        b.norm1, b.norm2 = _norm(D), _norm(D)
+        b.attn = _Holder()
+        b.attn.qkv, b.attn.proj = _linear(3 * D, D), _linear(D, D)
+        b.mlp = _Holder()
+        b.mlp.fc1, b.mlp.fc2 = _linear(I, D), _linear(D, I)
+        blocks.append(b)
+    trunk.blocks = nn.ModuleList(blocks)
+    trunk.norm = _norm(D)
+    ap = _Holder()
+    ap.latent = nn.Parameter(torch.empty(1, 1, D), requires_grad=False)
+    ap.q, ap.kv, ap.proj, ap.norm = _linear(D, D), _linear(2 * D, D), _linear(D, D), _norm(D)
+    ap.mlp = _Holder()
+    ap.mlp.fc1, ap.mlp.fc2 = _linear(I, D), _linear(D, I)
+    trunk.attn_pool = ap
+    return trunk
+
+
+def timm_state_from_canonical(canon: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Engine-canonical (HF-style) vision tensors -> open_clip/timm names under `visual.trunk.` (inverse of
+    engine.canonicalize_state_dict for that layout)."""
+    out: Dict[str, torch.Tensor] = {}
+    T = "visual.trunk."
+    out[T + "patch_embed.proj.weight"] = canon["embeddings.patch_embedding.weight"]
+    out[T + "patch_embed.proj.bias"] = canon["embeddings.patch_embedding.bias"]
+    pe = canon["embeddings.position_embedding.weight"]
+    out[T + "pos_embed"] = pe.reshape(1, pe.shape[-2], pe.shape[-1])
+    L = 1 + max(int(k.split(".")[2]) for k in canon if k.startswith("encoder.layers."))
+    for i in range(L):
+        s, d = f"encoder.layers.{i}.", f"{T}blocks.{i}."
+        for n in ("weight", "bias"):
+            out[d + "norm1." + n] = canon[s + "layer_norm1." + n]
+            out[d + "norm2." + n] = canon[s + "layer_norm2." + n]
+            if s + "self_attn.qkv." + n in canon:
+                out[d + "attn.qkv." + n] = canon[s + "self_attn.qkv." + n]
+            else:
+                out[d + "attn.qkv." + n] = torch.cat([canon[s + f"self_attn.{x}_proj." + n] for x in "qkv"], 0)
+            out[d + "attn.proj." + n] = canon[s + "self_attn.out_proj." + n]
+            out[d + "mlp.fc1." + n] = canon[s + "mlp.fc1." + n]
+            out[d + "mlp.fc2." + n] = canon[s + "mlp.fc2." + n]
+    for n in ("weight", "bias"):
+        out[T + "norm." + n] = canon["post_layernorm." + n]
+        out[T + "attn_pool.proj." + n] = canon["head.attention.out_proj." + n]
+        out[T + "attn_pool.norm." + n] = canon["head.layernorm." + n]
+        out[T + "attn_pool.mlp.fc1." + n] = canon["head.mlp.fc1." + n]
+        out[T + "attn_pool.mlp.fc2." + n] = canon["head.mlp.fc2." + n]
+    D = pe.shape[-1]
+    out[T + "attn_pool.latent"] = canon["head.probe"].reshape(1, 1, D)
+    w, b = canon["head.attention.in_proj_weight"], canon["head.attention.in_proj_bias"]
+    out[T + "attn_pool.q.weight"], out[T + "attn_pool.kv.weight"] = w[:D], w[D:]
+    out[T + "attn_pool.q.bias"], out[T + "attn_pool.kv.bias"] = b[:D], b[D:]
+    return out
+
+
+class _TextSink(nn.Module):
+    """Stands where open_clip keeps the text tower: swallows `text.*` checkpoint keys (the reference drops them,
+    train_fusion_head_only.py:115) so that a strict load of a full open_clip checkpoint still succeeds."""
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        return
+
+
+class VisionTower(nn.Module):
+    """What `open_clip.create_model_and_transforms` returns, reduced to what the reference touches: an nn.Module with
+    `encode_image`, `embed_dim`, `visual.trunk.*` parameters (timm names), `eval/to/parameters/state_dict/
+    load_state_dict`.  The forward runs on the dfd engine (hand-written sm_100a kernels); there is no torch fallback."""
+
+    def __init__(self, arch: VisionArch, device, max_batch: int = 64, state_dict: Optional[dict] = None, seed: int = 0,
+                 fuse_ln: bool = True):
+        super().__init__()
         self.arch = arch
-        self.device = _as_device(device)
+        d = torch.device(device)
+        # Without a CUDA device only the parameter skeleton exists (state-dict round trips work, e.g. to inspect or
+        # convert checkpoints); every forward raises - there is no CPU fallback.
+        self._device = _as_device(d) if d.type == "cuda" else d
         self.embed_dim = arch.hidden_size
-        self.engine = SiglipEngine(arch, self.device.index, max_batch)
-        sd = state_dict if state_dict is not None else random_vision_state_dict(arch, seed, device=self.device)
-        self.engine.load_state_dict(sd)
         self.resize_mode = ops.RESIZE_NONE
+        self.visual = _Holder()
+        self.visual.trunk = _timm_trunk(arch)
+        self.visual.image_size = (arch.image_size, arch.image_size)
+        self.text = _TextSink()
+        self.to_empty(device=self._device)
+        self.engine = (SiglipEngine(arch, self._device.index, max_batch, fuse_ln=fuse_ln)
+                       if self._device.type == "cuda" else None)
+        self._synced = None                 # parameter-version fingerprint the engine's packed copy corresponds to
+        self.weights_source = "random"      # "random" until real tensors arrive through load_state_dict
+        self._warned_random = False
+        src = state_dict if state_dict is not None else random_vision_state_dict(arch, seed, device=self._device)
+        canon = canonicalize_state_dict(src)
+        own = timm_state_from_canonical(canon)
+        with torch.no_grad():
+            params = dict(self.named_parameters())
+            for k, v in own.items():
+                params[k].copy_(v.to(self._device, torch.float32).reshape(params[k].shape))
+        if state_dict is not None:
+            self.weights_source = "state_dict"
+        self.register_load_state_dict_post_hook(VisionTower._after_load)
 
+    # ---- state dict plumbing -------------------------------------------------------------------------------------
+    _IGNORED_TOP = ("logit_scale", "logit_bias")
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        # the tower itself owns no tensors; open_clip's scalar `logit_scale` / `logit_bias` are accepted and dropped, and
+        # HF-layout keys (`vision_model.*`) are translated so either checkpoint flavour loads through the same path
+        hf = {k[len(prefix):]: v for k, v in state_dict.items()
+              if k.startswith(prefix + "vision_model.") or k.startswith(prefix + "visual.vision_model.")}
+        if hf:
+            own = timm_state_from_canonical(canonicalize_state_dict(hf))
+            for k in list(state_dict.keys()):
+                if k.startswith(prefix + "vision_model.") or k.startswith(prefix + "visual.vision_model."):
+                    del state_dict[k]
+            for k, v in own.items():
+                state_dict[prefix + k] = v
+        if strict:
+            for key in state_dict.keys():
+                if key.startswith(prefix):
+                    head = key[len(prefix):].split(".", 1)[0]
+                    if head not in ("visual", "text") and head not in self._IGNORED_TOP:
+                        unexpected_keys.append(key)
+
+    @staticmethod
+    def _after_load(module, incompatible_keys):
+        missing = [k for k in incompatible_keys.missing_keys if "visual.trunk." in k]
+        total = sum(1 for _ in module.visual.trunk.parameters())
+        if len(missing) < total:   # at least part of the backbone arrived
+            module.weights_source = "checkpoint" if not missing else "checkpoint (partial)"
+            if missing:
+                warnings.warn(f"dfd: {len(missing)} of {total} backbone tensors were not in the checkpoint and keep their "
+                              f"previous values (first: {missing[0]})", stacklevel=2)
+        module._synced = None
+
+    def _fingerprint(self):
+        ps = list(self.visual.trunk.parameters())
+        try:
+            vers = tuple(p._version for p in ps)
+        except RuntimeError:   # inference tensors carry no version counter: storage identity only
+            vers = ()
+        return vers + tuple(p.data_ptr() for p in ps)
+
+    def sync_engine(self, force: bool = False) -> None:
+        """Repack the registered parameters into the engine if they changed since the last forward."""
+        if self.engine is None:
+            raise RuntimeError("dfd: the vision tower was created without a CUDA device; the backbone has no CPU fallback")
+        fp = self._fingerprint()
+        if force or fp != self._synced:
+            sd = {"visual.trunk." + k: v.detach() for k, v in self.visual.trunk.named_parameters()}
+            self.engine.load_state_dict(sd)
+            self._synced = fp
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        p = next(self.visual.trunk.parameters(), None)
+        if p is not None and p.device != self._device and self.engine is not None:
+            raise RuntimeError(f"dfd: the vision tower lives on {self._device}; moving it to {p.device} is not supported "
+                               "(the engine's workspace and packed weights stay on the device it was created on)")
+        self._synced = None
+        return out
+
+    # ---- forward -------------------------------------------------------------------------------------------------
+    @torch.compiler.disable
     def encode_image(self, x: torch.Tensor, normalize: bool = False) -> torch.Tensor:
-        """x: float32 [B,3,H,W] normalised to [-1,1] (or uint8 [B,H,W,3]) -> float32 [B,D] pooled embeddings."""
-        x = x.to(self.device, non_blocking=True)
-        if x.dtype in (torch.float16, torch.bfloat16, torch.float64):
+        """x: float [B,3,H,W] normalised to [-1,1] (or uint8 [B,H,W,3]) -> [B,D] pooled embeddings; fp32, or the autocast
+        dtype when called under torch.autocast (as open_clip's module would return)."""
+        if self.weights_source == "random" and not self._warned_random:
+            warnings.warn("dfd: this vision tower still carries seeded RANDOM weights - no pretrained checkpoint is "
+                          "reachable offline and no backbone tensors were loaded; embeddings are meaningless until "
+                          "load_state_dict() delivers `visual.trunk.*` (or `backbone.*`) tensors", stacklevel=2)
+            self._warned_random = True
+        self.sync_engine()
+        out_dtype = torch.float32
+        if torch.is_autocast_enabled("cuda"):
+            out_dtype = torch.get_autocast_dtype("cuda")
+        x = x.to(self._device, non_blocking=True)
+        if x.dtype != torch.uint8 and x.dtype != torch.float32:
             x = x.float()
-        mode = self.resize_mode
+        mode = self.resize_mode & 0xF
+        flip = self.resize_mode & ops.FLIP_H
         hw = x.shape[1:3] if x.dtype == torch.uint8 else x.shape[2:4]
         gp, P = self.arch.grid * self.arch.patch_size, self.arch.patch_size
         if not all(gp <= s < gp + P for s in hw) and mode == ops.RESIZE_NONE:
             mode = ops.RESIZE_BILINEAR
-        pooled, _ = self.engine(x, resize_mode=mode)
+        with torch.cuda.device(self._device):
+            pooled, _ = self.engine(x, resize_mode=mode | flip)
         f = pooled.float()
-        return f / f.norm(dim=-1, keepdim=True) if normalize else f
+        if normalize:
+            f = f / f.norm(dim=-1, keepdim=True)
+        return f.to(out_dtype)
 
-    def load_state_dict(self, sd: dict, strict: bool = False):
-        canon = canonicalize_state_dict(sd)
-        if canon:
-            self.engine.load_state_dict(sd)
-        elif strict:
-            raise RuntimeError("no vision-tower tensors in the state dict")
-        return self
+    def forward(self, image: torch.Tensor, text=None):
+        if text is not None:
+            raise NotImplementedError("dfd: only the vision tower of the SigLIP model is built (the reference never calls the text tower)")
+        return self.encode_image(image)
 
-    def eval(self):
-        return self
-
-    def train(self, mode: bool = True):
-        return self
-
-    def to(self, *a, **k):
-        return self
-
-    def parameters(self) -> Iterable[torch.Tensor]:
-        return iter(())
-
-    def named_parameters(self):
-        return iter(())
-
-    __call__ = encode_image
+    @property
+    def device(self) -> torch.device:
+        return self._device
 
 
 def create_model_and_transforms(model_name: str, pretrained: Optional[str] = None, device="cuda", max_batch: int = 64,
                                 state_dict: Optional[dict] = None, **_):
-    """open_clip-shaped factory.  No pretrained weights are reachable offline: unless `state_dict` is given the
-    tower gets seeded random weights of the named architecture (`pretrained` is accepted and ignored)."""
+    """open_clip-shaped factory.  `pretrained` may be a local checkpoint path (.safetensors / .pt / .bin with open_clip
+    or HF vision-tower keys); tags such as 'webli' cannot be resolved offline: the tower then keeps seeded random
+    weights of the named architecture and says so (warning here, and once more on the first forward unless a
+    checkpoint has been loaded through load_state_dict by then, which is what the reference scripts do next)."""
     if model_name not in ARCHS:
         raise KeyError(f"unknown model '{model_name}'; known: {sorted(ARCHS)}")
     arch = ARCHS[model_name]
+    if state_dict is None and pretrained and os.path.exists(str(pretrained)):
+        state_dict = _load_checkpoint_file(str(pretrained))
+    elif state_dict is None and pretrained:
+        warnings.warn(f"dfd: pretrained='{pretrained}' cannot be downloaded here; '{model_name}' starts from seeded random "
+                      "weights until a checkpoint is loaded", stacklevel=2)
     model = VisionTower(arch, device, max_batch=max_batch, state_dict=state_dict)
     return model, None, make_preprocess(arch.image_size)
+
+
+def _load_checkpoint_file(path: str) -> dict:
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+
+        return load_file(path)
+    ck = torch.load(path, map_location="cpu", weights_only=True)
+    for k in ("model_state_dict", "model_state", "state_dict", "model"):
+        if isinstance(ck, dict) and k in ck and isinstance(ck[k], dict):
+            return ck[k]
+    return ck
 
 
 class _Head:
@@ -145,6 +353,7 @@ class BinaryClassifier:
         self.head_kind = head
         self._head_state = {k: v.clone() for k, v in random_classifier_head(head, self.arch.hidden_size, seed + 1).items()}
         self._params = None
+        self.tta_flags = 0   # ops.FLIP_H: the forward reads every image mirrored (run_tta_inference's "H-Flip" pass)
         if head == "B":
             self.backbone.resize_mode = ops.RESIZE_NEAREST  # F.interpolate default (train_fusion_head_only.py:103-104)
 
@@ -177,22 +386,25 @@ class BinaryClassifier:
         engine, `classifier.*` / `se.*` to the head.  Non-strict loading drops shape mismatches like
         train_fusion_head_only.py:111-123."""
         sd = {k[len("_orig_mod."):] if k.startswith("_orig_mod.") else k: v for k, v in sd.items()}
-        missing, loaded = [], 0
+        missing, unexpected = [], []
         for k in self._head_state:
             if k in sd and tuple(sd[k].shape) == tuple(self._head_state[k].shape):
                 self._head_state[k] = sd[k].detach().float().cpu().clone()
-                loaded += 1
             else:
                 missing.append(k)
-        bb = {k: v for k, v in sd.items() if k.startswith("backbone.") and not k.startswith("backbone.text.")}
+        bb = {k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}
         if bb:
-            self.backbone.load_state_dict(bb)
-        elif strict:
-            missing.append("backbone.*")
-        if strict and missing:
-            raise RuntimeError(f"missing keys: {missing}")
+            r = self.backbone.load_state_dict(bb, strict=False)
+            missing += ["backbone." + k for k in r.missing_keys]
+            unexpected += ["backbone." + k for k in r.unexpected_keys]
+        else:
+            missing += ["backbone." + k for k, _ in self.backbone.named_parameters()]
+        unexpected += [k for k in sd if not k.startswith("backbone.") and k not in self._head_state]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict: missing keys {missing[:8]}{'...' if len(missing) > 8 else ''}, "
+                               f"unexpected keys {unexpected[:8]}{'...' if len(unexpected) > 8 else ''}")
         self._params = None
-        return types.SimpleNamespace(missing_keys=missing, unexpected_keys=[])
+        return _IncompatibleKeys(missing, unexpected)
 
     def _head(self):
         if self._params is None:
@@ -207,8 +419,10 @@ class BinaryClassifier:
         mode = ops.RESIZE_NONE
         gp, P = self.arch.grid * self.arch.patch_size, self.arch.patch_size
         if not all(gp <= s < gp + P for s in hw):
-            mode = self.backbone.resize_mode or ops.RESIZE_BILINEAR
-        return self.backbone.engine(x, resize_mode=mode)[0]
+            mode = (self.backbone.resize_mode & 0xF) or ops.RESIZE_BILINEAR
+        self.backbone.sync_engine()
+        with torch.cuda.device(self.device):
+            return self.backbone.engine(x, resize_mode=mode | (self.tta_flags & ops.FLIP_H))[0]
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return ops.head_fwd(self._head(), self._pooled(x))[1]
@@ -254,13 +468,17 @@ class FastBinaryClassifier(BinaryClassifier):
                 if k.startswith(("layer_norm.", "attention.", "classifier."))}
         if head:
             self._head_state = head
-        bb = {k: v for k, v in sd.items() if k.startswith("backbone.") and not k.startswith("backbone.text.")}
+        bb = {k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}
+        missing, unexpected = [], []
         if bb:
-            self.backbone.load_state_dict(bb)
-        if strict and (not head or not bb):
-            raise RuntimeError("missing keys: " + ("head " if not head else "") + ("backbone.*" if not bb else ""))
+            r = self.backbone.load_state_dict(bb, strict=False)
+            missing += ["backbone." + k for k in r.missing_keys]
+            unexpected += ["backbone." + k for k in r.unexpected_keys]
+        if strict and (not head or not bb or missing or unexpected):
+            raise RuntimeError("Error(s) in loading state_dict: " + ("no head tensors; " if not head else "") +
+                               ("no backbone.* tensors; " if not bb else "") + f"missing {missing[:8]} unexpected {unexpected[:8]}")
         self._params = None
-        return types.SimpleNamespace(missing_keys=[], unexpected_keys=[])
+        return _IncompatibleKeys(missing, unexpected)
 
 
 @torch.no_grad()
@@ -279,6 +497,129 @@ def run_inference(model: BinaryClassifier, dataloader, device=None, use_amp: boo
         all_labels.extend(np.asarray(labels))
         all_files.extend(filenames)
     return np.array(all_labels), np.array(all_probs), all_files
+
+
+class AIHumanDataset(torch.utils.data.Dataset):
+    """(image, label, filename) triples from a metadata CSV with `file_name` (path relative to data_dir) and `label`
+    (0 real / 1 fake) columns - inference_ai_human_images.py:155-192.  Rows whose file does not exist are dropped."""
+
+    def __init__(self, data_dir, metadata_csv, transform=None, max_samples: Optional[int] = None):
+        import pandas as pd
+
+        self.transform = transform
+        df = pd.read_csv(metadata_csv)
+        self.samples = [(os.path.join(str(data_dir), str(f)), int(lab), str(f))
+                        for f, lab in zip(df["file_name"], df["label"]) if os.path.exists(os.path.join(str(data_dir), str(f)))]
+        if max_samples and len(self.samples) > max_samples:
+            keep = np.random.choice(len(self.samples), max_samples, replace=False)
+            self.samples = [self.samples[i] for i in keep]
+
+    def __len__(self):
+        return len(self.samples)
+
+    def __getitem__(self, i):
+        from PIL import Image
+
+        path, label, name = self.samples[i]
+        try:
+            img = Image.open(path).convert("RGB")
+        except Exception:   # unreadable file -> black image, as the reference's loader does (:77-80)
+            img = Image.new("RGB", (384, 384), color="black")
+        return (self.transform(img) if self.transform else img), label, name
+
+
+def _clahe_lab(pil):
+    """CLAHE(2.0, 8x8) on the L channel of LAB (inference_ai_human_images.py:83-97)."""
+    import cv2
+    from PIL import Image
+
+    img = np.array(pil)
+    cl = cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8))
+    if img.ndim == 3:
+        lab = cv2.cvtColor(img, cv2.COLOR_RGB2LAB)
+        lab[:, :, 0] = cl.apply(lab[:, :, 0])
+        img = cv2.cvtColor(lab, cv2.COLOR_LAB2RGB)
+    else:
+        img = cl.apply(img)
+    return Image.fromarray(img)
+
+
+def _sharpen(pil):
+    """ImageFilter.SHARPEN then Sharpness x1.5 (inference_ai_human_images.py:100-108)."""
+    from PIL import ImageEnhance, ImageFilter
+
+    return ImageEnhance.Sharpness(pil.filter(ImageFilter.SHARPEN)).enhance(1.5)
+
+
+TTA_NAMES = ("Original", "H-Flip", "CLAHE", "Sharpen", "CLAHE+Sharpen")
+
+
+def create_tta_transforms(image_size: int, num_augments: int = 5):
+    """[(name, transform)] in the reference's order (inference_ai_human_images.py:195-247): Resize((S,S)) [+ H-flip |
+    CLAHE | sharpen | both] + ToTensor + Normalize(.5,.5).  Host-side PIL transforms, exactly like the reference; the
+    first two are also available without a second decode/upload through `run_tta_inference` (DFD_FLIP_H pass)."""
+    from torchvision import transforms
+
+    def make(extra):
+        return transforms.Compose([transforms.Resize((image_size, image_size))] + extra +
+                                  [transforms.ToTensor(), transforms.Normalize([0.5] * 3, [0.5] * 3)])
+
+    extras = [[], [transforms.RandomHorizontalFlip(p=1.0)], [transforms.Lambda(_clahe_lab)], [transforms.Lambda(_sharpen)],
+              [transforms.Lambda(lambda im: _sharpen(_clahe_lab(im)))]]
+    return [(TTA_NAMES[i], make(extras[i])) for i in range(max(1, min(num_augments, 5)))]
+
+
+def run_tta_inference(model, data_dir, metadata_csv, tta_transforms, batch_size, num_workers=0, device=None,
+                      use_amp: bool = True, invert_logits: bool = False, prototypes: Optional[dict] = None):
+    """inference_ai_human_images.py:321-360: one pass per TTA transform, probabilities averaged.
+    Returns (y_true, mean probabilities, [per-transform probabilities], filenames).
+
+    The reference decodes, resizes and uploads the dataset once per transform.  For the default configuration
+    (NUM_TTA_AUGMENTS = 2: "Original" + "H-Flip", :731-732) and a dfd BinaryClassifier the mirrored view is produced by
+    the patch kernel from the pixels that are already resident (DFD_FLIP_H), so both views cost one decode and one
+    upload per image; the remaining transforms (CLAHE / sharpen, host PIL ops in the reference too) run as extra passes."""
+    from torch.utils.data import DataLoader
+
+    names = [n for n, _ in tta_transforms]
+    fused = (isinstance(model, BinaryClassifier) and len(names) >= 2 and names[0] == "Original" and names[1] == "H-Flip")
+    all_probs, y_true, filenames = [], None, None
+
+    def loader(tf):
+        ds = AIHumanDataset(data_dir, metadata_csv, transform=tf)
+        return DataLoader(ds, batch_size=batch_size, shuffle=False, num_workers=num_workers,
+                          pin_memory=torch.cuda.is_available(), persistent_workers=False)
+
+    start = 0
+    if fused:
+        labs, p0, p1, files = [], [], [], []
+        with torch.no_grad():
+            for images, labels, fn in loader(tta_transforms[0][1]):
+                images = images.to(model.device, non_blocking=True)
+                for flags, acc in ((0, p0), (ops.FLIP_H, p1)):
+                    model.tta_flags = flags
+                    try:
+                        if prototypes is not None:
+                            pr = model.prototype_probs(images, prototypes)
+                        else:
+                            z = model(images)
+                            pr = torch.sigmoid(-z if invert_logits else z)
+                    finally:
+                        model.tta_flags = 0
+                    acc.extend(pr.cpu().numpy())
+                labs.extend(np.asarray(labels))
+                files.extend(fn)
+        y_true, filenames = np.array(labs), files
+        all_probs += [np.array(p0), np.array(p1)]
+        start = 2
+    for name, tf in tta_transforms[start:]:
+        labels, probs, fnames = run_inference(model, loader(tf), device, use_amp, desc=f"  {name}",
+                                              invert_logits=invert_logits, prototypes=prototypes)
+        if y_true is None:
+            y_true, filenames = labels, fnames
+        else:
+            assert np.array_equal(y_true, labels), "Labels mismatch across TTA!"
+        all_probs.append(probs)
+    return y_true, np.mean(all_probs, axis=0), all_probs, filenames
 
 
 @torch.no_grad()

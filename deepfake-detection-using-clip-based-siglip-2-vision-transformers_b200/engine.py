@@ -149,8 +149,8 @@ class SiglipEngine:
         self.arch = arch
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         self.max_batch = int(max_batch)
-        # fuse_ln: LayerNorm1/2 folded into the qkv / fc1 GEMMs (row statistics accumulated by the GEMM that wrote
-        # the residual stream, with fp32 atomics — results then differ run to run in the last bf16 bit)
+        # fuse_ln: LayerNorm1/2 folded into the qkv / fc1 GEMMs; the row statistics are left by the GEMM that wrote the
+        # residual stream as per-64-column partial sums and added in a fixed order (no atomics: bit-reproducible)
         self.fuse_ln = bool(fuse_ln)
         self._lib = _lib.load()
         cfg = EngineConfig(arch.image_size, arch.patch_size, arch.hidden_size, arch.intermediate_size,
@@ -231,12 +231,16 @@ class SiglipEngine:
         pooled = torch.empty((B, a.hidden_size), dtype=torch.bfloat16, device=self.device)
         last = (torch.empty((B, a.tokens, a.hidden_size), dtype=torch.bfloat16, device=self.device)
                 if want_last_hidden else None)
-        st = current_stream()
-        for b0 in range(0, B, self.max_batch):
-            nb = min(self.max_batch, B - b0)
-            check(self._lib.dfd_engine_forward(self._h, pixels[b0:b0 + nb].data_ptr(), fmt, nb, Hin, Win, resize_mode,
-                                               pooled[b0:b0 + nb].data_ptr(),
-                                               None if last is None else last[b0:b0 + nb].data_ptr(), st))
+        if pixels.device != self.device:
+            raise RuntimeError(f"pixels live on {pixels.device}, this engine on {self.device}")
+        # launch on THIS engine's device and on its current stream, whatever device the caller has selected
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            for b0 in range(0, B, self.max_batch):
+                nb = min(self.max_batch, B - b0)
+                check(self._lib.dfd_engine_forward(self._h, pixels[b0:b0 + nb].data_ptr(), fmt, nb, Hin, Win, resize_mode,
+                                                   pooled[b0:b0 + nb].data_ptr(),
+                                                   None if last is None else last[b0:b0 + nb].data_ptr(), st))
         return pooled, last
 
     __call__ = forward

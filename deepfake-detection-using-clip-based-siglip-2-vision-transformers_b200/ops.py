@@ -30,7 +30,9 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = 0, pos=
               ln_rowstats=None, ln_colsum=None, ln_dim: int = 0, ln_eps: float = 1e-6, stats_out=None,
               out: Optional[torch.Tensor] = None, tile_n: int = 0, residual_op: int = 0) -> torch.Tensor:
     """out[M,N] = epilogue(a[M,K] @ w[N,K].T); bf16 in/out, fp32 accumulate in TMEM (dfd_gemm_bf16).
-    act: 0 none, 1 gelu_tanh, 2 gelu_erf, 3 sigmoid; residual_op: 0 add, 1 multiply."""
+    act: 0 none, 1 gelu_tanh, 2 gelu_erf, 3 sigmoid; residual_op: 0 add, 1 multiply.
+    stats_out: fp32 [ceil(N/64), M, 2] per-chunk (sum, sum of squares) of the bf16 output rows (written, not
+    accumulated); ln_rowstats: fp32 [M, 2] (rowstats_bf16) or [parts, M, 2] partials (a previous GEMM's stats_out)."""
     _need_cuda(a, w, bias, pos, residual, out)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
@@ -52,6 +54,13 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = 0, pos=
     epi.ln_eps = ln_eps
     epi.stats_out = _p(stats_out)
     epi.residual_op = residual_op
+    epi.ln_parts = 0
+    if ln_rowstats is not None:
+        assert ln_rowstats.dtype == torch.float32 and ln_rowstats.is_contiguous() and ln_rowstats.shape[-2:] == (M, 2)
+        epi.ln_parts = ln_rowstats.shape[0] if ln_rowstats.dim() == 3 else 1
+    if stats_out is not None:
+        assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and \
+            tuple(stats_out.shape) == ((N + 63) // 64, M, 2)
     lib = _lib.load()
     if tile_n:
         rc = lib.dfd_gemm_bf16_tile(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
@@ -113,7 +122,19 @@ def map_attention_bf16(kv: torch.Tensor, q: torch.Tensor, B: int, N: int, H: int
     return out
 
 
+def gemm_last_variant() -> dict:
+    """Which kernel instantiation the last gemm_bf16 call launched: {'bn', 'cg', 'res', 'epi'} (dfd_gemm_last_variant)."""
+    v = _lib.load().dfd_gemm_last_variant()
+    return {"bn": v % 1000, "cg": v // 1000 % 10, "res": v // 10000 % 10, "epi": v // 100000}
+
+
+def gemm_variant_launches(bn: int, cg: int, res: int, epi: int) -> int:
+    """Launches of the gemm kernel instantiation <bn, cg, res, epi> by this process so far."""
+    return int(_lib.load().dfd_gemm_variant_launches(bn + 1000 * cg + 10000 * res + 100000 * epi))
+
+
 RESIZE_NONE, RESIZE_NEAREST, RESIZE_BILINEAR = 0, 1, 2
+FLIP_H = 0x10   # or-ed into resize_mode: the source images are read mirrored left-right (DFD_FLIP_H)
 
 
 def patchify(pixels: torch.Tensor, S: int, P: int, resize_mode: int = RESIZE_NONE, lda: Optional[int] = None) -> torch.Tensor:

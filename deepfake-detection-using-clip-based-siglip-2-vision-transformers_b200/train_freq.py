@@ -92,10 +92,13 @@ class TrainableFreqMLP:
     def loss_and_grad(self, feats, y, global_batch: Optional[int] = None, train: bool = True):
         """(mean BCE-with-logits over the GLOBAL batch, d loss / d flat params), all-reduced over ranks."""
         n = global_batch if global_batch is not None else feats.shape[0]
+        self._step += 1     # on every rank, also on one with an empty shard: the dropout streams stay aligned by step
         if feats.shape[0] > 0:
-            self._step += 1
+            # the kernel hashes (seed, LOCAL sample index, block, feature): fold the rank into the seed so that sample i of
+            # every rank's shard does not share one dropout mask (the reference drops every sample independently)
+            seed = (self._step * 2654435761 + distributed.rank() * 0x85EBCA6B) & 0xFFFFFFFF
             loss, grads, _ = ops.freqmlp_fwd_bwd(self.flat.data, self.mean, self.std, feats.contiguous(), y.contiguous(),
-                                                 1.0 / n, self.dropout if train else 0.0, seed=self._step * 2654435761)
+                                                 1.0 / n, self.dropout if train else 0.0, seed=seed)
         else:  # a rank may own an empty shard of a ragged last mini-batch
             loss = torch.zeros(1, device=self.device)
             grads = torch.zeros(ops.FREQMLP_NUM_PARAMS, device=self.device)

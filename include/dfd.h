@@ -62,7 +62,11 @@ DFD_API int64_t dfd_launch_count(void);
  *                                                     Siglip2sidafrozen.py:704-722)
  *   if (pos)      v += pos[(m % pos_rows)·N + n]   HF:modeling_siglip.py:179-185 (position embedding)
  *   if (residual) v += residual[m·ldr + n]     HF:modeling_siglip.py:354,359 (residual adds)
- *   C[m·ldc + n] = bf16(v);  if (stats_out) stats_out[m] += (Σ_n bf16(v), Σ_n bf16(v)²)  (atomics)
+ *   C[m·ldc + n] = bf16(v)
+ *   if (stats_out) stats_out[c][m] = (Σ bf16(v), Σ bf16(v)²) over the columns [64c, 64c+64) of row m — one partial per
+ *                  64-column chunk, layout [ceil(N/64)][M][2] fp32, every slot written exactly once (no atomics, no
+ *                  zero-fill needed); a consumer GEMM reads them back through ln_rowstats with ln_parts = ceil(N/64)
+ *                  and adds them in chunk order, so the LayerNorm-folded path is bit-reproducible
  */
 typedef struct dfd_gemm_epilogue {
   const float* bias;         /* [N] fp32 or NULL */
@@ -71,12 +75,13 @@ typedef struct dfd_gemm_epilogue {
   int pos_rows;
   const void* residual;      /* bf16 [M, ldr] or NULL; may alias C */
   int64_t ldr;
-  const float* ln_rowstats;  /* [M,2] fp32 (Σx, Σx²) or NULL */
+  const float* ln_rowstats;  /* [ln_parts][M][2] fp32 partial (Σx, Σx²) per row, or NULL */
   const float* ln_colsum;    /* [N] fp32 */
   int ln_dim;
   float ln_eps;
-  float* stats_out;          /* [M,2] fp32, accumulated atomically, or NULL */
+  float* stats_out;          /* [ceil(N/64)][M][2] fp32 partials (see above), or NULL */
   int residual_op;           /* 0: v += residual (default), 1: v *= residual (gating: Siglip2sidafrozen.py:737) */
+  int ln_parts;              /* partial pairs per row in ln_rowstats; 0 or 1 = plain [M,2] (dfd_rowstats_bf16) */
 } dfd_gemm_epilogue;
 
 /* C[M,N] (bf16) = epi(A[M,K] (bf16, lda) · W[N,K]ᵀ (bf16, ldw)), fp32 accumulate in TMEM.
@@ -91,6 +96,13 @@ DFD_API int dfd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw
  * work unit `unit` of `units` (CTAs or CTA pairs) processes in round `round`, or -1 if it has none.  Each round covers `units`
  * consecutive tiles, rotated between rounds so that every unit cycles through all n-tiles (gemm_tcgen05.cu: sched_rotation). */
 DFD_API int dfd_gemm_schedule(int num_tiles, int num_n, int units, int unit, int round);
+/* Test / audit hooks: which kernel instantiation the last dfd_gemm_bf16[_tile] call of this process launched, encoded
+ * as tile_n + 1000·CTAs-per-tile + 10000·has_residual + 100000·EPI (EPI: 0 generic, 1 LN fold + bias, 2 LN fold + bias +
+ * tanh-GELU, 3 bias + residual + row statistics, 4 bias + residual, 5 bias, 6 bias + tanh-GELU), and how often a given
+ * instantiation has been launched since load (-1: no such kernel).  The parity tests use them to prove that the
+ * specialised kernels bench.py times are the ones being compared with the oracle. */
+DFD_API int dfd_gemm_last_variant(void);
+DFD_API int64_t dfd_gemm_variant_launches(int variant);
 
 /* y[M,D] (bf16) = LayerNorm(x[M,D] (bf16)) · gamma + beta, fp32 statistics, eps as given.
  * HF:modeling_siglip.py:348,357 (layer_norm1/2), :618 (post_layernorm). */
@@ -116,7 +128,10 @@ DFD_API int dfd_attention_bf16_impl(const void* qkv, int64_t ldqkv, void* out, i
  * source to S×S first (resize_mode: 0 none (Hin==S), 1 nearest — train_fusion_head_only.py:103-104,
  * 2 bilinear align_corners=False — cifake_binary_classifier.py:716-717).  Only pixels
  * [0, G·P) of each axis are read (conv padding='valid': HF:modeling_siglip.py:124-130).
+ * resize_mode | DFD_FLIP_H reads every source image mirrored left-right first (RandomHorizontalFlip(p=1) of the TTA
+ * "H-Flip" transform, inference_ai_human_images.py:207-214): the second TTA pass re-uses the resident pixels.
  * pix_format: 0 = u8 NHWC [B,Hin,Win,3]; 1 = f32 NCHW [B,3,Hin,Win] already normalised. */
+#define DFD_FLIP_H 0x10
 DFD_API int dfd_patchify(const void* pixels, int pix_format, int B, int Hin, int Win, int S, int P,
                          int resize_mode, void* A, int64_t lda, void* stream);
 

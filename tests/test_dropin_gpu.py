@@ -414,3 +414,197 @@ def test_siglip2_mtl_end_to_end():
     scale = float(seg_ref.abs().max())
     assert (seg.cpu() - seg_ref).abs().max() < 0.03 * max(scale, 0.3), ((seg.cpu() - seg_ref).abs().max(), scale)
     assert np.corrcoef(seg.cpu().numpy().ravel(), seg_ref.numpy().ravel())[0, 1] > 0.999
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's own flow on the GPU.  /root/reference does not exist on the GPU box, so the two model classes are
+# restated here the way the reference declares them (same submodule names, same forward; the source-extracted originals
+# run against the same shims in tests/test_dropin_cpu.py) and driven like its entry points drive them.
+# ---------------------------------------------------------------------------------------------------------------------
+def _reference_style_classifier(kind, arch_name, dim, img_size):
+    """kind 'A': inference_ai_human_images.py:111-152; kind 'B': train_fusion_head_only.py:78-109."""
+    import open_clip  # the dfd stand-in (install_import_shims)
+    import torch.nn as nn
+
+    class BinaryClassifierA(nn.Module):
+        def __init__(self, device):
+            super().__init__()
+            self.resolution = img_size
+            self.backbone, _, self.preprocess = open_clip.create_model_and_transforms(arch_name, pretrained="webli", device=device)
+            self.classifier = nn.Sequential(nn.LayerNorm(dim), nn.Dropout(0.3), nn.Linear(dim, dim // 2), nn.GELU(),
+                                            nn.Dropout(0.2), nn.Linear(dim // 2, 1))
+
+        def forward(self, x):
+            features = self.backbone.encode_image(x)
+            features = features / features.norm(dim=-1, keepdim=True)
+            return self.classifier(features).squeeze(-1)
+
+    class BinaryClassifierB(nn.Module):
+        def __init__(self, device):
+            super().__init__()
+            self.backbone, _, _ = open_clip.create_model_and_transforms(arch_name, pretrained="webli", device=device)
+            self.se = nn.Sequential(nn.Linear(dim, dim // 16), nn.ReLU(), nn.Linear(dim // 16, dim), nn.Sigmoid())
+            self.classifier = nn.Sequential(nn.LayerNorm(dim), nn.Dropout(0.3), nn.Linear(dim, dim // 2), nn.GELU(),
+                                            nn.Dropout(0.2), nn.Linear(dim // 2, dim // 4), nn.GELU(), nn.Linear(dim // 4, 1))
+
+        def forward(self, x):
+            with torch.no_grad():
+                if x.shape[-1] != img_size:
+                    x = nn.functional.interpolate(x, size=(img_size, img_size))
+                f = self.backbone.encode_image(x)
+                f = f / (f.norm(dim=-1, keepdim=True) + 1e-6)
+            return self.classifier(f * self.se(f)).squeeze(-1)
+
+    return BinaryClassifierA if kind == "A" else BinaryClassifierB
+
+
+def _timm_checkpoint(sd, hs):
+    """`best_model` checkpoint as the reference's trainers write it: open_clip/timm backbone names + head + text tower."""
+    from dfd import dropin
+    from dfd.engine import canonicalize_state_dict
+
+    ck = {"backbone." + k: v.clone() for k, v in dropin.timm_state_from_canonical(canonicalize_state_dict(sd)).items()}
+    ck.update({k: v.clone() for k, v in hs.items()})
+    ck["backbone.logit_scale"], ck["backbone.logit_bias"] = torch.tensor(2.3), torch.tensor(-10.0)
+    ck["backbone.text.token_embedding.weight"] = torch.zeros(4, 8)
+    return ck
+
+
+@pytest.mark.parametrize("kind,eps", [("A", 0.0), ("B", 1e-6)])
+def test_reference_style_module_strict_load_inference_mode_autocast(kind, eps):
+    """Entry-point flow of inference_ai_human_images.py (:836-857 load, :265-309 loop) / train_fusion_head_only.py
+    (:118-124, :339-347): nn.Module that owns the tower as `self.backbone`, strict load of a timm-named checkpoint,
+    `inference_mode()` + `autocast()`, sigmoid, `.cpu()`.  The logits must match the oracle ON THE CHECKPOINT'S weights
+    (and be far from what the tower's initial random weights give)."""
+    import warnings
+
+    from dfd import dropin
+    from oracle import siglip_ref as R
+
+    dropin.install_import_shims()
+    name = "small-hd72"
+    c = R.CONFIGS[name]
+    sd, hs = R.init_state_dict(c, 0), R.init_head(kind, c.hidden_size, 1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = _reference_style_classifier(kind, name, c.hidden_size, c.image_size)(DEV).to(DEV)
+    assert model.backbone.weights_source == "random"
+    x = R.preprocess_u8(R.synthetic_images(6, c.image_size, 3))
+    model.eval()
+    with torch.inference_mode(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        z_random = model(x.to(DEV)).float().cpu()
+    model.load_state_dict(_timm_checkpoint(sd, hs), strict=True)
+    assert model.backbone.weights_source == "checkpoint"
+    with torch.inference_mode():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            f = model.backbone.encode_image(x.to(DEV))
+            assert f.dtype == torch.bfloat16           # the tower honours the autocast dtype like a torch module would
+            z = model(x.to(DEV))
+        probs = torch.sigmoid(z).float().cpu().numpy()
+        assert model.backbone.encode_image(x.to(DEV)).dtype == torch.float32
+    pooled = R.siglip_vision_forward(sd, c, x, "fp32")["pooler_output"]
+    z_ref = R.classifier_head(hs, kind, pooled, eps)
+    # the head runs as torch modules under autocast here (bf16 GEMMs, as in the reference): 3e-2 on O(1) logits
+    assert (z.float().cpu() - z_ref).abs().max() < 3e-2 * max(1.0, float(z_ref.abs().max())), (z, z_ref)
+    assert np.abs(probs - torch.sigmoid(z_ref).numpy()).max() < 1e-2
+    assert (z_random - z_ref).abs().max() > 0.1, "the strict load must have replaced the random backbone"
+    # in-place parameter updates reach the engine too (version counters), not only load_state_dict
+    with torch.no_grad():
+        model.backbone.visual.trunk.pos_embed.mul_(0.0)
+    with torch.inference_mode():
+        z2 = model(x.to(DEV)).float().cpu()
+    sd2 = dict(sd)
+    sd2["embeddings.position_embedding.weight"] = torch.zeros_like(sd["embeddings.position_embedding.weight"])
+    z2_ref = R.classifier_head(hs, kind, R.siglip_vision_forward(sd2, c, x, "fp32")["pooler_output"], eps)
+    assert (z2 - z2_ref).abs().max() < 3e-2 * max(1.0, float(z2_ref.abs().max()))
+
+
+def test_reference_style_module_survives_torch_compile():
+    """inference_ai_human_images.py:868-881 wraps the model in torch.compile; the tower's forward is opaque to dynamo
+    (torch.compiler.disable) and keeps running on the dfd engine, the torch head around it is compiled."""
+    import warnings
+
+    from dfd import dropin
+    from oracle import siglip_ref as R
+
+    dropin.install_import_shims()
+    name = "tiny-hd64"
+    c = R.CONFIGS[name]
+    sd, hs = R.init_state_dict(c, 0), R.init_head("A", c.hidden_size, 1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = _reference_style_classifier("A", name, c.hidden_size, c.image_size)(DEV).to(DEV).eval()
+    model.load_state_dict(_timm_checkpoint(sd, hs), strict=True)
+    x = R.preprocess_u8(R.synthetic_images(4, c.image_size, 3)).to(DEV)
+    with torch.inference_mode():
+        z_eager = model(x).float().cpu()
+    try:
+        compiled = torch.compile(model)
+        with torch.inference_mode():
+            z_c = compiled(x).float().cpu()
+    except Exception as e:  # the box may lack a working inductor toolchain; the reference itself falls back to eager then
+        pytest.skip(f"torch.compile unavailable here: {type(e).__name__}: {str(e)[:80]}")
+    assert (z_c - z_eager).abs().max() < 1e-3, (z_c, z_eager)
+
+
+def test_run_tta_inference_fused_flip_equals_two_host_passes(tmp_path):
+    """run_tta_inference (inference_ai_human_images.py:321-360) with the default 2 transforms: the fused pass (mirrored view
+    produced by the patch kernel from the resident pixels) equals the reference's way — a second decode + host flip —
+    bit for bit, and the averaged probabilities match the oracle."""
+    from PIL import Image
+
+    from dfd import dropin
+    from oracle import siglip_ref as R
+
+    m, c, sd, hs = _bc("A")
+    rng = np.random.default_rng(5)
+    rows = []
+    for i in range(7):
+        arr = np.clip(rng.normal(128, 60, (40 + 3 * i, 50 + 2 * i, 3)), 0, 255).astype(np.uint8)
+        Image.fromarray(arr).save(os.path.join(tmp_path, f"img{i}.png"))
+        rows.append(f"img{i}.png,{i % 2}")
+    rows.append("missing.png,1")   # rows without a file are dropped (:168-169)
+    csv = os.path.join(tmp_path, "meta.csv")
+    open(csv, "w").write("file_name,label\n" + "\n".join(rows) + "\n")
+    tfs = dropin.create_tta_transforms(c.image_size, 2)
+    assert [n for n, _ in tfs] == ["Original", "H-Flip"]
+    y, p_avg, per, files = dropin.run_tta_inference(m, tmp_path, csv, tfs, batch_size=3, num_workers=0, device=torch.device(DEV))
+    assert y.tolist() == [0, 1, 0, 1, 0, 1, 0] and files[3] == "img3.png" and len(per) == 2
+    # the reference's way: one pass per transform, flip done by the host transform
+    ref_passes = []
+    for _, tf in tfs:
+        ds = dropin.AIHumanDataset(tmp_path, csv, transform=tf)
+        loader = torch.utils.data.DataLoader(ds, batch_size=3, shuffle=False)
+        ref_passes.append(dropin.run_inference(m, loader, torch.device(DEV))[1])
+    assert np.array_equal(per[0], ref_passes[0]) and np.array_equal(per[1], ref_passes[1])
+    assert np.array_equal(p_avg, np.mean(ref_passes, axis=0))
+    assert np.abs(per[0] - per[1]).max() > 1e-4      # the mirrored view really is a different input
+    # oracle on the host-transformed tensors
+    ds0 = dropin.AIHumanDataset(tmp_path, csv, transform=tfs[1][1])
+    xf = torch.stack([ds0[i][0] for i in range(len(ds0))])
+    pr = torch.sigmoid(R.classifier_head(hs, "A", R.siglip_vision_forward(sd, c, xf, "fp32")["pooler_output"], 0.0)).numpy()
+    assert np.abs(per[1] - pr).max() < 5e-3
+    # three transforms: the third (CLAHE) runs as an ordinary extra pass
+    y3, p3, per3, _ = dropin.run_tta_inference(m, tmp_path, csv, dropin.create_tta_transforms(c.image_size, 3), 4, 0, torch.device(DEV))
+    assert len(per3) == 3 and np.array_equal(per3[0], per[0]) and np.array_equal(per3[1], per[1])
+    assert np.allclose(p3, np.mean(per3, axis=0))
+
+
+@pytest.mark.parametrize("fmt", ["u8", "f32"])
+@pytest.mark.parametrize("S,P,Hin", [(64, 16, 64), (60, 14, 60), (60, 14, 37)])
+def test_patchify_flip_equals_flipped_input(fmt, S, P, Hin):
+    """DFD_FLIP_H: mirrored read of the source image == patchify of the host-flipped image, bit for bit, on the fast
+    row kernel (u8, on-grid), the generic kernel (f32) and through the in-model bilinear resample (off-grid input)."""
+    from dfd import ops
+    from oracle import siglip_ref as R
+
+    img = R.synthetic_images(3, Hin, seed=S + Hin)
+    src = img if fmt == "u8" else R.preprocess_u8(img)
+    flipped = torch.flip(src, dims=[2] if fmt == "u8" else [3]).contiguous()
+    mode = ops.RESIZE_NONE if Hin == S else ops.RESIZE_BILINEAR
+    a = ops.patchify(src.to(DEV), S, P, resize_mode=mode | ops.FLIP_H)
+    b = ops.patchify(flipped.to(DEV), S, P, resize_mode=mode)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    assert not torch.equal(a, ops.patchify(src.to(DEV), S, P, resize_mode=mode))
