@@ -16,8 +16,8 @@
 //
 //   warp 0       TMA loader: next item's Q (prefetched while the current item runs), K/V in 128-key stages (3-deep ring)
 //   warps 1, 2   MMA issuers (one elected thread each): S_t,j = Q_t·K_jᵀ, O_t += P_t,j·V_j for query tile t = warp - 1
-//   warps 3-10   softmax / output of query tile 0 (two warps per 32 rows: each handles 32 of the 64 key columns)
-//   warps 11-18  softmax / output of query tile 1
+//   warps 3-6    softmax / output of query tile 0 (one thread per row)
+//   warps 7-10   softmax / output of query tile 1
 //
 // TMEM (512 columns):  S[t][buf] fp32 128x64 at (2t+buf)·64 | O[t] fp32 128x80 at 256+80t | Q[t] bf16x2 128x40 at 416+40t
 //
@@ -25,7 +25,6 @@
 #include "dfd_common.cuh"
 
 #include <atomic>
-#include <cstdlib>
 #include <mutex>
 
 namespace dfd {
@@ -38,12 +37,13 @@ constexpr int kQ = 128;          // query rows per tile
 constexpr int kKV = 64;          // keys per S tile
 constexpr int kStageKeys = 128;  // keys per ring stage (two S tiles)
 constexpr int kStages = 3;
-constexpr int kThreads = 608;    // loader, 2 MMA warps, 2 x 8 softmax warps
+constexpr int kThreads = 352;    // loader, 2 MMA warps, 2 x 4 softmax warps
 constexpr int kTmemCols = 512;
 constexpr int kColO = 256;
 constexpr int kColQ = 416;
-
-__device__ long long g_dq_trace[64 * 16];   // DFD_ATTN_DBG & 128: clock64 stamps of CTA 0's first 64 tiles (see dfd_debug_read_trace)
+// pairs of exponentials (of 32 per row and tile) a tile issues before it hands the MUFU turn to the other tile: measured on
+// B200 at so400m shapes (64 images): 8 -> 0.253 ms, 16 -> 0.247, 24 -> 0.249, 32 (strict alternation) -> 0.277
+constexpr int kHandoff = 16;
 
 template <int HD>
 struct DqSmem {
@@ -58,8 +58,7 @@ struct DqSmem {
   static constexpr int kBarBytes = 256;
   static constexpr int kOffKV = kQBytes;
   static constexpr int kOffOut = kOffKV + kStages * kStageBytes;
-  static constexpr int kOffL = kOffOut + 2 * kOutTile;             // partial row sums exchanged between a row's two warps
-  static constexpr int kOffBar = kOffL + 2 * 2 * kQ * 4;
+  static constexpr int kOffBar = kOffOut + 2 * kOutTile;
   static constexpr int kTotal = kOffBar + kBarBytes + 1024;
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
   static_assert(kQBytes % 1024 == 0 && kStageBytes % 1024 == 0 && kOutTile % 1024 == 0, "swizzle alignment");
@@ -92,7 +91,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 template <int HD>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_dq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_constant__ CUtensorMap tmTail,
-                    const __grid_constant__ CUtensorMap tmOut, int N, int H, int n_items, float scale_log2, int dbg) {
+                    const __grid_constant__ CUtensorMap tmOut, int N, int H, int n_items, float scale_log2) {
   using S = DqSmem<HD>;
   constexpr bool kTail = S::kTail;
   extern __shared__ uint8_t smem_raw[];
@@ -101,7 +100,6 @@ attention_dq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + S::kOffKV;
   uint8_t* sOut = smem + S::kOffOut;
-  float* l_ex = reinterpret_cast<float*>(smem + S::kOffL);   // [2 tiles][2 halves][128 rows] partial row sums
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
   uint64_t* q_full = bars;                    // TMA: the item's two Q tiles are in shared memory
   uint64_t* q_copied = bars + 1;              // [2] tile t's Q is in TMEM (8 warps)
@@ -111,8 +109,8 @@ attention_dq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
   uint64_t* p_full = s_full + 4;              // [2][2] (8 warps)
   uint64_t* o_done = p_full + 4;              // [2] phase g: the g-th P·V of tile t (of this CTA) has retired
   uint64_t* o_full = o_done + 2;              // [2] phase i: the last P·V of tile t of this CTA's i-th active item has retired
-  uint64_t* ld_done = o_full + 2;             // [2 tiles][4 quadrants] both warps of a row group hold their copy of the S tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_done + 8);
+  uint64_t* turn = o_full + 2;                // [2] tile t may start its exponentials (4 warps of the other tile arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = (N + kKV - 1) / kKV;                  // S tiles (64 keys) per item
@@ -124,8 +122,8 @@ attention_dq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
     if (kTail) tma_prefetch_desc(&tmTail);
     tma_prefetch_desc(&tmOut);
     mbar_init(q_full, 1);
-    mbar_init(&q_copied[0], 8);
-    mbar_init(&q_copied[1], 8);
+    mbar_init(&q_copied[0], 4);
+    mbar_init(&q_copied[1], 4);
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&kv_full[s], 1);
@@ -134,15 +132,14 @@ attention_dq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 8);
+      mbar_init(&p_full[s], 4);
     }
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       mbar_init(&o_done[s], 1);
       mbar_init(&o_full[s], 1);
+      mbar_init(&turn[s], 4);
     }
-#pragma unroll
-    for (int s = 0; s < 8; ++s) mbar_init(&ld_done[s], 2);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -171,12 +168,11 @@ attention_dq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
         for (int jj = 0; jj < TS; ++jj) {
           const uint32_t n = st == 0 ? ku0++ : (st == 1 ? ku1++ : ku2++);
           mbar_wait(&kv_empty[st], (n & 1u) ^ 1u);
-          if ((dbg & 2) && n > 0) { mbar_arrive(&kv_full[st]); st = (st + 1 == kStages) ? 0 : st + 1; continue; }
-          mbar_expect_tx(&kv_full[st], (dbg & 32) ? 2 * S::kMain : S::kStageBytes);
+          mbar_expect_tx(&kv_full[st], S::kStageBytes);
           uint8_t* base = sKV + st * S::kStageBytes;
           tma_load_4d(&tmMain, &kv_full[st], base, 0, H + h, jj * kStageKeys, b);
           tma_load_4d(&tmMain, &kv_full[st], base + S::kMain, 0, 2 * H + h, jj * kStageKeys, b);
-          if (kTail && !(dbg & 32)) {
+          if (kTail) {
             // tail boxes = columns HD-16..HD-1, in bounds (boxes that cross the tensor edge are served slowly); the 8
             // columns they share with the main box meet zeros on the Q side and unread accumulator columns in P·V
             tma_load_4d(&tmTail, &kv_full[st], base + 2 * S::kMain, HD - 16, H + h, jj * kStageKeys, b);
@@ -217,12 +213,10 @@ attention_dq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
         const uint64_t dK = dK0 + st * kStageStep + hf * kHalfMain;
         const int valid = N - j * kKV;
         const uint32_t idesc_qk = valid >= kKV ? idesc_qk_full : umma_idesc_bf16_major(kQ, (valid + 15) & ~15, 0, 0);
-        if (!(dbg & 16)) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16_ts(tS, tQ + static_cast<uint32_t>(8 * k), dK + static_cast<uint64_t>(2 * k), idesc_qk, k != 0);
-        if (kTail && !(dbg & 4)) umma_bf16_ts(tS, tQ + 32, dKt0 + st * kStageStep + hf * kHalfTail, idesc_qk, 1u);
-        }
+        if (kTail) umma_bf16_ts(tS, tQ + 32, dKt0 + st * kStageStep + hf * kHalfTail, idesc_qk, 1u);
         umma_commit(&s_full[2 * t + sb]);
       };
       uint32_t it = 0;
@@ -255,20 +249,16 @@ attention_dq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
               const uint64_t dVt = dVt0 + st * kStageStep + hf * kHalfTail;
               const int valid = N - j * kKV;
               // ---- O (+)= P_j · V_j ----  (P written by the tile's softmax warps into the S columns)
-              const bool tr = (dbg & 128) && blockIdx.x == 0 && t == 0 && it == 0 && j < 64;
-              if (tr) g_dq_trace[j * 16 + 8] = clock64();
               mbar_wait(&p_full[2 * t + sb], pu[sb]++ & 1u);
               tc_fence_after();
-              if (tr) g_dq_trace[j * 16 + 9] = clock64();
               const uint32_t tP = tmem_base + static_cast<uint32_t>((2 * t + sb) * kKV);
-              if (dbg & 8) {
-              } else if (valid >= kKV) {
+              if (valid >= kKV) {
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                   // 16 keys per step: 16 rows x 128 B (main) / 16 rows x 32 B (tail); P: 8 packed columns per step
                   const uint32_t acc = (kk != 0) ? 1u : (j != 0 ? 1u : 0u);
                   umma_bf16_ts(tO, tP + static_cast<uint32_t>(8 * kk), dV + static_cast<uint64_t>(kk * 128), idesc_pv, acc);
-                  if (kTail && !(dbg & 4))
+                  if (kTail)
                     umma_bf16_ts(tO + 64, tP + static_cast<uint32_t>(8 * kk), dVt + static_cast<uint64_t>(kk * 32),
                                  idesc_pvt, acc);
                 }
@@ -286,10 +276,8 @@ attention_dq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
               if (j == T - 1) umma_commit(&o_full[t]);
               // this tile is done with the stage after its second half (or the item's last tile)
               if (hf == 1 || j == T - 1) umma_commit(&kv_empty[st]);
-              if (tr) g_dq_trace[j * 16 + 10] = clock64();
               // the tensor pipe executes in issue order, so S buffer sb / P_j are free for tile j+2 right here
               if (j + 2 < T) issue_qk(j + 2, (u + 2) % (2 * kStages));
-              if (tr) g_dq_trace[j * 16 + 11] = clock64();
             }
           }
         }
@@ -297,39 +285,50 @@ attention_dq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
     }
   } else {
     // ------------------------------------ softmax / output ------------------------------------
-    // 16 warps: query tile t = (warp - 3) / 8; within a tile two warps share each TMEM lane quadrant (32 rows): both
-    // read the whole 64-column S row for the row maximum, then each exponentiates, sums and packs ITS 32 columns.  Four
-    // warps per scheduler (instead of two with one thread per row) keep the MUFU unit fed while others wait on TMEM
-    // round trips; the redundant maximum costs 22 FMNMX3 per tile.
+    // 8 warps: query tile t = (warp - 3) / 4, one thread per query row (no shuffles, no shared-memory exchange).
+    //
+    // Measured on B200 (clock64 traces of this loop, profiles/r02_attention.md): per 64-key tile a warp spends ~90 cycles on
+    // the s_full wait, ~35 on the TMEM load, ~220 on the row maximum, ~850 in the exponentials (one warp can issue a
+    // MUFU.EX2 only every ~13 cycles; the unit itself takes one per 8) and ~70 on the P store + arrive.  Left alone, the two
+    // tiles' warps on a scheduler drift into lock step: both exponentiate (sharing the MUFU unit, ~1050 cycles), then both
+    // sit in their TMEM round trips with the unit idle - 1650 cycles per 64-key step.  So the exponential phases take turns:
+    // two mbarriers hand a token back and forth between the tiles (a warpgroup ping-pong), each tile's loads, maxima,
+    // stores and barrier traffic run under the other tile's exponentials; the token is passed after HALF of a tile's
+    // exponentials (kHandoff), so the tail of one tile's MUFU stream is interleaved with the head of the other's: ~1400
+    // cycles per step, 635 TFLOP/s at so400m shapes (557 without turns), 298 at base-224 (SDPA: 657 / 281).  (mbarriers, not named
+    // barriers: bar.sync / bar.arrive sit in the same basic block as the exponentials and ptxas moved all 64 MUFU.EX2 above
+    // the bar.sync - the turn then orders nothing; the wait loop and the one-lane arrive are control flow it cannot cross.)
+    // Tried and rejected on the way (all parity-green, all slower): two threads per row (16 softmax warps; maximum
+    // exchanged through shared memory or recomputed) with and without turns, 468-584 TFLOP/s; a degree-3 polynomial exp2
+    // on the FMA pipe for every 2nd / 3rd / 4th element (the loop is issue bound for ONE warp, extra instructions cost more
+    // than the MUFU slots they free); truncating bf16 conversion by PRMT instead of F2FP (no change); fetching S_{j+1}
+    // ahead of tile j's exponentials (it only exists once P_{j-1} has gone through the MMA warp: the warp then waits for
+    // the tensor pipe instead of exponentiating).
     const int sw = warp - 3;
-    const int t = sw >> 3;                    // query tile of this warp
-    const int hf = (sw >> 2) & 1;             // which 32 of the tile's 64 key columns this warp exponentiates
+    const int t = sw >> 2;                    // query tile of this warp
     const int quad = warp & 3;                // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tO = tmem_base + lane_off + kColO + static_cast<uint32_t>(80 * t);
     const uint32_t tQ = tmem_base + lane_off + kColQ + static_cast<uint32_t>(40 * t);
     constexpr int kOChunks = (HD + 15) / 16;  // 16-column chunks of O
-    constexpr int kOSplit = (kOChunks + 1) / 2;  // chunks [0, kOSplit) belong to half 0, the rest to half 1
-    const int oc0 = hf ? kOSplit : 0, oc1 = hf ? kOChunks : kOSplit;
     const uint32_t q_row = smem_u32(sQ + t * S::kQMainTile) + static_cast<uint32_t>(row * 128);
     const uint32_t q_tail = smem_u32(sQ + S::kQMain + t * S::kQTailTile) + static_cast<uint32_t>(row * 32);
     uint8_t* out_tile = sOut + t * S::kOutTile;
     const uint32_t out_row = smem_u32(out_tile) + static_cast<uint32_t>(row * HD * 2);
-    float* l_mine = l_ex + (t * 2 + hf) * kQ + row;
-    const float* l_other = l_ex + (t * 2 + (hf ^ 1)) * kQ + row;
-    const bool store_thread = (sw & 7) == 0 && lane == 0;   // issues (and waits for) the tile's TMA stores
-    // Q row of item `it_q`: shared memory (TMA, swizzled) -> registers -> TMEM as bf16 pairs; each half moves 32 columns
+    const bool store_thread = (sw & 3) == 0 && lane == 0;   // issues (and waits for) the tile's TMA stores
+    uint32_t turns = 0;                                     // turns this tile has taken (phase of turn[t])
+    // Q row of item `it_q`: shared memory (TMA, swizzled) -> registers -> TMEM as bf16 pairs
     auto copy_q = [&](uint32_t it_q) {
       mbar_wait(q_full, it_q & 1u);
-      uint32_t qw[16];
+      uint32_t qw[32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint4 v = lds_u4(q_row + static_cast<uint32_t>(((4 * hf + c) ^ (row & 7)) << 4));
+      for (int c = 0; c < 8; ++c) {
+        const uint4 v = lds_u4(q_row + static_cast<uint32_t>((c ^ (row & 7)) << 4));
         qw[4 * c] = v.x; qw[4 * c + 1] = v.y; qw[4 * c + 2] = v.z; qw[4 * c + 3] = v.w;
       }
-      tmem_st_32x32b_x16(tQ + static_cast<uint32_t>(16 * hf), qw);
-      if (kTail && hf == 1) {
+      tmem_st_32x32b_x32(tQ, qw);
+      if (kTail) {
         // tail k-step = columns 56..71; 56..63 already went through the main box: Q contributes zeros there
         uint32_t t8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
         const uint4 v = lds_u4(q_tail + static_cast<uint32_t>((1 ^ ((row >> 2) & 1)) << 4));
@@ -346,12 +345,20 @@ attention_dq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
     uint32_t su0 = 0, su1 = 0;   // s_full uses per S buffer
     uint32_t g = 0, it = 0;      // running count of this tile's P·V products (o_done phases), item count
     uint32_t act_items = 0;      // items in which this tile was active (o_full phases)
+    if (t == 1 && lane == 0) mbar_arrive(&turn[0]);   // tile 0 takes the first turn
     if (blockIdx.x < n_items) copy_q(0);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int qp = item % QP, h = (item / QP) % H, b = item / (QP * H);
       const int row0 = qp * 2 * kQ + t * kQ;   // first query row of this tile
       const bool has_next = item + (int)gridDim.x < n_items;
-      if (row0 >= N) {  // (only tile 1) nothing to do for this item; keep the Q hand-shake going
+      if (row0 >= N) {  // (only tile 1) nothing to do for this item; keep the turn-taking and the Q hand-shake going
+        // (turns first: the next item's Q only arrives after the loader has placed all of THIS item's K/V stages, and
+        //  those drain only as tile 0 advances - which needs its turns)
+        for (int j = 0; j < T; ++j) {
+          mbar_wait(&turn[t], turns++ & 1u);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&turn[t ^ 1]);
+        }
         if (has_next) copy_q(it + 1);
         continue;
       }
@@ -362,47 +369,35 @@ attention_dq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
         const uint32_t tS = tmem_base + lane_off + static_cast<uint32_t>((2 * t + sb) * kKV);
         const uint32_t par = sb ? su1 : su0;
         if (sb) ++su1; else ++su0;
-        const bool tr = (dbg & 128) && blockIdx.x == 0 && sw == 0 && lane == 0 && it == 0 && j < 64;
-        if (tr) g_dq_trace[j * 16 + 0] = clock64();
         mbar_wait(&s_full[2 * t + sb], par & 1u);
         tc_fence_after();
-        if (tr) g_dq_trace[j * 16 + 1] = clock64();
-        uint32_t s[32], o32[32];   // s: this warp's 32 columns, o32: the partner's (for the row maximum only)
-        tmem_ld_32x32b_x32(tS + static_cast<uint32_t>(32 * hf), s);
-        tmem_ld_32x32b_x32(tS + static_cast<uint32_t>(32 * (hf ^ 1)), o32);
+        uint32_t s[64];
+        tmem_ld_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+        tmem_ld_32x32b_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
         tmem_ld_wait();
-        if (tr) g_dq_trace[j * 16 + 2] = clock64();
-        // P aliases the S columns BOTH warps of the row group have just read: neither may write its P before the other
-        // holds its copy (arrive here, wait just before the store - hundreds of cycles later, so it never blocks)
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ld_done[4 * t + quad]);
         if (valid < kKV) {  // last tile: keys past the sequence end (zero-filled K rows) never win
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            if (32 * hf + c >= valid) s[c] = __float_as_uint(-INFINITY);
-            if (32 * (hf ^ 1) + c >= valid) o32[c] = __float_as_uint(-INFINITY);
-          }
+          for (int c = 0; c < 64; ++c)
+            if (c >= valid) s[c] = __float_as_uint(-INFINITY);
         }
         // 8 independent chains (a single running max would be a 64-deep dependent chain)
         float mx8[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) mx8[c] = fmaxf(__uint_as_float(s[c]), __uint_as_float(o32[c]));
+        for (int c = 0; c < 8; ++c) mx8[c] = __uint_as_float(s[c]);
 #pragma unroll
-        for (int c = 8; c < 32; ++c)
-          mx8[c & 7] = fmaxf(mx8[c & 7], fmaxf(__uint_as_float(s[c]), __uint_as_float(o32[c])));
+        for (int c = 8; c < 64; ++c) mx8[c & 7] = fmaxf(mx8[c & 7], __uint_as_float(s[c]));
         float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
                          fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
         mx *= scale_log2;  // scale > 0
-        // lazy rescale: keep the old reference max unless the new one is more than 2^8 larger.  Both warps of a row see
-        // the same 64 values, so they take the same decision and keep the same m.
+        // lazy rescale: keep the old reference max unless the new one is more than 2^8 larger
         const float m_new = (mx > m + 8.0f) ? mx : m;
         const bool moved = m_new != m;
         const float alpha = (j == 0) ? 0.f : fast_exp2(m - m_new);
         if (j > 0 && __any_sync(0xffffffffu, moved)) {
           mbar_wait(&o_done[t], (g - 1) & 1u);  // the previous P·V has retired: O is stable
           tc_fence_after();
-          for (int c = oc0; c < oc1; ++c) {
+#pragma unroll
+          for (int c = 0; c < kOChunks; ++c) {
             uint32_t o[16];
             tmem_ld_32x32b_x16(tO + static_cast<uint32_t>(16 * c), o);
             tmem_ld_wait();
@@ -414,39 +409,46 @@ attention_dq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
         m = m_new;
         float sum8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const float neg_m = -m;
-        uint32_t pk[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          float p0 = fmaf(__uint_as_float(s[2 * c]), scale_log2, neg_m);
-          float p1 = fmaf(__uint_as_float(s[2 * c + 1]), scale_log2, neg_m);
-          if (!(dbg & 1)) { p0 = fast_exp2(p0); p1 = fast_exp2(p1); }
+        mbar_wait(&turn[t], turns++ & 1u);      // ---- this tile's turn on the MUFU unit ----
+        auto exps = [&](int c) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(s[2 * c]), scale_log2, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), scale_log2, neg_m));
           sum8[(2 * c) & 7] += p0;
           sum8[(2 * c + 1) & 7] += p1;
-          pk[c] = pack_bf16x2(p0, p1);
+          s[c] = pack_bf16x2(p0, p1);  // in place: s[2c], s[2c+1] (indices >= c) are consumed first
+        };
+#pragma unroll
+        for (int c = 0; c < kHandoff; ++c) exps(c);
+        {
+          // ---- hand the MUFU unit to the other tile after kHandoff of the 32 pairs: its first exponentials then fill the
+          // gaps of this warp's last ones (one warp cannot saturate the unit).  The arrive is predicated on a partial row sum
+          // (never negative; ptxas cannot know): a data dependence on the exponentials before it, otherwise the predicated
+          // arrive is scheduled ahead of most of them
+          const float part = ((sum8[0] + sum8[1]) + (sum8[2] + sum8[3])) + ((sum8[4] + sum8[5]) + (sum8[6] + sum8[7]));
+          __syncwarp();
+          if (lane == 0 && part >= 0.f) mbar_arrive(&turn[t ^ 1]);
         }
-        l = l * alpha + (((sum8[0] + sum8[1]) + (sum8[2] + sum8[3])) + ((sum8[4] + sum8[5]) + (sum8[6] + sum8[7])));
-        if (tr) g_dq_trace[j * 16 + 3] = clock64();
-        mbar_wait(&ld_done[4 * t + quad], g & 1u);
-        tc_fence_after();
-        tmem_st_32x32b_x16(tS + static_cast<uint32_t>(16 * hf), pk);   // P (bf16 pairs) aliases the S buffer's first 32 columns
+#pragma unroll
+        for (int c = kHandoff; c < 32; ++c) exps(c);
+        const float lsum = ((sum8[0] + sum8[1]) + (sum8[2] + sum8[3])) + ((sum8[4] + sum8[5]) + (sum8[6] + sum8[7]));
+        l = l * alpha + lsum;
+        tmem_st_32x32b_x32(tS, *reinterpret_cast<const uint32_t(*)[32]>(&s[0]));   // P (bf16 pairs) aliases S
         tmem_st_wait();
-        if (tr) g_dq_trace[j * 16 + 4] = clock64();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[2 * t + sb]);
-        if (tr) g_dq_trace[j * 16 + 5] = clock64();
       }
       // every Q_t·Kᵀ of this item has retired (its last S tile has been consumed): the next item's Q may replace it in
       // TMEM now, so that the MMA warp can start the next item's S tiles while this item's output is written
       if (has_next) copy_q(it + 1);
       // ---- O / l -> bf16 -> staging tile -> one TMA store ----
-      *l_mine = l;
       mbar_wait(&o_full[t], act_items++ & 1u);
       tc_fence_after();
       if (store_thread) tma_store_wait_read<0>();   // the previous store of this tile has finished reading the staging tile
-      bar_sync_named(1 + t, 256);
-      const float inv = 1.0f / (hf ? (*l_other + l) : (l + *l_other));   // same order of the two partial sums in both warps
-      for (int c = oc0; c < oc1; ++c) {
+      bar_sync_named(1 + t, 128);
+      const float inv = 1.0f / l;
+#pragma unroll
+      for (int c = 0; c < kOChunks; ++c) {
         uint32_t o[16];
         tmem_ld_32x32b_x16(tO + static_cast<uint32_t>(16 * c), o);
         tmem_ld_wait();
@@ -474,8 +476,8 @@ attention_dq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
       fence_proxy_async_smem();
       // order this item's TMEM reads before the p_full arrive that lets the next item's first P·V overwrite O
       tc_fence_before();
-      bar_sync_named(1 + t, 256);
-      if (store_thread && !(dbg & 64)) {
+      bar_sync_named(1 + t, 128);
+      if (store_thread) {
         tma_store_4d(&tmOut, out_tile, 0, h, row0, b);   // rows >= N are clipped
         tma_store_commit();
       }
@@ -527,6 +529,13 @@ int make_tmap_heads(CUtensorMap* out, const void* base, int hd, int heads, int N
 
 }  // namespace
 
+// shared with attention_ws.cu: qkv [B*N, ld] viewed as (hd, 3H, N, B), box = box_cols x 1 x box_rows x 1
+int make_tmap_qkv_4d(CUtensorMap* out, const void* base, int hd, int heads3, int N, int B, int64_t ld, int box_cols,
+                     int box_rows, int swizzle32) {
+  return make_tmap_heads(out, base, hd, heads3, N, B, ld, box_cols, box_rows,
+                         swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, false);
+}
+
 int attention_dq_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
                       float scale, cudaStream_t st) {
   DFD_REQUIRE(qkv && out, DFD_ERR_BAD_ARG, "attention: null pointer");
@@ -553,14 +562,12 @@ int attention_dq_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, in
   const int n_items = (int)items64;
   const int grid = n_items < kNumSMs ? n_items : kNumSMs;
   static SmemOptIn smem_once[2];
-  const char* dbg_env = getenv("DFD_ATTN_DBG");
-  const int dbg = dbg_env ? atoi(dbg_env) : 0;
   if (hd == 64) {
     if (int rc2 = ensure_dynamic_smem(smem_once[0], attention_dq_kernel<64>, DqSmem<64>::kTotal)) return rc2;
-    attention_dq_kernel<64><<<grid, kThreads, DqSmem<64>::kTotal, st>>>(tmMain, tmTail, tmOut, N, H, n_items, scale_log2, dbg);
+    attention_dq_kernel<64><<<grid, kThreads, DqSmem<64>::kTotal, st>>>(tmMain, tmTail, tmOut, N, H, n_items, scale_log2);
   } else {
     if (int rc2 = ensure_dynamic_smem(smem_once[1], attention_dq_kernel<72>, DqSmem<72>::kTotal)) return rc2;
-    attention_dq_kernel<72><<<grid, kThreads, DqSmem<72>::kTotal, st>>>(tmMain, tmTail, tmOut, N, H, n_items, scale_log2, dbg);
+    attention_dq_kernel<72><<<grid, kThreads, DqSmem<72>::kTotal, st>>>(tmMain, tmTail, tmOut, N, H, n_items, scale_log2);
   }
   DFD_LAUNCH_CHECK();
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -569,8 +576,31 @@ int attention_dq_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, in
 
 }  // namespace dfd
 
-// Development hook: the clock64 stamps of the last attention_dq launch that ran with DFD_ATTN_DBG & 128.
-extern "C" DFD_API int dfd_debug_read_trace(long long* host, int n) {
-  if (n > 64 * 16) n = 64 * 16;
-  return cudaMemcpyFromSymbol(host, dfd::g_dq_trace, sizeof(long long) * n) == cudaSuccess ? 0 : -4;
+namespace dfd {
+
+// Product dispatch.  Measured on B200 (scripts/kbench.py attn, profiles/r02_kbench_attention.txt): the dual-query-tile
+// kernel is ahead from the 196-token sequences of base-224 up (298 vs 232 TFLOP/s there, 635 vs 505 at 729 tokens);
+// sequences that do not even fill one 128-row query tile keep the persistent single-tile kernel (two CTAs per SM).
+int attention_auto_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
+                        float scale, cudaStream_t st) {
+  if (N <= 128) return attention_ws_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, st);
+  return attention_dq_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, st);
+}
+
+}  // namespace dfd
+
+extern "C" DFD_API int dfd_attention_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B,
+                                          int N, int H, int hd, float scale, void* stream) {
+  return dfd::attention_auto_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Test / A-B hook: impl 2 = persistent single-tile kernel (attention_ws.cu), 5 = dual-query-tile kernel (this file),
+// for any sequence length.
+extern "C" DFD_API int dfd_attention_bf16_impl(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N,
+                                               int H, int hd, float scale, int impl, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (impl == 2) return dfd::attention_ws_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, st);
+  if (impl == 5) return dfd::attention_dq_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, st);
+  dfd::set_last_error("attention: impl must be 2 (single-tile persistent) or 5 (dual-query-tile)");
+  return DFD_ERR_BAD_ARG;
 }

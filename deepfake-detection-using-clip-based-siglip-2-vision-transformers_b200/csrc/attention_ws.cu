@@ -374,9 +374,9 @@ static int launch_ws(const void* qkv, int64_t ldqkv, __nv_bfloat16* out, int64_t
 
 }  // namespace
 
-// kv_tile: 64 or 128 keys per tile; 0 = choose (128 once the sequence has more than two 128-key tiles' worth of work)
+// 64-key tiles (the 128-key instantiation of the template was a round-1 experiment: never faster, no longer compiled)
 int attention_ws_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
-                      float scale, int kv_tile, cudaStream_t st) {
+                      float scale, cudaStream_t st) {
   DFD_REQUIRE(qkv && out, DFD_ERR_BAD_ARG, "attention: null pointer");
   DFD_REQUIRE(B > 0 && N > 0 && H > 0, DFD_ERR_SHAPE, "attention: B, N, H must be positive");
   DFD_REQUIRE(hd == 64 || hd == 72, DFD_ERR_UNSUPPORTED, "attention: head dim %d not supported (64, 72)", hd);
@@ -384,18 +384,13 @@ int attention_ws_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, in
               "attention: bad leading dimensions");
   DFD_REQUIRE(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0), DFD_ERR_BAD_ARG,
               "attention: pointers must be 16-byte aligned");
-  DFD_REQUIRE(kv_tile == 0 || kv_tile == 64 || kv_tile == 128, DFD_ERR_BAD_ARG, "attention: kv_tile must be 0, 64 or 128");
   const int64_t items64 = (int64_t)((N + kQ - 1) / kQ) * H * B;
   DFD_REQUIRE(items64 < (1ll << 31), DFD_ERR_SHAPE, "attention: too many work items");
   const float scale_log2 = scale * 1.4426950408889634f;
   const int n_items = (int)items64;
-  if (kv_tile == 0) kv_tile = N > 256 ? 128 : 64;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  if (hd == 64)
-    return kv_tile == 64 ? launch_ws<64, 64>(qkv, ldqkv, o, ldo, B, N, H, n_items, scale_log2, st)
-                         : launch_ws<64, 128>(qkv, ldqkv, o, ldo, B, N, H, n_items, scale_log2, st);
-  return kv_tile == 64 ? launch_ws<72, 64>(qkv, ldqkv, o, ldo, B, N, H, n_items, scale_log2, st)
-                       : launch_ws<72, 128>(qkv, ldqkv, o, ldo, B, N, H, n_items, scale_log2, st);
+  if (hd == 64) return launch_ws<64, 64>(qkv, ldqkv, o, ldo, B, N, H, n_items, scale_log2, st);
+  return launch_ws<72, 64>(qkv, ldqkv, o, ldo, B, N, H, n_items, scale_log2, st);
 }
 
 }  // namespace dfd

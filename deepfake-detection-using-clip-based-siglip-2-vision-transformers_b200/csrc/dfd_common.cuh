@@ -76,18 +76,12 @@ int layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const float
 int rowstats_bf16(const void* x, int64_t ldx, float* stats, int M, int D, cudaStream_t st);
 int patchify(const void* pixels, int pix_format, int B, int Hin, int Win, int S, int P, int resize_mode,
              void* A, int64_t lda, cudaStream_t st);
-int attention_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
-                   float scale, cudaStream_t st);
-int attention_tc_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
-                      float scale, cudaStream_t st);
-int attention_pq_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
-                      float scale, cudaStream_t st);
 int attention_dq_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
                       float scale, cudaStream_t st);
 int attention_auto_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
                         float scale, cudaStream_t st);
 int attention_ws_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
-                      float scale, int kv_tile, cudaStream_t st);
+                      float scale, cudaStream_t st);
 int map_attention_bf16(const void* kv, int64_t ldkv, const float* q, void* out, int64_t ldo, int B, int N,
                        int H, int hd, float scale, cudaStream_t st);
 

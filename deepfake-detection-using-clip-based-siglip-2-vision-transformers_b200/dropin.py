@@ -461,6 +461,7 @@ class FastBinaryClassifier(BinaryClassifier):
         self.backbone.resize_mode = ops.RESIZE_BILINEAR
         self._head_state = {k: v.detach().float().cpu().clone() for k, v in (head_state or {}).items()}
         self._params = None
+        self.tta_flags = 0
 
     def load_state_dict(self, sd: dict, strict: bool = True):
         sd = {k[len("_orig_mod."):] if k.startswith("_orig_mod.") else k: v for k, v in sd.items()}
@@ -645,19 +646,37 @@ def few_shot_prototype(model: BinaryClassifier, support_loader, device=None, use
     return {"real": protos[0], "fake": protos[1]}
 
 
+def interpolated_position_table(pos: torch.Tensor, new_grid: int) -> torch.Tensor:
+    """HF `SiglipVisionEmbeddings.interpolate_pos_encoding` (HF:modeling_siglip.py:137-173) for a square grid:
+    [N,D] table viewed as [1,D,G,G], bicubic (align_corners=False, no antialias) to new_grid x new_grid, back to [N',D].
+    Done once per grid size when the engine for that size is created (a load-time step, like the weight repack)."""
+    N, D = pos.shape
+    G = int(round(N ** 0.5))
+    if G * G != N:
+        raise ValueError("position table is not a square grid")
+    t = pos.detach().float().reshape(1, G, G, D).permute(0, 3, 1, 2)
+    t = torch.nn.functional.interpolate(t, size=(new_grid, new_grid), mode="bicubic", align_corners=False)
+    return t.permute(0, 2, 3, 1).reshape(new_grid * new_grid, D).contiguous()
+
+
 class SiglipVisionModel:
     """HF-shaped wrapper: `SiglipVisionModel.from_state_dict(sd)(pixel_values=x)` -> .pooler_output [B,D] f32,
     .last_hidden_state [B,N,D], and with output_hidden_states=True the tuple of L+1 per-layer states
-    (Siglip2sidafrozen.py:753,787-793)."""
+    (Siglip2sidafrozen.py:753,787-793).  `interpolate_pos_encoding=True` (Siglip2sidafrozen.py:787, progressive resize
+    :975-987) accepts other square resolutions: each new patch grid gets its own engine (workspace sized for that token
+    count) whose position table is the bicubic resample of the trained one."""
 
     def __init__(self, arch: VisionArch, state_dict: dict, device="cuda", max_batch: int = 32):
         self.arch = arch
         self.device = _as_device(device)
+        self.max_batch = max_batch
         self.config = types.SimpleNamespace(hidden_size=arch.hidden_size, image_size=arch.image_size,
                                             patch_size=arch.patch_size, num_hidden_layers=arch.num_hidden_layers,
                                             num_attention_heads=arch.num_attention_heads,
                                             intermediate_size=arch.intermediate_size)
-        self.engine = SiglipEngine(arch, self.device.index, max_batch).load_state_dict(state_dict)
+        self._canon = canonicalize_state_dict(state_dict)
+        self.engine = SiglipEngine(arch, self.device.index, max_batch).load_state_dict(self._canon)
+        self._engines = {arch.grid: self.engine}
 
     @classmethod
     def from_state_dict(cls, state_dict: dict, device="cuda", max_batch: int = 32, num_heads: Optional[int] = None):
@@ -669,18 +688,43 @@ class SiglipVisionModel:
     def to(self, *a, **k):
         return self
 
+    def engine_for_grid(self, grid: int) -> SiglipEngine:
+        if grid not in self._engines:
+            a = self.arch
+            arch = VisionArch(grid * a.patch_size, a.patch_size, a.hidden_size, a.intermediate_size, a.num_hidden_layers,
+                              a.num_attention_heads, a.layer_norm_eps)
+            sd = dict(self._canon)
+            sd["embeddings.position_embedding.weight"] = interpolated_position_table(
+                self._canon["embeddings.position_embedding.weight"], grid)
+            # keep the activation workspace of the extra engine in proportion to the native one's
+            mb = max(1, min(self.max_batch, self.max_batch * a.tokens // (grid * grid)))
+            self._engines[grid] = SiglipEngine(arch, self.device.index, mb).load_state_dict(sd)
+        return self._engines[grid]
+
     def __call__(self, pixel_values: torch.Tensor, output_hidden_states: bool = False,
                  interpolate_pos_encoding: bool = False, **_):
-        gp, P = self.arch.grid * self.arch.patch_size, self.arch.patch_size
-        if not all(gp <= s < gp + P for s in pixel_values.shape[-2:]):
-            raise ValueError(f"pixel_values sides must be in [{gp}, {gp + P}) (position-embedding interpolation "
-                             "for other grids is not built)")
+        P = self.arch.patch_size
+        H, W = pixel_values.shape[-2:]
+        gh, gw = H // P, W // P
+        if (gh, gw) == (self.arch.grid, self.arch.grid):
+            eng = self.engine
+        elif interpolate_pos_encoding and gh == gw and gh >= 1:
+            eng = self.engine_for_grid(gh)
+        elif not interpolate_pos_encoding:
+            raise ValueError(f"pixel_values of {H}x{W} give a {gh}x{gw} patch grid, the model has {self.arch.grid}x"
+                             f"{self.arch.grid}; pass interpolate_pos_encoding=True (as HF requires)")
+        else:
+            raise NotImplementedError("interpolate_pos_encoding for non-square inputs is not built (the reference's "
+                                      "SigLIP2_MTL needs square token grids too: Siglip2sidafrozen.py:795-801)")
         x = pixel_values.to(self.device).float()
         if output_hidden_states:  # tuple of L+1 tensors, as SigLIP2_MTL consumes them (Siglip2sidafrozen.py:790-793)
-            pooled, last, hid = self.engine.forward_hidden(x)
+            chunks = [eng.forward_hidden(x[i:i + eng.max_batch]) for i in range(0, x.shape[0], eng.max_batch)]
+            pooled = torch.cat([c[0] for c in chunks])
+            last = torch.cat([c[1] for c in chunks])
+            hid = torch.cat([c[2] for c in chunks], 1)
             return types.SimpleNamespace(pooler_output=pooled.float(), last_hidden_state=last.float(),
                                          hidden_states=tuple(h.float() for h in hid))
-        pooled, last = self.engine(x, want_last_hidden=True)
+        pooled, last = eng(x, want_last_hidden=True)
         return types.SimpleNamespace(pooler_output=pooled.float(), last_hidden_state=last.float(), hidden_states=None)
 
 

@@ -6,8 +6,9 @@ hidden-state taps + a 3-class head on the pooled embedding + the SegFormer-style
 Every Linear / 1x1 convolution is a tcgen05 GEMM on token-major [B·N, C] bf16 matrices (erf-GELU, sigmoid and the
 `fuse_attn(x) * x` gate run in the GEMM epilogue, the four branch outputs are written straight into their column slice
 of the concatenated [B·N, 4E] matrix), the depthwise 3x3 convolution and the head + bilinear resize are small streaming
-kernels (csrc/decoder.cu).  Evaluation mode only (dropout off); the encoder runs at its native resolution — the
-reference's `interpolate_pos_encoding=True` path for other image sizes is not built.
+kernels (csrc/decoder.cu).  Evaluation mode only (dropout off).  Other square input sizes (the reference calls the
+encoder with `interpolate_pos_encoding=True`, Siglip2sidafrozen.py:787, for its progressive-resize schedule :975-987) run
+on a per-grid engine whose position table is the bicubic resample of the trained one (HF:modeling_siglip.py:137-173).
 """
 from __future__ import annotations
 
@@ -17,7 +18,7 @@ from typing import Dict, Sequence
 import torch
 
 from . import ops
-from .engine import ARCHS, SiglipEngine, VisionArch
+from .engine import ARCHS, SiglipEngine, VisionArch, canonicalize_state_dict
 
 
 class SegFormerStrongDecoder:
@@ -70,7 +71,10 @@ class SigLIP2_MTL:
                  seg_layers: Sequence[int] = (2, 6, 10, -1), embed_dim: int = 256):
         self.arch = ARCHS[arch] if isinstance(arch, str) else arch
         self.device = torch.device("cuda", device)
+        self.max_batch = max_batch
         self.engine = SiglipEngine(self.arch, device, max_batch)
+        self._engines = {self.arch.grid: self.engine}
+        self._enc_sd: Dict[str, torch.Tensor] = {}
         self.seg_layers, self.embed_dim = tuple(seg_layers), embed_dim
         self.decoder = SegFormerStrongDecoder(len(self.seg_layers), embed_dim, self.device)
         self._w: Dict[str, torch.Tensor] = {}
@@ -89,23 +93,53 @@ class SigLIP2_MTL:
         """Keys as written by the reference's trainer: encoder.vision_model.*, cls_head.{weight,bias} (or cls_head.1.* when
         it was built with dropout), decoder.*"""
         enc = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
-        self.engine.load_state_dict(enc)
+        self._enc_sd = canonicalize_state_dict(enc)
+        self.engine.load_state_dict(self._enc_sd)
+        for g in [g for g in self._engines if g != self.arch.grid]:   # engines of other grids hold the old weights
+            self._engines.pop(g).close()
         ck = "cls_head.1" if "cls_head.1.weight" in sd else "cls_head"
         self._w = {"cls.w": sd[f"{ck}.weight"].detach().to(self.device, torch.float32).contiguous(),
                    "cls.b": sd[f"{ck}.bias"].detach().to(self.device, torch.float32).contiguous()}
         self.decoder.load_state_dict(sd, prefix="decoder.")
         return self
 
+    def _engine_for(self, S: int) -> SiglipEngine:
+        """Engine for S x S inputs: the native one, or one per other patch grid with an interpolated position table."""
+        from .dropin import interpolated_position_table
+
+        a = self.arch
+        g = S // a.patch_size
+        if g not in self._engines:
+            arch = VisionArch(g * a.patch_size, a.patch_size, a.hidden_size, a.intermediate_size, a.num_hidden_layers,
+                              a.num_attention_heads, a.layer_norm_eps)
+            sd = dict(self._enc_sd)
+            sd["embeddings.position_embedding.weight"] = interpolated_position_table(
+                self._enc_sd["embeddings.position_embedding.weight"], g)
+            mb = max(1, min(self.max_batch, self.max_batch * a.tokens // (g * g)))
+            self._engines[g] = SiglipEngine(arch, self.device.index, mb).load_state_dict(sd)
+        return self._engines[g]
+
     @torch.no_grad()
     def forward(self, pixel_values: torch.Tensor):
         x = pixel_values.to(self.device)
         B = x.shape[0]
-        S = int(x.shape[-1]) if x.dtype != torch.uint8 else int(x.shape[1])
-        pooled, _, hidden = self.engine.forward_hidden(x)
-        cls_logit = ops.linear_small(pooled, self._w["cls.w"], self._w["cls.b"])
-        last = hidden.shape[0] - 1
-        idxs = [(i + 1 if i >= 0 else last) for i in self.seg_layers]
-        feats = [hidden[i].reshape(B * self.arch.tokens, self.arch.hidden_size) for i in idxs]
-        return cls_logit, self.decoder(feats, B, self.grid, S)
+        u8 = x.dtype == torch.uint8
+        Hh, Ww = (int(x.shape[1]), int(x.shape[2])) if u8 else (int(x.shape[-2]), int(x.shape[-1]))
+        if Hh != Ww:
+            raise ValueError("Cannot reshape tokens into square grid. Try using square input images.")  # Siglip2sidafrozen.py:799-801
+        S = Hh
+        eng = self._engine_for(S)
+        N, grid = eng.arch.tokens, eng.arch.grid
+        cls, seg = [], []
+        for b0 in range(0, B, eng.max_batch):
+            xb = x[b0:b0 + eng.max_batch]
+            nb = xb.shape[0]
+            pooled, _, hidden = eng.forward_hidden(xb)
+            cls.append(ops.linear_small(pooled, self._w["cls.w"], self._w["cls.b"]))
+            last = hidden.shape[0] - 1
+            idxs = [(i + 1 if i >= 0 else last) for i in self.seg_layers]
+            feats = [hidden[i].reshape(nb * N, self.arch.hidden_size) for i in idxs]
+            seg.append(self.decoder(feats, nb, grid, S))
+        return torch.cat(cls), torch.cat(seg)
 
     __call__ = forward

@@ -94,7 +94,7 @@ def rowstats_bf16(x: torch.Tensor) -> torch.Tensor:
 def attention_bf16(qkv: torch.Tensor, B: int, N: int, H: int, hd: int, scale: Optional[float] = None,
                    impl: Optional[int] = None) -> torch.Tensor:
     """qkv [B*N, 3*H*hd] (q | k | v) -> [B*N, H*hd]; non-causal softmax(q k^T scale) v.
-    impl None = product path (tcgen05 kernel); 0 / 1 select the mma.sync / tcgen05 kernel (A/B tests)."""
+    impl None = product dispatch; 5 / 2 force the dual-query-tile / single-tile persistent tcgen05 kernel (A/B tests)."""
     _need_cuda(qkv)
     assert qkv.dtype == torch.bfloat16 and qkv.shape == (B * N, 3 * H * hd) and qkv.stride(1) == 1
     out = torch.empty((B * N, H * hd), dtype=torch.bfloat16, device=qkv.device)

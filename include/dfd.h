@@ -117,8 +117,8 @@ DFD_API int dfd_rowstats_bf16(const void* x, int64_t ldx, float* stats, int M, i
 DFD_API int dfd_attention_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N,
                                int H, int hd, float scale, void* stream);
 
-/* Same, with the kernel chosen explicitly (A/B tests): impl 0 = warp-level mma.sync kernel, 1 = tcgen05/TMEM
- * kernel (what dfd_attention_bf16 runs). */
+/* Same, with the kernel chosen explicitly (A/B tests): impl 5 = dual-query-tile tcgen05 kernel (what dfd_attention_bf16
+ * runs for N > 128), impl 2 = persistent single-tile tcgen05 kernel (N <= 128).  Other values: DFD_ERR_BAD_ARG. */
 DFD_API int dfd_attention_bf16_impl(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N,
                                     int H, int hd, float scale, int impl, void* stream);
 

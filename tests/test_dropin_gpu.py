@@ -34,7 +34,10 @@ def test_binary_classifier_forward(head, eps):
     z = m(x).cpu()
     pooled = R.siglip_vision_forward(sd, c, x, "fp32")["pooler_output"]
     z_ref = R.classifier_head(hs, head, pooled, eps)
-    assert (z - z_ref).abs().max() < 1e-2 * max(1.0, float(z_ref.abs().max())), (z, z_ref)
+    # 128-wide toy model with the production engine mode (LayerNorm folded into the GEMMs): bf16 noise averages over 6-9x
+    # fewer channels than at the named architectures, where the 1e-2 gate is asserted (tests/test_engine_gpu.py:
+    # test_benched_configuration_vs_hf_on_gpu, test_base_224_logits) — 2e-2 here, as for the other toy-model checks
+    assert (z - z_ref).abs().max() < 2e-2 * max(1.0, float(z_ref.abs().max())), (z, z_ref)
     if head == "B":  # off-size input -> F.interpolate default (nearest) inside the model
         xs = R.preprocess_u8(R.synthetic_images(3, 40, 4))
         z2 = m(xs).cpu()
@@ -414,6 +417,23 @@ def test_siglip2_mtl_end_to_end():
     scale = float(seg_ref.abs().max())
     assert (seg.cpu() - seg_ref).abs().max() < 0.03 * max(scale, 0.3), ((seg.cpu() - seg_ref).abs().max(), scale)
     assert np.corrcoef(seg.cpu().numpy().ravel(), seg_ref.numpy().ravel())[0, 1] > 0.999
+    # progressive-resize sizes (Siglip2sidafrozen.py:975-987 with interpolate_pos_encoding=True at :787): 280 px = 20 x 20 tokens
+    import dataclasses
+
+    from dfd import dropin
+
+    S2, g2 = 280, 20
+    img2 = R.synthetic_images(3, S2, 4)      # 3 images through a max_batch-1 engine (workspace scaled to the token count): chunked
+    cls2, seg2 = model(img2.to(DEV))
+    sd2 = dict(R.init_state_dict(c, 0))
+    sd2["embeddings.position_embedding.weight"] = dropin.interpolated_position_table(sd2["embeddings.position_embedding.weight"], g2)
+    c2 = dataclasses.replace(c, image_size=S2) if dataclasses.is_dataclass(c) else type(c)(**{**c.__dict__, "image_size": S2})
+    o2 = R.siglip_vision_forward(sd2, c2, R.preprocess_u8(img2), "fp32", output_hidden_states=True)
+    hs2 = o2["hidden_states"]
+    seg_ref2 = D.decoder_forward(sd, [hs2[i + 1 if i >= 0 else len(hs2) - 1] for i in seg_layers], g2, S2)
+    assert tuple(seg2.shape) == (3, 1, S2, S2)
+    assert (cls2.cpu() - D.cls_head(sd, o2["pooler_output"])).abs().max() < 2e-2 * max(1.0, float(cls_ref.abs().max()))
+    assert np.corrcoef(seg2.cpu().numpy().ravel(), seg_ref2.numpy().ravel())[0, 1] > 0.999
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -584,7 +604,7 @@ def test_run_tta_inference_fused_flip_equals_two_host_passes(tmp_path):
     ds0 = dropin.AIHumanDataset(tmp_path, csv, transform=tfs[1][1])
     xf = torch.stack([ds0[i][0] for i in range(len(ds0))])
     pr = torch.sigmoid(R.classifier_head(hs, "A", R.siglip_vision_forward(sd, c, xf, "fp32")["pooler_output"], 0.0)).numpy()
-    assert np.abs(per[1] - pr).max() < 5e-3
+    assert np.abs(per[1] - pr).max() < 1e-2      # 128-wide toy model, production engine mode (see test_binary_classifier_forward)
     # three transforms: the third (CLAHE) runs as an ordinary extra pass
     y3, p3, per3, _ = dropin.run_tta_inference(m, tmp_path, csv, dropin.create_tta_transforms(c.image_size, 3), 4, 0, torch.device(DEV))
     assert len(per3) == 3 and np.array_equal(per3[0], per[0]) and np.array_equal(per3[1], per[1])
@@ -608,3 +628,229 @@ def test_patchify_flip_equals_flipped_input(fmt, S, P, Hin):
     torch.cuda.synchronize()
     assert torch.equal(a, b)
     assert not torch.equal(a, ops.patchify(src.to(DEV), S, P, resize_mode=mode))
+
+
+def test_cifake_evaluate_vs_oracle():
+    """cifake_binary_classifier.py:893-953 (BASELINE config 4): 32x32 images, bilinear 32 -> S inside the model, head H-D,
+    BCE-with-logits, the reference's metric tuple — against the oracle flow on the same tensors."""
+    from dfd import cifake, dropin
+    from oracle import siglip_ref as R
+
+    c = R.CONFIGS["tiny-hd64"]
+    sd = R.init_state_dict(c, 0)
+    hd = R.init_head_d("small", c.hidden_size, 4)
+    m = dropin.FastBinaryClassifier("small", DEV, arch="tiny-hd64", max_batch=16)
+    ck = {"backbone.vision_model." + k: v for k, v in sd.items()}
+    ck.update(hd)
+    m.load_state_dict(ck)
+    img = R.synthetic_images(22, 32, 8)
+    labels = torch.tensor([0, 1] * 11)
+    x = R.preprocess_u8(img)
+    xr = R.resize_input(x, c.image_size, "bilinear")
+    z_ref = R.classifier_head_d(hd, R.siglip_vision_forward(sd, c, xr, "fp32")["pooler_output"])
+    p_ref = torch.sigmoid(z_ref).numpy()
+    bs = 8
+    for src in (x, img):   # float NCHW batches (the reference's loaders) and uint8 NHWC batches
+        loader = [(src[i:i + bs], labels[i:i + bs]) for i in range(0, 22, bs)]
+        loss, acc, bacc, prec, rec, f1, auc, mcc, cm, y, probs = cifake.evaluate(m, loader, torch.nn.BCEWithLogitsLoss(), torch.device(DEV))
+        assert y.tolist() == labels.tolist() and probs.shape == (22,)
+        assert np.abs(probs - p_ref).max() < 1e-2
+        loss_ref = np.mean([float(torch.nn.functional.binary_cross_entropy_with_logits(z_ref[i:i + bs], labels[i:i + bs].float()))
+                            for i in range(0, 22, bs)])
+        assert abs(loss - loss_ref) < 1e-2
+        sure = np.abs(p_ref - 0.5) > 2e-2                      # samples whose decision cannot flip within the tolerance
+        assert ((probs > 0.5) == (p_ref > 0.5))[sure].all()
+        assert cm.shape == (2, 2) and cm.sum() == 22 and 0.0 <= auc <= 1.0 and -1.0 <= mcc <= 1.0
+        if sure.all():
+            assert acc == float(((p_ref > 0.5) == labels.numpy()).mean())
+    # TTA variant runs (random views: statistical check only — the mean stays near the base prediction)
+    g = torch.Generator().manual_seed(0)
+    z_tta = cifake.test_time_augmentation(m, img.to(DEV), n_tta=3, generator=g).cpu()
+    assert z_tta.shape == (22,) and torch.isfinite(z_tta).all()
+    sweep = cifake.throughput_sweep(m, batches=(16, 32), iters=1)
+    assert set(sweep) == {16, 32} and all(v > 0 for v in sweep.values())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# SURVEY §8 f.2: multicrop / rot-90 / patch-grid / video views produced on the device from one upload per image
+# ---------------------------------------------------------------------------------------------------------------------
+def _toy_pipeline(name="tiny-hd64", max_batch=32):
+    from dfd import pipeline, scoring
+    from oracle import siglip_ref as R
+    from tests.conftest import SIGLIP_ARTEFACTS
+
+    c = R.CONFIGS[name]
+    sd, hs = R.init_state_dict(c, 0), R.init_head("B", c.hidden_size, 1)
+    st = scoring.ScoringStack.from_dir(SIGLIP_ARTEFACTS, DEV)
+    return pipeline.DetectionPipeline(name, sd, hs, st, device=0, max_batch=max_batch), c, sd, hs
+
+
+def _pils(n, seed=3):
+    from PIL import Image
+
+    rng = np.random.default_rng(seed)
+    return [Image.fromarray(np.clip(rng.normal(120, 50, (90 + 21 * i, 131 - 9 * i, 3)), 0, 255).astype(np.uint8)) for i in range(n)]
+
+
+@pytest.mark.parametrize("clahe", [False, True])
+def test_views_on_device_are_bit_exact_with_pil(clahe):
+    """Every view (crop + PIL-exact resize for the model, crop + luma [+ CLAHE] + bicubic 256 for the frequency branch) built
+    on the device from the resident original equals what the reference builds on the host with PIL / cv2, bit for bit."""
+    from PIL import Image
+
+    from dfd.scoring import pil_to_gray256
+
+    pipe, c, _, _ = _toy_pipeline()
+    S = c.image_size
+    for pil in _pils(2):
+        w, h = pil.size
+        img = pipe._upload(pil)
+        for maker in (pipe.multicrop_rects_v2, pipe.multicrop_rects_v3):
+            rects, _ = maker(w, h)
+            x, g = pipe.views_on_device(img, rects, clahe)
+            torch.cuda.synchronize()
+            assert x.shape == (len(rects), S, S, 3) and g.shape == (len(rects), 256, 256)
+            for i, r in enumerate(rects):
+                crop = pil.resize((S, S), Image.BICUBIC) if r == "bicubic" else pil.crop(r)
+                ref_x = np.asarray(crop.resize((S, S), Image.BILINEAR))          # transforms.Resize((S,S)) on a PIL image
+                assert np.array_equal(x[i].cpu().numpy(), ref_x), (r, "model input")
+                assert np.array_equal(g[i].cpu().numpy(), pil_to_gray256(crop, clahe)), (r, "gray256")
+        rot = pipe.rotate90_noexpand(img).cpu().numpy()
+        assert np.array_equal(rot, np.asarray(pil.rotate(90, expand=False)))
+
+
+def test_detect_core_device_equals_host_preprocessed_detect_core():
+    """Same 6-view flow, views made on the device vs on the host (the path test_detect_core_multicrop_vs_oracle pins to the
+    oracle): identical inputs reach the engine, so the results agree to fp32 rounding of the tiny weight sums."""
+    pipe, _, _, _ = _toy_pipeline()
+    pils = _pils(3)
+    a = pipe.detect_core(pils, multicrop=True, clahe=False)
+    b = pipe.detect_core_device(pils, views="v2", clahe=False)
+    for ra, rb in zip(a, b):
+        for k in ("z_sig", "z_freq", "z_scaled", "p_fake_raw", "p_fake_coral", "p_blend", "entropy"):
+            assert abs(ra[k] - rb[k]) < 2e-6, (k, ra[k], rb[k])
+        assert ra["risk_idx"] == rb["risk_idx"]
+    one_a = pipe.detect_core(pils[:1], multicrop=False)
+    one_b = pipe.detect_core_device(pils[:1], views=None)
+    assert abs(one_a[0]["z_sig"] - one_b[0]["z_sig"]) < 2e-6 and abs(one_a[0]["z_freq"] - one_b[0]["z_freq"]) < 2e-6
+
+
+def test_detect_core_v3_nine_crops_and_rot90_vs_oracle():
+    """appv3.py:3214-3260 + :3315-3350: 9-crop weighted logits, 90-degree dual view (0.6 / 0.4 on probabilities, back to a
+    logit), G1 fusion on probabilities, temperature, CORAL — restated with PIL + the oracle, vs one batched device call."""
+    import json
+    import math
+
+    from safetensors.torch import load_file
+
+    from dfd import dropin
+    from oracle import scoring_ref as S
+    from oracle import siglip_ref as R
+    from tests.conftest import SIGLIP_ARTEFACTS
+
+    pipe, c, sd, hs = _toy_pipeline()
+    pils = _pils(2, seed=9)
+    res = pipe.detect_core_device(pils, views="v3", rot90=True, clahe=False)
+    fm, fu = load_file(f"{SIGLIP_ARTEFACTS}/freq_mlp.safetensors"), load_file(f"{SIGLIP_ARTEFACTS}/fusion_head.safetensors")
+    cuts = S.coral_cut_logits(json.load(open(f"{SIGLIP_ARTEFACTS}/coral_cutpoints.json")))
+    temp = json.load(open(f"{SIGLIP_ARTEFACTS}/coral_temp.json"))["temperature"]
+    pre = dropin.make_preprocess(c.image_size, "bilinear")
+
+    def z_of(views):
+        x = torch.stack([pre(v) for v in views])
+        return R.classifier_head(hs, "B", R.siglip_vision_forward(sd, c, x, "fp32")["pooler_output"], 1e-6).numpy()
+
+    for pil, r in zip(pils, res):
+        rects, w = pipe.multicrop_rects_v3(*pil.size)
+        crops = [pil.crop(rc) for rc in rects]
+        w = np.array(w, np.float32)
+        z_sig = float((z_of(crops) * w).sum())
+        z_rot = float(z_of([pil.rotate(90, expand=False)])[0])
+        p = 0.6 / (1 + math.exp(-z_sig)) + 0.4 / (1 + math.exp(-z_rot))
+        p = min(max(p, 1e-6), 1 - 1e-6)
+        z_sig2 = math.log(p / (1 - p))
+        assert abs(r["z_sig"] - z_sig2) < 3e-2, (r["z_sig"], z_sig2)      # toy 128-wide model, 10 bf16 forwards combined
+        assert abs(r["visual_prob"] - p) < 1e-2
+        # frequency branch + fusion + CORAL on the device's own z_sig: exact arithmetic of the reference flow
+        host = pipe.detect_core([pil], multicrop=False)  # only to get the G1 parameters exercised the same way
+        assert set(host[0]) == set(r)
+        p_sig, p_freq = 1 / (1 + math.exp(-r["z_sig"])), 1 / (1 + math.exp(-r["z_freq"] / 1.25))
+        z = float(fu["fc.weight"][0, 0]) * p_sig + float(fu["fc.weight"][0, 1]) * p_freq + float(fu["fc.bias"][0])
+        d = S.detect_scores(np.array([z], np.float32), cuts, temp)
+        assert abs(r["z_scaled"] - float(d["z_scaled"][0])) < 1e-4 and abs(r["p_blend"] - float(d["p_blend"][0])) < 1e-4
+        tp = S.coral_transition_points(cuts)
+        if np.abs(float(d["z_scaled"][0]) - tp).min() > 1e-3:
+            assert r["risk_idx"] == int(d["risk_idx"][0])
+
+
+def test_patch_grid_equals_per_cell_calls():
+    """compute_patch_grid (app.py:1461-1485): all 16 cells in one batch == one single-view call per cell."""
+    pipe, _, _, _ = _toy_pipeline()
+    pil = _pils(1, seed=4)[0].resize((150, 97))
+    grid, flat = pipe.patch_grid(pil, 4, 4)
+    assert grid.shape == (4, 4) and len(flat) == 16
+    rects = pipe.patch_grid_rects(150, 97, 4, 4)
+    assert rects[3] == (111, 0, 150, 24) and rects[15] == (111, 72, 150, 97)      # last column / row take the remainder
+    for i in (0, 3, 6, 15):
+        cell = pipe.detect_core_device([pil.crop(rects[i])], views=None)[0]["p_fake_raw"]
+        assert abs(cell - flat[i]) < 5e-6, (i, cell, flat[i])
+    assert pipe.patch_grid(pil.resize((40, 80))) == (None, [])                     # below MIN_SIDE
+
+
+def test_frame_features_vs_oracle():
+    """hidf_video_classifier.py:299-320: frames -> encode_image -> L2 normalise -> mean over frames."""
+    from oracle import siglip_ref as R
+
+    pipe, c, sd, _ = _toy_pipeline()
+    frames = R.synthetic_images(5, c.image_size, 12)
+    f = pipe.frame_features(frames).cpu()
+    ref = R.l2_normalize(R.siglip_vision_forward(sd, c, R.preprocess_u8(frames), "fp32")["pooler_output"])
+    assert R.cosine_report(f, ref)["cos_min"] >= 0.999
+    assert (f.norm(dim=-1) - 1).abs().max() < 1e-4
+    assert R.cosine_report(f.mean(0, keepdim=True), ref.mean(0, keepdim=True))["cos_min"] >= 0.9995
+
+
+@pytest.mark.parametrize("size", [280, 154])
+def test_interpolate_pos_encoding_vs_hf(size):
+    """HF `interpolate_pos_encoding=True` (HF:modeling_siglip.py:137-173; Siglip2sidafrozen.py:787 with the progressive
+    resize of :975-987): inputs whose patch grid differs from the trained one (15x15 here -> 20x20 / 11x11) against the
+    real transformers module in fp32, pooled output, last hidden state and every per-layer hidden state."""
+    transformers = pytest.importorskip("transformers")
+    from dfd import dropin
+    from oracle import siglip_ref as R
+
+    name = "small-hd72"
+    c = R.CONFIGS[name]
+    sd = R.init_state_dict(c, 0)
+    hc = transformers.SiglipVisionConfig(hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
+                                         num_hidden_layers=c.num_hidden_layers, num_attention_heads=c.num_attention_heads,
+                                         image_size=c.image_size, patch_size=c.patch_size)
+    hf = transformers.SiglipVisionModel(hc).eval()
+    hf.load_state_dict({"vision_model." + k: v for k, v in sd.items()}, strict=True)
+    x = R.preprocess_u8(R.synthetic_images(3, size, 5))
+    with torch.no_grad():
+        ref = hf(pixel_values=x, output_hidden_states=True, interpolate_pos_encoding=True)
+    m = dropin.SiglipVisionModel.from_state_dict({"vision_model." + k: v for k, v in sd.items()}, DEV, max_batch=2,
+                                                 num_heads=c.num_attention_heads)
+    with pytest.raises(ValueError):
+        m(pixel_values=x)                                   # like HF: a foreign grid needs the flag
+    o = m(pixel_values=x, output_hidden_states=True, interpolate_pos_encoding=True)
+    g = size // c.patch_size
+    assert o.last_hidden_state.shape == (3, g * g, c.hidden_size) == tuple(ref.last_hidden_state.shape)
+    rep = R.cosine_report(o.pooler_output.cpu(), ref.pooler_output)
+    assert rep["cos_min"] >= 0.999 and rep["cos_centered_min"] >= 0.99 and rep["rel_l2"] <= 0.03, rep
+    assert len(o.hidden_states) == len(ref.hidden_states) == c.num_hidden_layers + 1
+    for a, b in zip(o.hidden_states, ref.hidden_states):
+        r = R.cosine_report(a.cpu().reshape(-1, c.hidden_size), b.reshape(-1, c.hidden_size))
+        assert r["cos_min"] >= 0.998 and r["rel_l2"] <= 0.03, r
+    # the position table itself: bit-equal to HF's interpolation
+    emb = hf.vision_model.embeddings
+    want = emb.interpolate_pos_encoding(torch.zeros(1, g * g, c.hidden_size), size, size)[0]
+    got = dropin.interpolated_position_table(sd["embeddings.position_embedding.weight"], g)
+    assert torch.equal(got, want)
+    # native-size calls keep using the native engine
+    x0 = R.preprocess_u8(R.synthetic_images(2, c.image_size, 6))
+    o0 = m(pixel_values=x0, interpolate_pos_encoding=True)
+    with torch.no_grad():
+        r0 = hf(pixel_values=x0, interpolate_pos_encoding=True)
+    assert R.cosine_report(o0.pooler_output.cpu(), r0.pooler_output)["cos_min"] >= 0.999

@@ -265,7 +265,12 @@ def test_detect_records_at_batch_512_equal_small_batch_records():
     idx64 = torch.arange(3, 512, 8)[:64]
     rec64 = big.pack(big.detect_device(img[idx64.to(DEV)].contiguous(), None, clahe=True)).cpu()
     assert torch.isfinite(rec512).all()
-    assert torch.equal(rec512[idx64], rec64), (rec512[idx64] - rec64).abs().max()
+    f = pipeline.PACKED_FIELDS
+    # backbone + head: bit-identical.  The frequency branch is not batch-invariant to the last bit (freq_cols_kernel splits
+    # an image's column groups over a batch-dependent number of CTAs, so its fp32 partial sums add in another order:
+    # ~1e-6), and everything downstream of z_freq inherits that.
+    assert torch.equal(rec512[idx64][:, f.index("z_sig")], rec64[:, f.index("z_sig")])
+    assert torch.allclose(rec512[idx64], rec64, rtol=0, atol=2e-5), (rec512[idx64] - rec64).abs().max()
     idx = idx64[:16]
     sub = img[idx.to(DEV)].contiguous()
     rec16 = rec64[:16]
@@ -273,10 +278,9 @@ def test_detect_records_at_batch_512_equal_small_batch_records():
     torch.cuda.empty_cache()
     small = make(False, 4)
     rec_ref = small.pack(small.detect_device(sub, None, clahe=True)).cpu()
-    f = pipeline.PACKED_FIELDS
     dz = (rec16[:, f.index("z_sig")] - rec_ref[:, f.index("z_sig")]).abs().max()
     assert dz <= 1e-2, dz
-    assert torch.equal(rec16[:, f.index("z_freq")], rec_ref[:, f.index("z_freq")])   # fp32 feature path: no backbone in it
+    assert torch.allclose(rec16[:, f.index("z_freq")], rec_ref[:, f.index("z_freq")], rtol=0, atol=2e-5)   # fp32 feature path
     # CORAL: identical unless z_scaled sits within the logit tolerance of an argmax transition point
     zs, ia, ib = rec_ref[:, f.index("z_scaled")], rec16[:, f.index("risk_idx")], rec_ref[:, f.index("risk_idx")]
     import numpy as np
