@@ -184,6 +184,14 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
+def hbm_entry(name, bytes_per_call, ms, calls, peak):
+    if not calls or ms <= 0:
+        return None
+    ach = bytes_per_call * calls / (ms / 1e3) / 1e9
+    return {"kernel": name, "bound": "hbm", "algorithmic_bytes_per_call": int(bytes_per_call), "calls": calls,
+            "avg_ms": ms / calls, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
+
+
 def run_ours(args):
     import torch
 
@@ -202,108 +210,193 @@ def run_ours(args):
     arch = ARCHS[arch_name]
     peaks = load_peaks()
     lib = _lib.load()
+    # sub-batch = the unit of the work queue.  One GPU: the whole batch in one call.  Several GPUs: quarters of the per-GPU
+    # batch, so that a step of world x B images is 4 x world units which the ranks share dynamically.
+    sub = args.sub_batch or (B if world == 1 else max(1, B // 4))
+    sub = min(sub, B)
+    units_per_step = world * ((B + sub - 1) // sub)
 
     bsd = weights.random_vision_state_dict(arch, seed=0, device=dev)
     st = scoring.ScoringStack(dev, weights.random_freq_mlp_g2(2), weights.random_fusion_g2(3), [-1.0, -0.2, 0.3, 1.5], 1.0)
     pipe = pipeline.DetectionPipeline(arch, bsd, weights.random_classifier_head("B", arch.hidden_size, 1), st,
-                                      device=local, max_batch=min(B, args.max_batch), fuse_ln=bool(args.fuse_ln))
+                                      device=local, max_batch=min(sub, args.max_batch), fuse_ln=bool(args.fuse_ln))
     del bsd
     S = arch.image_size
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     images = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8, device=dev, generator=g)
+    local_units = (B + sub - 1) // sub
+    F = len(pipeline.PACKED_FIELDS)
 
-    def step_device():
-        # u8 images in, score records out: gray256 (luma + CLAHE + bicubic, as train_fusion_head_only.py:142-148)
-        # is derived on the device from the same pixels
-        out = pipe.detect_device(images, None, clahe=True)
-        return distributed.all_gather_records(pipe.pack(out))
+    def unit_images(u: int, src):
+        j = u % local_units
+        return src[j * sub: min(B, (j + 1) * sub)]
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
+    def drain_device(n_units: int, key: str, slab):
+        """This rank's share of a queue of n_units sub-batches, inputs resident in HBM; records land in slab[u]."""
+        q = distributed.WorkQueue(key)
+        inflight, done = [], 0
+        while True:
+            u = q.next()
+            if u >= n_units:
+                break
+            if len(inflight) >= 2:            # keep the host at most two sub-batches ahead of the device
+                inflight.pop(0).synchronize()
+            x = unit_images(u, images)
+            slab[u, : x.shape[0]] = pipe.pack(pipe.detect_device(x, None, clahe=True))
+            ev = torch.cuda.Event()
+            ev.record()
+            inflight.append(ev)
+            done += 1
+        return done
+
+    def gather(slab):
+        # every unit was filled by exactly one rank and is zero elsewhere: a sum over ranks IS the all-gather of the score
+        # records under dynamic ownership (x + 0 is exact) — ONE collective for all steps, not a rendezvous per step
+        if world > 1:
+            distributed.all_reduce_sum_(slab)
+        return slab
+
+    warm = max(args.warmup, 3)
+    slab = torch.zeros((warm * units_per_step, sub, F), dtype=torch.float32, device=dev)
+    drain_device(warm * units_per_step, "dfd_bench_warm", slab)
+    gather(slab)
     torch.cuda.synchronize()
 
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------------
     # every launch of the engine is bracketed by CUDA events on its stream; they are read back once, after the timed region
     # (no host synchronisation between steps)
-    chunks = (B + pipe.engine.max_batch - 1) // pipe.engine.max_batch
-    pipe.engine.profile(args.steps * chunks)
-    fam_ms = {k: 0.0 for k in ("gemm", "attention", "layernorm", "other")}
-    fam_n = dict.fromkeys(fam_ms, 0)
-    sampler = ClockSampler(local) if rank == 0 else None
+    n_units = args.steps * units_per_step
+    slab = torch.zeros((n_units, sub, F), dtype=torch.float32, device=dev)
+    chunks_per_unit = (sub + pipe.engine.max_batch - 1) // pipe.engine.max_batch
+    pipe.engine.profile(n_units * chunks_per_unit)   # room for the case that this rank takes every unit
+    pipe.profile_stages(True)
+    sampler = ClockSampler(local)
     launches0 = lib.dfd_launch_count()
     distributed.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, eb, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
-    for _ in range(args.steps):
-        step_device()
+    mine = drain_device(n_units, "dfd_bench_timed", slab)
+    eb.record()                      # this rank's own kernels end here; what follows is waiting for the others
+    gather(slab)
     e1.record()
     distributed.barrier()
     torch.cuda.synchronize()
-    for k, (ms, n) in pipe.engine.profile_read().items():
-        fam_ms[k] += ms
-        fam_n[k] += n
-    dt = distributed.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
-    launches = (lib.dfd_launch_count() - launches0) // args.steps
-    clocks = sampler.stop() if sampler else None
+    fam = pipe.engine.profile_read()
+    stages = pipe.profile_stages_read()
+    pipe.profile_stages(False)
     pipe.engine.profile(0)
+    dt = distributed.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+    launches = lib.dfd_launch_count() - launches0
+    clocks = sampler.stop()
     value = world * B * args.steps / dt
+    mine_rec = {"rank": rank, "units": mine, "images": mine * sub, "busy_ms": e0.elapsed_time(eb),
+                "wait_ms": eb.elapsed_time(e1), "kernel_ms": sum(v[0] for v in fam.values()) + sum(v[0] for v in stages.values()),
+                "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons")}
+    per_rank = [mine_rec]
+    if world > 1:
+        import torch.distributed as dist
+
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine_rec)
 
     # ---- timed region 2: end to end through the public API, host buffers --------------------------------
+    # DetectionPipeline.detect_many: pinned host images in, numpy score records out; the upload of sub-batch k+1 and the
+    # download of k's records run on a copy stream under k's kernels.  Same work queue.
     h_img = torch.empty((B, S, S, 3), dtype=torch.uint8).pin_memory()
     h_img.copy_(images)
 
-    def step_host():
-        rec = pipe.detect(h_img, None, clahe=True)   # H2D (pinned) + kernels + D2H of the packed score records
-        if world > 1:
-            distributed.all_gather_records(torch.from_numpy(rec).to(dev))
-        return rec
+    def drain_host(n: int, key: str):
+        q = distributed.WorkQueue(key)
+        taken = []
 
-    for _ in range(2):
-        step_host()
+        def feed():
+            while True:
+                u = q.next()
+                if u >= n:
+                    return
+                taken.append(u)
+                yield unit_images(u, h_img)
+
+        recs = pipe.detect_many(feed(), clahe=True)
+        out = torch.zeros((n, sub, F), dtype=torch.float32)
+        for u, r in zip(taken, recs):
+            out[u, : r.shape[0]] = torch.from_numpy(r)
+        if world > 1:   # the all-gather of the records (dynamic ownership, see gather())
+            out = gather(out.to(dev)).cpu()
+        return out, sum(r.shape[0] for r in recs)
+
+    drain_host(2 * units_per_step, "dfd_bench_e2e_warm")
     distributed.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        rec = step_host()
-    e1.record()
+    rec, n_mine = drain_host(n_units, "dfd_bench_e2e")
     torch.cuda.synchronize()
+    dt_e2e = distributed.max_over_ranks(time.perf_counter() - t0, dev)
     distributed.barrier()
-    dt_e2e = distributed.max_over_ranks(max(e0.elapsed_time(e1) / 1e3, time.perf_counter() - t0), dev)
     e2e_value = world * B * args.steps / dt_e2e
-    h2d = h_img.numel()
-    d2h = rec.size * 4
+    # bytes this rank moved per step (rank 0's share; the ranks' shares differ by the dynamic split)
+    h2d = n_mine * S * S * 3 // args.steps
+    d2h = n_mine * F * 4 // args.steps
 
     if rank != 0:
         return
-    gemm_flops = pipe.engine.gemm_flops(B) * args.steps
-    roof = None
-    if fam_ms["gemm"] > 0:
-        ach = gemm_flops / (fam_ms["gemm"] / 1e3) / 1e12
+    step_ms = dt / args.steps * 1e3
+    busy_ms = mine_rec["busy_ms"]
+    my_images = max(mine * sub, 1)
+    roof, hbm = None, []
+    if fam["gemm"][0] > 0:
+        gemm_flops = pipe.engine.gemm_flops(1) * my_images
+        ach = gemm_flops / (fam["gemm"][0] / 1e3) / 1e12
         peak = float(peaks["bf16_tflops_sustained"])
-        step_ms = dt / args.steps * 1e3
-        roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of the step)",
+        shares = {k: v[0] / busy_ms for k, v in fam.items()}
+        shares.update({k: v[0] / busy_ms for k, v in stages.items()})
+        roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of rank 0 in the timed region)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
-                "launches_per_step": fam_n["gemm"] // args.steps,
-                "avg_launch_ms": fam_ms["gemm"] / max(fam_n["gemm"], 1),
-                "traffic": args.gemm_traffic if args.gemm_traffic is not None else load_traffic(),
-                "share_of_step": {k: fam_ms[k] / args.steps / step_ms for k in fam_ms}}
+                "launches_per_step": fam["gemm"][1] // args.steps, "avg_launch_ms": fam["gemm"][0] / max(fam["gemm"][1], 1),
+                "traffic": args.gemm_traffic,
+                "traffic_note": "dram bytes are not measurable inside a plain run: pass --gemm-traffic from the ncu capture of "
+                                "this command (scripts/collect_profiles.sh -> profiles/); committed capture: "
+                                f"{load_traffic()} B per GEMM launch",
+                "share_of_rank0_busy_time": shares}
+        att_flops = 4.0 * arch.tokens ** 2 * arch.hidden_size * arch.num_hidden_layers * my_images
+        if fam["attention"][0] > 0:
+            a = att_flops / (fam["attention"][0] / 1e3) / 1e12
+            roof["attention"] = {"kernel": "attention_dq_kernel", "achieved": a, "peak": peak, "unit": "TFLOP/s",
+                                 "frac": a / peak, "avg_launch_ms": fam["attention"][0] / max(fam["attention"][1], 1)}
+        # memory-bound kernels: algorithmic bytes per call (SURVEY.md §8d) / CUDA-event time, against the measured copy rate
+        hb = float(peaks["hbm_gbs"])
+        N, D, Kp = arch.tokens, arch.hidden_size, (3 * arch.patch_size ** 2 + 63) // 64 * 64
+        nb = min(sub, pipe.engine.max_batch)
+        for e in (hbm_entry("patchify_u8_rows_kernel", nb * (3 * S * S + N * Kp * 2), *fam["patchify"], hb),
+                  hbm_entry("map_attention_kernel", nb * N * 2 * D * 2, *fam["map_attention"], hb),
+                  hbm_entry("layernorm_bf16_kernel (post-LN of all tokens + the pooling head's LN)",
+                            (nb * N + nb) * D * 4 / 2, *fam["layernorm"], hb),
+                  hbm_entry("gray256: luma + clahe_lut + clahe_apply + resample_rows + resample_cols",
+                            sub * (3 * S * S + 256 * 256 * 4), *stages.get("gray256", (0, 0)), hb),
+                  hbm_entry("freq_rows_kernel + freq_cols_kernel", sub * (256 * 256 * 4 + 96), *stages.get("freq", (0, 0)), hb)):
+            if e:
+                hbm.append(e)
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "warmup": warm, "ms_per_step": step_ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {arch_name} detect (backbone+H-B head+gray256/CLAHE+freq features+G2 fusion+CORAL)",
                    "per_gpu_batch": B, "global_batch": B * world, "tokens": arch.tokens, "parallelism": f"dp{world}",
-                   "l2": "per-step inputs (226 MB of u8 images) and activations are >> the 126 MB L2; no flush needed",
+                   "sub_batch": sub, "schedule": "one call per step" if world == 1 else
+                   f"work queue of {units_per_step} sub-batches per step shared by the ranks; one all-reduce(sum) of the zero-filled "
+                   "record slab (= all-gather under dynamic ownership) after the last step",
+                   "l2": f"per-step inputs ({B * S * S * 3 / 1e6:.0f} MB of u8 images) and activations are >> the 126 MB L2; no flush needed",
                    "weights": "random init (seeded), bf16", "fuse_ln": bool(args.fuse_ln)},
         "tensor_pipe_frac_of_step": arch.flops_per_image() * value / world / 1e12 / float(peaks["bf16_tflops_sustained"]),
-        "clocks": clocks,
+        "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": dt_e2e / args.steps * 1e3},
-        "gpu_launches": int(launches),
+                "ms_per_step": dt_e2e / args.steps * 1e3, "api": "DetectionPipeline.detect_many (pinned host u8 in, numpy records out)"},
+        "gpu_launches": int(launches // args.steps),
         "roofline": roof,
+        "roofline_hbm": hbm,
+        "per_rank": per_rank,
     }
     if world == 1 and not args.no_cpu_baseline:
         ref = CpuReference(args.workload)
@@ -324,8 +417,10 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="so400m-384")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--max-batch", type=int, default=512, help="engine workspace batch (larger batches are chunked)")
+    ap.add_argument("--sub-batch", type=int, default=0,
+                    help="images per work-queue unit (default: the whole batch on one GPU, a quarter of it on several)")
     ap.add_argument("--gemm-traffic", type=float, default=None,
-                    help="dram bytes per GEMM launch from an ncu --set full capture (profiles/), else null")
+                    help="dram bytes per GEMM launch from an ncu --set full capture of this command, else null")
     ap.add_argument("--fuse-ln", type=int, default=1, help="1 = LayerNorm folded into the qkv/fc1 GEMMs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -135,6 +135,7 @@ SIGNATURES = {
     "dfd_engine_set_hidden_tap": (_I, [_P, _P]),
     "dfd_engine_profile": (_I, [_P, _I]),
     "dfd_engine_profile_read": (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "dfd_engine_profile_read_families": (_I, [_P, _I, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
 }
 
 _lib = None

@@ -76,8 +76,10 @@ int layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const float
 int rowstats_bf16(const void* x, int64_t ldx, float* stats, int M, int D, cudaStream_t st);
 int patchify(const void* pixels, int pix_format, int B, int Hin, int Win, int S, int P, int resize_mode,
              void* A, int64_t lda, cudaStream_t st);
+// attention_dq variant = 100 * poly + handoff (see attention_dq.cu)
+constexpr int kDqVariantDefault = 416;
 int attention_dq_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
-                      float scale, cudaStream_t st);
+                      float scale, cudaStream_t st, int variant = kDqVariantDefault);
 int attention_auto_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,
                         float scale, cudaStream_t st);
 int attention_ws_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int B, int N, int H, int hd,

@@ -114,7 +114,7 @@ struct dfd_engine {
   void* staging;
   int64_t staging_bytes;
   // optional per-launch CUDA-event timing of the forward (bench.py roofline): family 0 GEMM, 1 attention,
-  // 2 LayerNorm, 3 other (patchify, MAP attention)
+  // 2 LayerNorm, 3 patchify, 4 MAP attention
   bool prof_on;
   std::vector<cudaEvent_t> prof_ev;
   std::vector<int> prof_fam;
@@ -483,20 +483,27 @@ extern "C" DFD_API int dfd_engine_profile(dfd_engine* e, int enable) {
 
 // Sums the event-timed durations of every launch recorded since the last read (or since profiling was switched on) per
 // kernel family (ms) and the launch counts, then clears the record.  Synchronises on the last recorded event.
-extern "C" DFD_API int dfd_engine_profile_read(dfd_engine* e, float* ms4, int* count4) {
-  DFD_REQUIRE(e && ms4 && count4, DFD_ERR_BAD_ARG, "profile_read: null pointer");
+// Families: 0 GEMM, 1 attention, 2 LayerNorm, 3 patchify, 4 MAP attention; n < 5 folds the higher ones into family n - 1.
+extern "C" DFD_API int dfd_engine_profile_read_families(dfd_engine* e, int n, float* ms, int* count) {
+  DFD_REQUIRE(e && ms && count && n > 0, DFD_ERR_BAD_ARG, "profile_read: null pointer");
   DeviceGuard guard(e->device);
-  for (int i = 0; i < 4; ++i) { ms4[i] = 0.f; count4[i] = 0; }
+  for (int i = 0; i < n; ++i) { ms[i] = 0.f; count[i] = 0; }
   if (e->prof_n == 0) return DFD_OK;
   DFD_CUDA(cudaEventSynchronize(e->prof_ev[2 * e->prof_n - 1]));
   for (int i = 0; i < e->prof_n; ++i) {
-    float ms = 0.f;
-    DFD_CUDA(cudaEventElapsedTime(&ms, e->prof_ev[2 * i], e->prof_ev[2 * i + 1]));
-    ms4[e->prof_fam[i] & 3] += ms;
-    count4[e->prof_fam[i] & 3] += 1;
+    float t = 0.f;
+    DFD_CUDA(cudaEventElapsedTime(&t, e->prof_ev[2 * i], e->prof_ev[2 * i + 1]));
+    const int f = e->prof_fam[i] < n ? e->prof_fam[i] : n - 1;
+    ms[f] += t;
+    count[f] += 1;
   }
   e->prof_n = 0;
   return DFD_OK;
+}
+
+// the four-family form of round 1: GEMM, attention, LayerNorm, other (patchify + MAP attention)
+extern "C" DFD_API int dfd_engine_profile_read(dfd_engine* e, float* ms4, int* count4) {
+  return dfd_engine_profile_read_families(e, 4, ms4, count4);
 }
 
 extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int pix_format, int B, int Hin,
@@ -596,7 +603,7 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
     ep.bias = e->b_in + D;
     DFD_OP(0, gemm_bf16_dispatch(xp, D, e->w_in + (int64_t)D * D, D, e->qkv, 2 * D, M, 2 * D, D, &ep, 0, st));
   }
-  DFD_OP(3, map_attention_bf16(e->qkv, 2 * D, e->q_probe, e->ao, D, B, N, H, hd, scale, st));
+  DFD_OP(4, map_attention_bf16(e->qkv, 2 * D, e->q_probe, e->ao, D, B, N, H, hd, scale, st));
   {
     dfd_gemm_epilogue ep{};
     ep.bias = e->b_mo;

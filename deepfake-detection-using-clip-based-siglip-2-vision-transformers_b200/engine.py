@@ -250,12 +250,15 @@ class SiglipEngine:
         forwards the event buffer holds before profile_read() must be called; 0 / False switches profiling off."""
         check(self._lib.dfd_engine_profile(self._h, int(forwards)))
 
+    FAMILIES = ("gemm", "attention", "layernorm", "patchify", "map_attention")
+
     def profile_read(self) -> dict:
         """Per kernel family, summed over every forward since the last read: {'gemm': (ms, launches), 'attention': ...,
-        'layernorm': ..., 'other': ...}.  Waits for the last recorded launch."""
-        ms, cnt = (C.c_float * 4)(), (C.c_int * 4)()
-        check(self._lib.dfd_engine_profile_read(self._h, ms, cnt))
-        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("gemm", "attention", "layernorm", "other"))}
+        'layernorm': ..., 'patchify': ..., 'map_attention': ...}.  Waits for the last recorded launch."""
+        n = len(self.FAMILIES)
+        ms, cnt = (C.c_float * n)(), (C.c_int * n)()
+        check(self._lib.dfd_engine_profile_read_families(self._h, n, ms, cnt))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.FAMILIES)}
 
     def gemm_flops(self, batch: int) -> float:
         """Algorithmic FLOPs of all GEMM launches of one forward of `batch` images (2·M·N·K each; the

@@ -281,6 +281,8 @@ def gray256_from_rgb(images: torch.Tensor, clahe: bool, scratch: Optional[torch.
     before handing pixels over, as the reference does)."""
     _need_cuda(images)
     assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[3] == 3 and images.is_contiguous()
+    if images.data_ptr() % 4:   # a contiguous row slice of a larger image (full-width crop) may start at any byte
+        images = images.clone()
     B, H, W, _ = images.shape
     lib = _lib.load()
     need = lib.dfd_gray256_scratch_bytes(B, H, W)

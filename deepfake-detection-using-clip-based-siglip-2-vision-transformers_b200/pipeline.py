@@ -67,6 +67,33 @@ class DetectionPipeline:
         self.freq = FreqFeatureExtractor(self.device, eps=freq_eps, zscore=zs)
         self._pin: Dict[str, torch.Tensor] = {}
         self._gray_scratch: Optional[torch.Tensor] = None
+        self._stage_ev = None    # measurement aid (bench.py): CUDA events around the non-backbone stages
+
+    # ---- measurement aid: per-stage CUDA-event timing of the kernels outside the engine --------------------------------
+    def profile_stages(self, enable: bool = True) -> None:
+        self._stage_ev = [] if enable else None
+
+    def profile_stages_read(self) -> Dict[str, tuple]:
+        """{'head' | 'gray256' | 'freq' | 'score': (ms, calls)} since profiling was switched on; clears the record."""
+        out: Dict[str, list] = {}
+        if self._stage_ev:
+            self._stage_ev[-1][2].synchronize()
+            for name, a, b in self._stage_ev:
+                acc = out.setdefault(name, [0.0, 0])
+                acc[0] += a.elapsed_time(b)
+                acc[1] += 1
+            self._stage_ev = []
+        return {k: (v[0], v[1]) for k, v in out.items()}
+
+    def _stage(self, name, fn):
+        if self._stage_ev is None:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        self._stage_ev.append((name, a, b))
+        return r
 
     # ---- device-resident path ---------------------------------------------------------------------
     def detect_device(self, images: torch.Tensor, gray256: Optional[torch.Tensor] = None, resize_mode: int = 0,
@@ -80,14 +107,14 @@ class DetectionPipeline:
         if pil_resize is not None and tuple(images.shape[1:3]) != (S, S):
             model_in = ops.resize_u8(images, S, S, pil_resize)
         pooled, _ = self.engine(model_in, resize_mode=resize_mode)
-        _, z_sig, _ = ops.head_fwd(self.head, pooled)
+        _, z_sig, _ = self._stage("head", lambda: ops.head_fwd(self.head, pooled))
         if gray256 is None:
             need = ops._lib.load().dfd_gray256_scratch_bytes(*images.shape[:3])
             if self._gray_scratch is None or self._gray_scratch.numel() < need:
                 self._gray_scratch = torch.empty((need,), dtype=torch.uint8, device=self.device)
-            gray256 = ops.gray256_from_rgb(images, clahe, scratch=self._gray_scratch)
-        feats = self.freq.from_gray(gray256)
-        out = self.scoring(z_sig, feats=feats)
+            gray256 = self._stage("gray256", lambda: ops.gray256_from_rgb(images, clahe, scratch=self._gray_scratch))
+        feats = self._stage("freq", lambda: self.freq.from_gray(gray256))
+        out = self._stage("score", lambda: self.scoring(z_sig, feats=feats))
         out["pooled"] = pooled
         return out
 

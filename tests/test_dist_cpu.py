@@ -60,6 +60,20 @@ def _worker(rank, world, port, q):
     res["fgrad_err"] = float(np.abs(fb[:-1].numpy() - gf_full).max())
     res["floss_err"] = abs(float(fb[-1]) - lf_full)
     res["max"] = distributed.max_over_ranks(float(rank + 1), "cpu")
+    # 5. work queue: the ranks drain 23 units between them, each unit exactly once; the records of a unit are written by its
+    #    owner into a zero-filled slab and ONE sum over ranks reassembles them (bench.py's dynamic all-gather)
+    wq = distributed.WorkQueue("test_queue")
+    slab = torch.zeros(23, 3)
+    taken = []
+    while True:
+        u = wq.next()
+        if u >= 23:
+            break
+        taken.append(u)
+        slab[u] = torch.tensor([u + 0.25, rank, 1.0])
+    distributed.all_reduce_sum_(slab)
+    res["queue_ok"] = bool(torch.equal(slab[:, 0], torch.arange(23.0) + 0.25)) and bool((slab[:, 2] == 1.0).all())
+    res["queue_taken"] = taken
     distributed.barrier()
     q.put((rank, res))
     dist.destroy_process_group()
@@ -81,6 +95,15 @@ def test_gloo_world2():
         assert out[r]["grad_err"] < 1e-12 and out[r]["loss_err"] < 1e-12
         assert out[r]["fgrad_err"] < 1e-12 and out[r]["floss_err"] < 1e-12
         assert out[r]["max"] == 2.0
+        assert out[r]["queue_ok"]
+    assert sorted(out[0]["queue_taken"] + out[1]["queue_taken"]) == list(range(23))
+
+
+def test_work_queue_without_process_group_is_a_local_counter():
+    from dfd import distributed
+
+    q = distributed.WorkQueue("solo")
+    assert [q.next() for _ in range(4)] == [0, 1, 2, 3]
 
 
 def test_shard_bounds_cover_everything():

@@ -352,7 +352,7 @@ def _ref_attention(qkv, B, N, H, hd):
 @pytest.mark.parametrize("B,N,H,hd", [(2, 196, 12, 64), (1, 729, 16, 72), (3, 16, 2, 64), (2, 16, 2, 72),
                                       (2, 225, 4, 72), (1, 1024, 2, 72), (2, 64, 1, 64), (1, 129, 3, 64), (1, 1, 2, 72),
                                       (40, 576, 16, 64), (330, 100, 1, 72)])
-@pytest.mark.parametrize("impl", [None, 5, 2])  # product dispatch; dual-query-tile and single-tile persistent tcgen05 kernels
+@pytest.mark.parametrize("impl", [None, 5, 6, 7, 2])  # product dispatch; dual-query-tile (exponentials on MUFU only / every 3rd / 4th pair on the FMA pipe); single-tile persistent
 def test_attention(B, N, H, hd, impl):
     from dfd import ops
 
@@ -378,7 +378,7 @@ def test_attention_large_logits():
     qkv[N - 40:N, H * hd:2 * H * hd] *= 8.0                  # late keys dominate -> the running max jumps
     qkv = _bf(qkv).to(DEV)
     ref = _ref_attention(qkv, B, N, H, hd)
-    for impl in (None, 5, 2):
+    for impl in (None, 5, 6, 7, 2):
         out = ops.attention_bf16(qkv, B, N, H, hd, impl=impl)
         torch.cuda.synchronize()
         assert torch.isfinite(out.float()).all()
