@@ -219,7 +219,8 @@ def run_ours(args):
     bsd = weights.random_vision_state_dict(arch, seed=0, device=dev)
     st = scoring.ScoringStack(dev, weights.random_freq_mlp_g2(2), weights.random_fusion_g2(3), [-1.0, -0.2, 0.3, 1.5], 1.0)
     pipe = pipeline.DetectionPipeline(arch, bsd, weights.random_classifier_head("B", arch.hidden_size, 1), st,
-                                      device=local, max_batch=min(sub, args.max_batch), fuse_ln=bool(args.fuse_ln))
+                                      device=local, max_batch=min(sub, args.max_batch), fuse_ln=bool(args.fuse_ln),
+                                      precise_residual=bool(args.precise_residual))
     del bsd
     S = arch.image_size
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -388,7 +389,8 @@ def run_ours(args):
                    f"work queue of {units_per_step} sub-batches per step shared by the ranks; one all-reduce(sum) of the zero-filled "
                    "record slab (= all-gather under dynamic ownership) after the last step",
                    "l2": f"per-step inputs ({B * S * S * 3 / 1e6:.0f} MB of u8 images) and activations are >> the 126 MB L2; no flush needed",
-                   "weights": "random init (seeded), bf16", "fuse_ln": bool(args.fuse_ln)},
+                   "weights": "random init (seeded), bf16", "fuse_ln": bool(args.fuse_ln),
+                   "residual_stream": "two bf16 tensors (hi + lo)" if args.precise_residual else "bf16"},
         "tensor_pipe_frac_of_step": arch.flops_per_image() * value / world / 1e12 / float(peaks["bf16_tflops_sustained"]),
         "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -408,13 +410,150 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Auxiliary workloads (BASELINE.json configs 4 and 5, and the small-batch latency a serving caller sees).  Not the driver's
+# headline: each prints one JSON line with its own metric; numbers land in profiles/ via scripts/collect_profiles.sh.
+# ---------------------------------------------------------------------------------------------------------
+def _event_ms(fn, iters, warm=3):
+    import torch
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / iters
+
+
+def run_latency(args):
+    """Small-batch latency of the whole detection step (what detect_core issues per upload: 1 view, the 6 views of
+    deepfake-detector-v2/app.py:1418-1430, the 9 crops of appv3.py:3315-3350), eager launches vs CUDA-graph replay."""
+    import torch
+
+    from dfd import _lib, pipeline, scoring, weights
+    from dfd.engine import ARCHS
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    out = {}
+    for wl in ("base-224", "so400m-384"):
+        arch = ARCHS[WORKLOADS[wl][0]]
+        bsd = weights.random_vision_state_dict(arch, seed=0, device=dev)
+        st = scoring.ScoringStack(dev, weights.random_freq_mlp_g2(2), weights.random_fusion_g2(3), [-1.0, -0.2, 0.3, 1.5], 1.0)
+        pipe = pipeline.DetectionPipeline(arch, bsd, weights.random_classifier_head("B", arch.hidden_size, 1), st, device=0,
+                                          max_batch=64, fuse_ln=True)
+        del bsd
+        S = arch.image_size
+        for B in (1, 6, 9, 32):
+            x = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8, device=dev)
+            row = {}
+            for mode in ("eager", "graph"):
+                pipe.engine.set_graphs(mode == "graph")
+                r0 = pipe.engine.graph_replays
+                ms = _event_ms(lambda: pipe.pack(pipe.detect_device(x, None, clahe=True)), iters=max(args.steps, 20))
+                row[mode + "_ms"] = ms
+                if mode == "graph":
+                    row["graph_replays"] = pipe.engine.graph_replays - r0
+            row["images_per_s_graph"] = B / row["graph_ms"] * 1e3
+            out[f"{wl}/B={B}"] = row
+        pipe.engine.close()
+        del pipe
+    print(json.dumps({"metric": "detection step latency, small batches (u8 images resident in HBM -> score records on the device)",
+                      "unit": "ms", "value": out["so400m-384/B=6"]["graph_ms"], "higher_is_better": False, "n_gpus": 1,
+                      "steps": max(args.steps, 20), "warmup": 3, "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": "latency: 1 / 6 / 9 / 32 views per call, base-224 and so400m-384, eager vs CUDA graph"},
+                      "gpu_launches": int(_lib.load().dfd_launch_count()), "table": out}), flush=True)
+
+
+def run_cifake(args):
+    """BASELINE config 4: 32x32 u8 images resampled to 224 inside the patch kernel (cifake_binary_classifier.py:714-749),
+    base-patch16-224 backbone + head H-D, batch sweep."""
+    import torch
+
+    from dfd import _lib, cifake, dropin, weights
+    from dfd.engine import ARCHS
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    name = WORKLOADS["base-224"][0]
+    model = dropin.FastBinaryClassifier("small", device=dev, arch=name, max_batch=1024,
+                                        head_state=weights.random_fast_classifier_head("small", ARCHS[name].hidden_size))
+    sweep = cifake.throughput_sweep(model, batches=(256, 512, 1024, 2048, 4096, 8192), side=32, iters=max(args.steps, 3))
+    best = max(sweep, key=sweep.get)
+    arch = model.arch
+    peaks = load_peaks()
+    print(json.dumps({"metric": "images/sec CiFake 32->224 binary classifier (FastBinaryClassifier, base-patch16-224)",
+                      "unit": "images/s", "value": sweep[best], "higher_is_better": True, "n_gpus": 1, "steps": max(args.steps, 3),
+                      "warmup": 1, "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": "cifake: 32x32 u8 -> bilinear 224 in the patch kernel -> backbone -> head H-D",
+                                 "best_batch": best, "engine_max_batch": 1024},
+                      "tensor_pipe_frac": arch.flops_per_image() * sweep[best] / 1e12 / float(peaks["bf16_tflops_sustained"]),
+                      "gpu_launches": int(_lib.load().dfd_launch_count()),
+                      "sweep": {str(k): v for k, v in sweep.items()}}), flush=True)
+
+
+def run_head_train(args):
+    """BASELINE config 5: head-only training steps (train_fusion_head_only.py:406-453) on cached logits — fused forward/backward
+    kernel, ONE all-reduce of the 196-float bucket over NCCL, clip + AdamW on every rank — and the FreqMLP trainer's step
+    (6 495-float bucket).  Global batch 32 / 128 as in the reference scripts, sharded over the ranks."""
+    import numpy as np
+    import torch
+
+    from dfd import _lib, distributed, train_freq, train_fusion
+
+    rank, world, local = distributed.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    rng = np.random.default_rng(0)
+    n = 32 * 64
+    y = torch.from_numpy((rng.random(n) > 0.5).astype(np.float32))
+    zs = torch.from_numpy((rng.normal(0, 2, n) + 2.0 * (y.numpy() - 0.5)).astype(np.float32))
+    zf = torch.from_numpy((rng.normal(0, 2, n) + 1.0 * (y.numpy() - 0.5)).astype(np.float32))
+    feats = torch.from_numpy((rng.normal(0.2, 0.7, (n, 24)) + 0.6 * (y.numpy()[:, None] - 0.5)).astype(np.float32))
+    torch.manual_seed(11)
+    t0 = time.perf_counter()
+    train_fusion.fit_fusion_head(zf, zs, y, batch_size=32, epochs=1, device=dev, verbose=False)       # warm-up epoch
+    torch.cuda.synchronize()
+    epochs = max(args.steps, 3)
+    t0 = time.perf_counter()
+    train_fusion.fit_fusion_head(zf, zs, y, batch_size=32, epochs=epochs, device=dev, verbose=False)
+    torch.cuda.synchronize()
+    dt_fusion = time.perf_counter() - t0
+    torch.manual_seed(5)
+    train_freq.fit_freq_mlp(feats, y, epochs=1, batch_size=128, lr=1e-3, device=dev, dropout=0.0, verbose=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    train_freq.fit_freq_mlp(feats, y, epochs=epochs, batch_size=128, lr=1e-3, device=dev, dropout=0.0, verbose=False)
+    torch.cuda.synchronize()
+    dt_freq = time.perf_counter() - t0
+    dt_fusion = distributed.max_over_ranks(dt_fusion, dev)
+    dt_freq = distributed.max_over_ranks(dt_freq, dev)
+    if rank == 0:
+        steps_fusion, steps_freq = epochs * (n // 32), epochs * (n // 128)
+        print(json.dumps({"metric": "head-only training steps/sec (fusion head, global batch 32, all-reduce of 196 floats)",
+                          "unit": "steps/s", "value": steps_fusion / dt_fusion, "higher_is_better": True, "n_gpus": world,
+                          "steps": steps_fusion, "warmup": n // 32, "dtype": "f32", "data": "synthetic", "scaling": "strong",
+                          "config": {"workload": "head-train: fit_fusion_head + fit_freq_mlp on cached logits / features, "
+                                                 "including the per-epoch evaluation pass, host loop timed by wall clock"},
+                          "freq_mlp_steps_per_s": steps_freq / dt_freq, "freq_mlp_bucket_floats": 6495,
+                          "us_per_fusion_step": dt_fusion / steps_fusion * 1e6, "us_per_freq_step": dt_freq / steps_freq * 1e6,
+                          "gpu_launches": int(_lib.load().dfd_launch_count())}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="so400m-384")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["latency", "cifake", "head-train"], default="so400m-384",
+                    help="so400m-384 (the driver's headline, BASELINE configs[2]) | base-224 (configs[1]) | latency | cifake "
+                         "(configs[3]) | head-train (configs[4])")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--max-batch", type=int, default=512, help="engine workspace batch (larger batches are chunked)")
     ap.add_argument("--sub-batch", type=int, default=0,
@@ -422,10 +561,21 @@ def main():
     ap.add_argument("--gemm-traffic", type=float, default=None,
                     help="dram bytes per GEMM launch from an ncu --set full capture of this command, else null")
     ap.add_argument("--fuse-ln", type=int, default=1, help="1 = LayerNorm folded into the qkv/fc1 GEMMs")
+    ap.add_argument("--precise-residual", type=int, default=0,
+                    help="1 = two-bf16 residual stream (dfd_engine_set_precise_residual): the reference's fp32 residual "
+                         "accumulation, a few percent slower; 0 = the default bf16 stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.workload not in WORKLOADS:
+            raise SystemExit("--impl reference covers the so400m-384 and base-224 workloads")
         run_reference_arm(args)
+    elif args.workload == "latency":
+        run_latency(args)
+    elif args.workload == "cifake":
+        run_cifake(args)
+    elif args.workload == "head-train":
+        run_head_train(args)
     else:
         run_ours(args)
     try:

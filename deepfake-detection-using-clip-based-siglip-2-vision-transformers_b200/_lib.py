@@ -35,6 +35,8 @@ class GemmEpilogue(C.Structure):
         ("stats_out", C.c_void_p),
         ("residual_op", C.c_int),
         ("ln_parts", C.c_int),
+        ("residual_lo", C.c_void_p),
+        ("ldlo", C.c_int64),
     ]
 
 
@@ -105,6 +107,7 @@ SIGNATURES = {
     "dfd_gemm_variant_launches": (_L, [_I]),
     "dfd_gemm_bf16_tile": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, C.POINTER(GemmEpilogue), _I, _P]),
     "dfd_layernorm_bf16": (_I, [_P, _L, _P, _L, _P, _P, _I, _I, _F, _P]),
+    "dfd_layernorm2_bf16": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _I, _I, _F, _P]),
     "dfd_rowstats_bf16": (_I, [_P, _L, _P, _I, _I, _P]),
     "dfd_attention_bf16": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _F, _P]),
     "dfd_attention_bf16_impl": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _F, _I, _P]),
@@ -133,6 +136,9 @@ SIGNATURES = {
     "dfd_engine_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "dfd_engine_workspace_bytes": (_L, [_P]),
     "dfd_engine_set_hidden_tap": (_I, [_P, _P]),
+    "dfd_engine_set_graphs": (_I, [_P, _I]),
+    "dfd_engine_set_precise_residual": (_I, [_P, _I]),
+    "dfd_engine_graph_replays": (C.c_int64, [_P]),
     "dfd_engine_profile": (_I, [_P, _I]),
     "dfd_engine_profile_read": (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "dfd_engine_profile_read_families": (_I, [_P, _I, C.POINTER(C.c_float), C.POINTER(C.c_int)]),

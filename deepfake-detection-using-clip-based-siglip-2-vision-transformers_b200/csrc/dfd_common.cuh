@@ -72,7 +72,8 @@ inline int ensure_dynamic_smem(SmemOptIn& once, F func, int bytes) {
 int gemm_bf16_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
                        int M, int N, int K, const dfd_gemm_epilogue* epi, int force_bn, cudaStream_t st);
 int layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,
-                   const float* beta, int M, int D, float eps, cudaStream_t st);
+                   const float* beta, int M, int D, float eps, cudaStream_t st, const void* lo = nullptr,
+                   int64_t ldlo = 0);
 int rowstats_bf16(const void* x, int64_t ldx, float* stats, int M, int D, cudaStream_t st);
 int patchify(const void* pixels, int pix_format, int B, int Hin, int Win, int S, int P, int resize_mode,
              void* A, int64_t lda, cudaStream_t st);

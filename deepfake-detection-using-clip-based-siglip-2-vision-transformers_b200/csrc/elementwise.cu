@@ -19,24 +19,43 @@ namespace {
 constexpr int kRowThreads = 256;  // 8 warps = 8 rows per CTA
 constexpr int kMaxVec = 8;        // rows up to 8*32*8 = 2048 elements stay in registers
 
+// elements 2j, 2j+1 of a 16-byte vector of a row (plus those of its low half)
+template <bool LO>
+__device__ __forceinline__ float2 ln_val(const uint4& hi, const uint4& lo, int j) {
+  const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w};
+  float2 a = unpack_bf16x2(h[j]);
+  if (LO) {
+    const uint32_t l[4] = {lo.x, lo.y, lo.z, lo.w};
+    const float2 b = unpack_bf16x2(l[j]);
+    a.x += b.x;
+    a.y += b.y;
+  }
+  return a;
+}
+
+// LO: the row is the sum of two bf16 tensors (x + lo: the two-bf16 residual stream of the precise engine mode)
+template <bool LO>
 __global__ void __launch_bounds__(kRowThreads)
-layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y,
-                      int64_t ldy, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      int M, int D, float eps) {
+layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ lo, int64_t ldlo,
+                      __nv_bfloat16* __restrict__ y, int64_t ldy, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, int M, int D, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (kRowThreads / 32) + warp;
   if (row >= M) return;
   const int nvec = D >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)row * ldx);
-  uint4 v[kMaxVec];
+  const uint4* lr = LO ? reinterpret_cast<const uint4*>(lo + (int64_t)row * ldlo) : nullptr;
+  uint4 v[kMaxVec], w[LO ? kMaxVec : 1];
+  w[0] = make_uint4(0u, 0u, 0u, 0u);
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i) {
     const int c = lane + i * 32;
     if (c < nvec) {
       v[i] = __ldg(xr + c);
-      const float2 a = unpack_bf16x2(v[i].x), b = unpack_bf16x2(v[i].y), c2 = unpack_bf16x2(v[i].z),
-                   d = unpack_bf16x2(v[i].w);
+      if (LO) w[i] = __ldg(lr + c);
+      const float2 a = ln_val<LO>(v[i], w[LO ? i : 0], 0), b = ln_val<LO>(v[i], w[LO ? i : 0], 1), c2 = ln_val<LO>(v[i], w[LO ? i : 0], 2),
+                   d = ln_val<LO>(v[i], w[LO ? i : 0], 3);
       sum += ((a.x + a.y) + (b.x + b.y)) + ((c2.x + c2.y) + (d.x + d.y));
     }
   }
@@ -46,10 +65,9 @@ layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfl
   for (int i = 0; i < kMaxVec; ++i) {
     const int c = lane + i * 32;
     if (c < nvec) {
-      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 a = unpack_bf16x2(w[j]);
+        const float2 a = ln_val<LO>(v[i], w[LO ? i : 0], j);
         const float d0 = a.x - mean, d1 = a.y - mean;
         sq += d0 * d0 + d1 * d1;
       }
@@ -65,8 +83,8 @@ layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfl
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c);
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c + 1);
-      const float2 a = unpack_bf16x2(v[i].x), b = unpack_bf16x2(v[i].y), c2 = unpack_bf16x2(v[i].z),
-                   d = unpack_bf16x2(v[i].w);
+      const float2 a = ln_val<LO>(v[i], w[LO ? i : 0], 0), b = ln_val<LO>(v[i], w[LO ? i : 0], 1), c2 = ln_val<LO>(v[i], w[LO ? i : 0], 2),
+                   d = ln_val<LO>(v[i], w[LO ? i : 0], 3);
       uint4 o;
       o.x = pack_bf16x2((a.x - mean) * rstd * g0.x + b0.x, (a.y - mean) * rstd * g0.y + b0.y);
       o.y = pack_bf16x2((b.x - mean) * rstd * g0.z + b0.z, (b.y - mean) * rstd * g0.w + b0.w);
@@ -239,17 +257,24 @@ __global__ void __launch_bounds__(256) patchify_u8_rows_kernel(PatchArgs a) {
 }  // namespace
 
 int layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,
-                   const float* beta, int M, int D, float eps, cudaStream_t st) {
+                   const float* beta, int M, int D, float eps, cudaStream_t st, const void* lo, int64_t ldlo) {
   DFD_REQUIRE(x && y && gamma && beta, DFD_ERR_BAD_ARG, "layernorm: null pointer");
   DFD_REQUIRE(M > 0 && D > 0, DFD_ERR_SHAPE, "layernorm: M and D must be positive");
   DFD_REQUIRE(D % 8 == 0 && D <= kMaxVec * 256, DFD_ERR_SHAPE,
               "layernorm: D must be a multiple of 8 and <= %d (D=%d)", kMaxVec * 256, D);
   DFD_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= D && ldy >= D, DFD_ERR_SHAPE,
               "layernorm: leading dimensions must be multiples of 8 and >= D");
+  DFD_REQUIRE(lo == nullptr || (ldlo % 8 == 0 && ldlo >= D), DFD_ERR_SHAPE, "layernorm: bad leading dimension of lo");
   const int rows_per_cta = kRowThreads / 32;
-  layernorm_bf16_kernel<<<(M + rows_per_cta - 1) / rows_per_cta, kRowThreads, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, gamma,
-      beta, M, D, eps);
+  const int grid = (M + rows_per_cta - 1) / rows_per_cta;
+  if (lo != nullptr)
+    layernorm_bf16_kernel<true><<<grid, kRowThreads, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<const __nv_bfloat16*>(lo), ldlo,
+        reinterpret_cast<__nv_bfloat16*>(y), ldy, gamma, beta, M, D, eps);
+  else
+    layernorm_bf16_kernel<false><<<grid, kRowThreads, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), ldx, nullptr, 0, reinterpret_cast<__nv_bfloat16*>(y), ldy, gamma,
+        beta, M, D, eps);
   DFD_LAUNCH_CHECK();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return DFD_OK;
@@ -312,6 +337,13 @@ int patchify(const void* pixels, int pix_format, int B, int Hin, int Win, int S,
 }
 
 }  // namespace dfd
+
+// LayerNorm of the two-bf16 row x + lo (the residual stream of dfd_engine_set_precise_residual)
+extern "C" DFD_API int dfd_layernorm2_bf16(const void* x, int64_t ldx, const void* lo, int64_t ldlo, void* y, int64_t ldy,
+                                           const float* gamma, const float* beta, int M, int D, float eps, void* stream) {
+  DFD_REQUIRE(lo != nullptr, DFD_ERR_BAD_ARG, "layernorm2: null pointer");
+  return dfd::layernorm_bf16(x, ldx, y, ldy, gamma, beta, M, D, eps, reinterpret_cast<cudaStream_t>(stream), lo, ldlo);
+}
 
 extern "C" DFD_API int dfd_layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy,
                                           const float* gamma, const float* beta, int M, int D,

@@ -108,6 +108,8 @@ struct dfd_engine {
   uint8_t* aslab;
   int64_t abytes;
   __nv_bfloat16 *patches, *x, *h, *qkv, *att, *mlp, *ao, *r, *h2, *m2;
+  __nv_bfloat16* x_lo;       // low half of the two-bf16 residual stream (precise mode), allocated on first use
+  bool precise;
   float *stats_a, *stats_b;  // per-row (sum, sum of squares) of the residual stream (fuse_ln)
   bool folded;
   void* hidden_tap;          // optional [L+1, B, N, D] bf16 destination of the per-layer hidden states
@@ -120,6 +122,26 @@ struct dfd_engine {
   std::vector<int> prof_fam;
   int prof_n;
   int prof_cap;  // launches the current profiling session may record
+  // CUDA graphs of the forward, one per call signature (see dfd_engine_set_graphs)
+  struct GraphKey {
+    const void *pixels, *pooled, *last_hidden;
+    int fmt, B, Hin, Win, resize_mode;
+    bool operator==(const GraphKey& o) const {
+      return pixels == o.pixels && pooled == o.pooled && last_hidden == o.last_hidden && fmt == o.fmt && B == o.B &&
+             Hin == o.Hin && Win == o.Win && resize_mode == o.resize_mode;
+    }
+  };
+  struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec;  // nullptr: the signature has been seen (and run eagerly) once
+    int64_t launches;      // kernel launches one replay stands for
+    uint64_t last_use;
+  };
+  bool graphs_on;
+  std::vector<GraphEntry> graphs;
+  uint64_t graph_clock;
+  cudaStream_t capture_stream;
+  int64_t graph_replays;
 };
 
 namespace dfd {
@@ -336,6 +358,12 @@ extern "C" DFD_API int dfd_engine_create(const dfd_config* cfg, int device, int 
   e->prof_on = false;
   e->prof_n = 0;
   e->prof_cap = 0;
+  e->x_lo = nullptr;
+  e->precise = false;
+  e->graphs_on = false;
+  e->graph_clock = 0;
+  e->capture_stream = nullptr;
+  e->graph_replays = 0;
   carve_weights(e, nullptr, &e->wbytes);
   carve_acts(e, nullptr, &e->abytes);
   cudaError_t err = cudaMalloc(&e->wslab, e->wbytes);
@@ -360,7 +388,11 @@ extern "C" DFD_API int dfd_engine_destroy(dfd_engine* e) {
   if (e->wslab) cudaFree(e->wslab);
   if (e->aslab) cudaFree(e->aslab);
   if (e->staging) cudaFree(e->staging);
+  if (e->x_lo) cudaFree(e->x_lo);
   for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
+  for (auto& g : e->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
   delete e;
   return DFD_OK;
 }
@@ -506,22 +538,9 @@ extern "C" DFD_API int dfd_engine_profile_read(dfd_engine* e, float* ms4, int* c
   return dfd_engine_profile_read_families(e, 4, ms4, count4);
 }
 
-extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int pix_format, int B, int Hin,
-                                          int Win, int resize_mode, void* pooled, void* last_hidden,
-                                          void* stream) {
-  DFD_REQUIRE(e && pixels && pooled, DFD_ERR_BAD_ARG, "forward: null pointer");
-  DFD_REQUIRE(e->finalized, DFD_ERR_STATE, "forward: engine not finalized");
-  DFD_REQUIRE(B > 0 && B <= e->max_batch, DFD_ERR_SHAPE, "forward: batch %d outside 1..%d", B, e->max_batch);
-  {
-    // kernels are launched on the CURRENT device: refuse to run against another device's pointers (the stream handed in
-    // belongs to the caller's device as well)
-    int cur = -1;
-    DFD_CUDA(cudaGetDevice(&cur));
-    DFD_REQUIRE(cur == e->device, DFD_ERR_STATE,
-                "forward: the engine lives on device %d but device %d is current (cudaSetDevice / torch.cuda.device first)",
-                e->device, cur);
-  }
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+// The launches of one forward, enqueued on st (which may be a capturing stream).
+static int forward_body(dfd_engine* e, const void* pixels, int pix_format, int B, int Hin, int Win, int resize_mode,
+                        void* pooled, void* last_hidden, cudaStream_t st) {
   const int N = e->N, D = e->D, I = e->I, H = e->H, hd = e->hd;
   const int M = B * N;
   const float eps = e->cfg.ln_eps;
@@ -539,6 +558,10 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
     DFD_OP(0, gemm_bf16_dispatch(e->patches, e->Kpad, e->w_pe, e->Kpad, e->x, D, M, D, e->Kpad, &ep, 0, st));
   }
   const size_t hid_bytes = (size_t)M * D * sizeof(__nv_bfloat16);
+  // precise mode: x = hi + lo.  The patch embedding leaves lo = 0 (one bf16 rounding, as for every branch input); each
+  // residual GEMM then reads and rewrites both halves, so the additions of all 2·L branches accumulate at ~16 mantissa bits
+  __nv_bfloat16* lo = e->precise ? e->x_lo : nullptr;
+  if (lo) DFD_CUDA(cudaMemsetAsync(lo, 0, hid_bytes, st));
   if (e->hidden_tap) DFD_CUDA(cudaMemcpyAsync(e->hidden_tap, e->x, hid_bytes, cudaMemcpyDeviceToDevice, st));
   for (int li = 0; li < e->L; ++li) {
     const Layer& l = e->layers[li];
@@ -553,7 +576,7 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
       ep.ln_eps = eps;
       DFD_OP(0, gemm_bf16_dispatch(e->x, D, l.w_qkv, D, e->qkv, 3 * D, M, 3 * D, D, &ep, 0, st));
     } else {
-      DFD_OP(2, layernorm_bf16(e->x, D, e->h, D, l.ln1_g, l.ln1_b, M, D, eps, st));
+      DFD_OP(2, layernorm_bf16(e->x, D, e->h, D, l.ln1_g, l.ln1_b, M, D, eps, st, lo, D));
       dfd_gemm_epilogue ep{};
       ep.bias = l.b_qkv;
       DFD_OP(0, gemm_bf16_dispatch(e->h, D, l.w_qkv, D, e->qkv, 3 * D, M, 3 * D, D, &ep, 0, st));
@@ -564,6 +587,8 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
       ep.bias = l.b_o;
       ep.residual = e->x;
       ep.ldr = D;
+      ep.residual_lo = lo;
+      ep.ldlo = D;
       if (fuse) ep.stats_out = e->stats_b;
       DFD_OP(0, gemm_bf16_dispatch(e->att, D, l.w_o, D, e->x, D, M, D, D, &ep, 0, st));
     }
@@ -578,7 +603,7 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
       ep.ln_eps = eps;
       DFD_OP(0, gemm_bf16_dispatch(e->x, D, l.w_fc1, D, e->mlp, I, M, I, D, &ep, 0, st));
     } else {
-      DFD_OP(2, layernorm_bf16(e->x, D, e->h, D, l.ln2_g, l.ln2_b, M, D, eps, st));
+      DFD_OP(2, layernorm_bf16(e->x, D, e->h, D, l.ln2_g, l.ln2_b, M, D, eps, st, lo, D));
       dfd_gemm_epilogue ep{};
       ep.bias = l.b_fc1;
       ep.act = 1;
@@ -589,6 +614,8 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
       ep.bias = l.b_fc2;
       ep.residual = e->x;
       ep.ldr = D;
+      ep.residual_lo = lo;
+      ep.ldlo = D;
       if (fuse && li + 1 < e->L) ep.stats_out = e->stats_a;  // for the next layer's LN1 (the post-LN runs as a kernel)
       DFD_OP(0, gemm_bf16_dispatch(e->mlp, I, l.w_fc2, I, e->x, D, M, D, I, &ep, 0, st));
     }
@@ -597,7 +624,7 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
                                cudaMemcpyDeviceToDevice, st));
   }
   __nv_bfloat16* xp = last_hidden ? reinterpret_cast<__nv_bfloat16*>(last_hidden) : e->h;
-  DFD_OP(2, layernorm_bf16(e->x, D, xp, D, e->post_g, e->post_b, M, D, eps, st));
+  DFD_OP(2, layernorm_bf16(e->x, D, xp, D, e->post_g, e->post_b, M, D, eps, st, lo, D));
   {  // K | V projection of every token (rows D..3D of in_proj)
     dfd_gemm_epilogue ep{};
     ep.bias = e->b_in + D;
@@ -623,5 +650,117 @@ extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int
     ep.ldr = D;
     DFD_OP(0, gemm_bf16_dispatch(e->m2, I, e->w_mfc2, I, pooled, D, B, D, I, &ep, 0, st));
   }
+  return DFD_OK;
+}
+
+// CUDA graphs of the forward.  A forward is 7·L + 13 launches, each with 3-4 tensor maps encoded on
+// the host; for small batches (multicrop: 6-9 views; base-224 at any batch below ~64) the host cannot keep ahead of the
+// device.  With graphs on, a call signature (pointers, batch, input geometry) runs eagerly the first time it is seen, is
+// captured the second time (on a private stream: the caller's may be the legacy default stream, which cannot capture) and
+// is replayed with ONE cudaGraphLaunch on the caller's stream from then on: tensor maps and kernel arguments are baked into
+// the graph.  Up to kMaxGraphs signatures are kept (least recently used out).  Profiling and hidden-state taps run eagerly.
+extern "C" DFD_API int dfd_engine_set_graphs(dfd_engine* e, int enable) {
+  DFD_REQUIRE(e, DFD_ERR_BAD_ARG, "set_graphs: null engine");
+  e->graphs_on = enable != 0;
+  if (!e->graphs_on) {
+    DeviceGuard guard(e->device);
+    cudaDeviceSynchronize();
+    for (auto& g : e->graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    e->graphs.clear();
+  }
+  return DFD_OK;
+}
+
+// Residual-stream precision.  0 (default): the stream is one bf16 tensor, rounded after each of the 2·L residual additions.
+// 1: two bf16 tensors (hi + lo, ~16 mantissa bits) — the additions accumulate like the fp32 residual stream the reference keeps
+// under autocast (HF:modeling_siglip.py:352,359); branch inputs are still the bf16 value hi.  Costs one extra [B·N, D] bf16
+// buffer (allocated here) and 4 more bytes per element and residual GEMM of HBM traffic.
+extern "C" DFD_API int dfd_engine_set_precise_residual(dfd_engine* e, int enable) {
+  DFD_REQUIRE(e, DFD_ERR_BAD_ARG, "set_precise_residual: null engine");
+  DeviceGuard guard(e->device);
+  DFD_REQUIRE(guard.ok, DFD_ERR_CUDA, "set_precise_residual: cudaSetDevice failed");
+  if (enable && e->x_lo == nullptr)
+    DFD_CUDA(cudaMalloc(&e->x_lo, (size_t)e->max_batch * e->N * e->D * sizeof(__nv_bfloat16)));
+  if ((enable != 0) != e->precise) {   // captured graphs bake the mode in
+    cudaDeviceSynchronize();
+    for (auto& g : e->graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    e->graphs.clear();
+  }
+  e->precise = enable != 0;
+  return DFD_OK;
+}
+
+// Graph replays since the engine was created (tests / bench: proves that the graph path ran).
+extern "C" DFD_API int64_t dfd_engine_graph_replays(const dfd_engine* e) { return e ? e->graph_replays : 0; }
+
+extern "C" DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int pix_format, int B, int Hin,
+                                          int Win, int resize_mode, void* pooled, void* last_hidden,
+                                          void* stream) {
+  DFD_REQUIRE(e && pixels && pooled, DFD_ERR_BAD_ARG, "forward: null pointer");
+  DFD_REQUIRE(e->finalized, DFD_ERR_STATE, "forward: engine not finalized");
+  DFD_REQUIRE(B > 0 && B <= e->max_batch, DFD_ERR_SHAPE, "forward: batch %d outside 1..%d", B, e->max_batch);
+  {
+    // kernels are launched on the CURRENT device: refuse to run against another device's pointers (the stream handed in
+    // belongs to the caller's device as well)
+    int cur = -1;
+    DFD_CUDA(cudaGetDevice(&cur));
+    DFD_REQUIRE(cur == e->device, DFD_ERR_STATE,
+                "forward: the engine lives on device %d but device %d is current (cudaSetDevice / torch.cuda.device first)",
+                e->device, cur);
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool eager = !e->graphs_on || e->prof_on || e->hidden_tap != nullptr;
+  if (eager) return forward_body(e, pixels, pix_format, B, Hin, Win, resize_mode, pooled, last_hidden, st);
+
+  constexpr size_t kMaxGraphs = 16;
+  const dfd_engine::GraphKey key{pixels, pooled, last_hidden, pix_format, B, Hin, Win, resize_mode};
+  dfd_engine::GraphEntry* hit = nullptr;
+  for (auto& g : e->graphs)
+    if (g.key == key) { hit = &g; break; }
+  if (hit != nullptr && hit->exec != nullptr) {
+    hit->last_use = ++e->graph_clock;
+    DFD_CUDA(cudaGraphLaunch(hit->exec, st));
+    g_launches.fetch_add(hit->launches, std::memory_order_relaxed);
+    ++e->graph_replays;
+    return DFD_OK;
+  }
+  if (hit == nullptr) {
+    // first sight: run eagerly (also takes care of one-time function attributes) and remember the signature
+    if (e->graphs.size() >= kMaxGraphs) {
+      size_t lru = 0;
+      for (size_t i = 1; i < e->graphs.size(); ++i)
+        if (e->graphs[i].last_use < e->graphs[lru].last_use) lru = i;
+      if (e->graphs[lru].exec) cudaGraphExecDestroy(e->graphs[lru].exec);
+      e->graphs.erase(e->graphs.begin() + lru);
+    }
+    e->graphs.push_back(dfd_engine::GraphEntry{key, nullptr, 0, ++e->graph_clock});
+    return forward_body(e, pixels, pix_format, B, Hin, Win, resize_mode, pooled, last_hidden, st);
+  }
+  // second sight: capture, instantiate, launch
+  if (e->capture_stream == nullptr) DFD_CUDA(cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking));
+  const int64_t l0 = g_launches.load(std::memory_order_relaxed);
+  DFD_CUDA(cudaStreamBeginCapture(e->capture_stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = forward_body(e, pixels, pix_format, B, Hin, Win, resize_mode, pooled, last_hidden, e->capture_stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t cerr = cudaStreamEndCapture(e->capture_stream, &graph);
+  const int64_t captured = g_launches.load(std::memory_order_relaxed) - l0;
+  g_launches.fetch_sub(captured, std::memory_order_relaxed);   // nothing ran yet
+  if (rc != DFD_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (cerr != cudaSuccess) return cuda_fail(cerr, "cudaStreamEndCapture(forward)", __FILE__, __LINE__);
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ierr = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ierr != cudaSuccess) return cuda_fail(ierr, "cudaGraphInstantiate(forward)", __FILE__, __LINE__);
+  hit->exec = exec;
+  hit->launches = captured;
+  hit->last_use = ++e->graph_clock;
+  DFD_CUDA(cudaGraphLaunch(exec, st));
+  g_launches.fetch_add(captured, std::memory_order_relaxed);
+  ++e->graph_replays;
   return DFD_OK;
 }

@@ -16,10 +16,10 @@ namespace dfd {
 
 extern std::atomic<int64_t> g_launches;
 static std::atomic<int> g_last_variant{0};  // BN + 1000·CG + 10000·RES + 100000·EPI of the last GEMM launch (tests)
-static std::atomic<int64_t> g_variant_launches[3 * 2 * 2 * 7];  // launches per instantiation since load (tests)
+static std::atomic<int64_t> g_variant_launches[3 * 2 * 2 * 8];  // launches per instantiation since load (tests)
 static int variant_slot(int bn, int cg, int res, int epi) {
   const int b = bn == 256 ? 2 : (bn == 192 ? 1 : 0);
-  return ((b * 2 + (cg - 1)) * 2 + res) * 7 + epi;
+  return ((b * 2 + (cg - 1)) * 2 + res) * 8 + epi;
 }
 
 namespace {
@@ -46,6 +46,8 @@ struct EpiArgs {
   float* stats_out;
   int residual_op;  // 0: v += residual, 1: v *= residual
   int ln_parts;     // ln_rowstats holds this many partial (Σx, Σx²) pairs per row: [ln_parts][M][2]
+  __nv_bfloat16* lo;  // low half of a two-bf16 ("hi + lo") residual stream: read with the residual, written with C
+  int64_t ldlo;
 };
 
 // CG = CTAs per MMA (1, or 2 = cta_group::2: a 256 x BN tile shared by an SM pair, each CTA staging its own
@@ -121,6 +123,8 @@ __device__ __noinline__ float2 act_rare(float2 v, int act) {
 // combinations the backbone launches, with everything else compiled out:
 //   1 LayerNorm fold + bias (qkv)           2 LayerNorm fold + bias + tanh-GELU (fc1)      5 bias        6 bias + tanh-GELU
 //   3 bias + residual add + row statistics (out-projection / fc2 under fuse_ln)            4 bias + residual add
+//   7 as 3 on a two-bf16 residual stream: v = acc + bias + hi + lo, C = hi' = bf16(v), lo' = bf16(v - hi') (row statistics of
+//     hi', the operand the next LayerNorm-folded GEMM reads, only if stats_out is given)
 // The generic epilogue if-converts its run-time options into predicated code: ~880 issued instructions per 64-column chunk
 // per warp for bias + residual (clock64 trace: 3600 of the 4900 cycles of a chunk), which made every GEMM with a short K
 // loop epilogue bound (K = 768 / 1152 out-projections at 45-75 % of the tensor peak).
@@ -323,7 +327,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const int f_act = kSpec ? ((EPI == 2 || EPI == 6) ? 1 : 0) : epi.act;
     const bool f_pos = kSpec ? false : (epi.pos != nullptr);
     const bool f_mul = kSpec ? false : (epi.residual_op != 0);
-    const bool f_stats = kSpec ? (EPI == 3) : (epi.stats_out != nullptr);
+    const bool f_stats = kSpec ? (EPI == 3 || (EPI == 7 && epi.stats_out != nullptr)) : (epi.stats_out != nullptr);
+    // two-bf16 residual stream: the low halves go straight between registers and global memory, one 128-byte row segment
+    // per thread and chunk (whole lines); read only where a residual is added, written wherever C is
+    const bool f_lo = EPI == 7;   // (the generic kernel has no registers left for it: EPI 7 exists for every tile shape)
     const float* tab_src = (tab_t < kChunkN) ? epi.ln_colsum : epi.bias;
     const int tab_e = tab_t & (kChunkN - 1);
     auto next_chunk_col = [&](int rr, int c) -> int {  // first column of the group's chunk after (round rr, c); -1: none
@@ -387,11 +394,33 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll 1
       for (int c = grp; c < nvalid; c += 2) {
         const int c0 = n0 + c * kChunkN;
+        uint4 lo_in[8];
+        __nv_bfloat16* lo_row = f_lo ? epi.lo + (int64_t)row * epi.ldlo + c0 : nullptr;
+        if (RES && f_lo) {
+          // issued ahead of the TMEM load: the global latency overlaps the TMEM round trip and the residual wait
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            lo_in[g] = make_uint4(0u, 0u, 0u, 0u);
+            if (row_ok && c0 + g * 8 < N) lo_in[g] = *reinterpret_cast<const uint4*>(lo_row + g * 8);
+          }
+        }
         uint32_t r[64];
         tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * kChunkN), *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
         tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * kChunkN + 32),
                            *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
         tmem_ld_wait();
+        if (RES && f_lo) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint32_t w4[4] = {lo_in[g].x, lo_in[g].y, lo_in[g].z, lo_in[g].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 l2 = unpack_bf16x2(w4[j]);
+              r[g * 8 + 2 * j] = __float_as_uint(__uint_as_float(r[g * 8 + 2 * j]) + l2.x);
+              r[g * 8 + 2 * j + 1] = __float_as_uint(__uint_as_float(r[g * 8 + 2 * j + 1]) + l2.y);
+            }
+          }
+        }
         const float tab_next = fetch_col(next_chunk_col(rr, c));  // consumed after the first barrier below
         if (c + 2 >= nvalid) {
           // last chunk of this group for this tile: the accumulator stage can go back to the MMA warp
@@ -484,6 +513,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           o[g].y = pack_bf16x2(v[1].x, v[1].y);
           o[g].z = pack_bf16x2(v[2].x, v[2].y);
           o[g].w = pack_bf16x2(v[3].x, v[3].y);
+          if (f_lo && row_ok && cc < N) {
+            const float2 h0 = unpack_bf16x2(o[g].x), h1 = unpack_bf16x2(o[g].y),
+                         h2 = unpack_bf16x2(o[g].z), h3 = unpack_bf16x2(o[g].w);
+            uint4 lw;
+            lw.x = pack_bf16x2(v[0].x - h0.x, v[0].y - h0.y);
+            lw.y = pack_bf16x2(v[1].x - h1.x, v[1].y - h1.y);
+            lw.z = pack_bf16x2(v[2].x - h2.x, v[2].y - h2.y);
+            lw.w = pack_bf16x2(v[3].x - h3.x, v[3].y - h3.y);
+            *reinterpret_cast<uint4*>(lo_row + g * 8) = lw;
+          }
           if (f_stats && cc < N) {
             const float2 q0 = unpack_bf16x2(o[g].x), q1 = unpack_bf16x2(o[g].y),
                          q2 = unpack_bf16x2(o[g].z), q3 = unpack_bf16x2(o[g].w);
@@ -651,6 +690,11 @@ int gemm_bf16_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, v
     ea.stats_out = epi->stats_out;
     ea.residual_op = epi->residual_op;
     ea.ln_parts = epi->ln_parts > 0 ? epi->ln_parts : 1;
+    ea.lo = reinterpret_cast<__nv_bfloat16*>(epi->residual_lo);
+    ea.ldlo = epi->ldlo;
+    DFD_REQUIRE(ea.lo == nullptr || (ea.ldlo % 8 == 0 && ea.ldlo >= N && (uintptr_t)ea.lo % 16 == 0), DFD_ERR_SHAPE,
+                "gemm: residual_lo must be 16-byte aligned with a leading dimension that is a multiple of 8 and >= N");
+    DFD_REQUIRE(ea.lo == nullptr || ea.residual_op == 0, DFD_ERR_BAD_ARG, "gemm: residual_lo goes with an additive residual");
     DFD_REQUIRE(ea.act >= 0 && ea.act <= 3, DFD_ERR_BAD_ARG, "gemm: act must be 0 (none), 1 (gelu_tanh), 2 (gelu_erf) or 3 (sigmoid)");
     DFD_REQUIRE(ea.residual_op == 0 || ea.residual_op == 1, DFD_ERR_BAD_ARG, "gemm: residual_op must be 0 (add) or 1 (multiply)");
     DFD_REQUIRE((ea.ln_colsum == nullptr) == (ea.ln_rowstats == nullptr), DFD_ERR_BAD_ARG,
@@ -680,6 +724,20 @@ int gemm_bf16_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, v
   if (has_res) {
     rc = make_tmap_bf16_2d(&tmR, ea.residual, M, N, ea.ldr, BM);
     if (rc != DFD_OK) return rc;
+  }
+  if (ea.lo != nullptr) {
+    // two-bf16 residual stream: one specialised epilogue (bias + residual + lo [+ row statistics]) for every tile shape
+    DFD_REQUIRE(has_res && ea.bias != nullptr && ea.pos == nullptr && ea.ln_colsum == nullptr && ea.act == 0, DFD_ERR_UNSUPPORTED,
+                "gemm: residual_lo needs bias + additive residual and no other fused option");
+#define DFD_GEMM_LO_CASE(BN_, CG_) \
+  if (bn == BN_ && cg == CG_) return launch_gemm<BN_, CG_, 1, 7>(tmA, tmB, tmC, tmR, M, N, K, ea, st);
+    DFD_GEMM_LO_CASE(256, 2)
+    DFD_GEMM_LO_CASE(192, 2)
+    DFD_GEMM_LO_CASE(128, 2)
+    DFD_GEMM_LO_CASE(256, 1)
+    DFD_GEMM_LO_CASE(192, 1)
+    DFD_GEMM_LO_CASE(128, 1)
+#undef DFD_GEMM_LO_CASE
   }
   // the backbone's own epilogues on its one large-M tile shape get compile-time specialised kernels (see EPI above)
   if (bn == 256 && cg == 2 && ea.bias != nullptr && ea.pos == nullptr) {
@@ -717,7 +775,7 @@ extern "C" DFD_API int dfd_gemm_last_variant(void) { return dfd::g_last_variant.
 // Launches of one instantiation (same encoding) by this process since load; -1 for an encoding that names no kernel.
 extern "C" DFD_API int64_t dfd_gemm_variant_launches(int variant) {
   const int bn = variant % 1000, cg = variant / 1000 % 10, res = variant / 10000 % 10, epi = variant / 100000;
-  if ((bn != 128 && bn != 192 && bn != 256) || cg < 1 || cg > 2 || res < 0 || res > 1 || epi < 0 || epi > 6) return -1;
+  if ((bn != 128 && bn != 192 && bn != 256) || cg < 1 || cg > 2 || res < 0 || res > 1 || epi < 0 || epi > 7) return -1;
   return dfd::g_variant_launches[dfd::variant_slot(bn, cg, res, epi)].load(std::memory_order_relaxed);
 }
 

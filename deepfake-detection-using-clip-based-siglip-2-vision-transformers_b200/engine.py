@@ -143,7 +143,8 @@ class SiglipEngine:
     """One engine per (device, architecture).  `forward` accepts uint8 NHWC images (preprocess fused into the
     im2col kernel) or float32 NCHW tensors that are already normalised, and returns bf16 pooled embeddings."""
 
-    def __init__(self, arch: VisionArch, device: int | torch.device = 0, max_batch: int = 64, fuse_ln: bool = False):
+    def __init__(self, arch: VisionArch, device: int | torch.device = 0, max_batch: int = 64, fuse_ln: bool = False,
+                 graphs: bool = False, precise_residual: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("SiglipEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.arch = arch
@@ -159,6 +160,18 @@ class SiglipEngine:
         check(self._lib.dfd_engine_create(C.byref(cfg), self.device.index or 0, self.max_batch, C.byref(h)))
         self._h = h
         self._finalized = False
+        # graphs: a forward whose buffers and shape have been seen before is replayed as ONE CUDA graph launch (tensor maps
+        # and arguments baked in) instead of 7·L + 13 launches — for small batches, where the host cannot keep ahead of the
+        # device.  The engine then writes into output buffers it keeps per batch size (stable pointers) and hands out copies.
+        self.graphs = False
+        self._out: Dict[tuple, torch.Tensor] = {}
+        if graphs:
+            self.set_graphs(True)
+        # precise_residual: the residual stream is carried as two bf16 tensors (hi + lo), so the 2·L residual additions
+        # accumulate like the fp32 stream of the reference's autocast path instead of being rounded to bf16 each time
+        self.precise_residual = False
+        if precise_residual:
+            self.set_precise_residual(True)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -170,6 +183,20 @@ class SiglipEngine:
             self.close()
         except Exception:
             pass
+
+    def set_graphs(self, on: bool) -> None:
+        check(self._lib.dfd_engine_set_graphs(self._h, int(bool(on))))
+        self.graphs = bool(on)
+        if not on:
+            self._out.clear()
+
+    def set_precise_residual(self, on: bool) -> None:
+        check(self._lib.dfd_engine_set_precise_residual(self._h, int(bool(on))))
+        self.precise_residual = bool(on)
+
+    @property
+    def graph_replays(self) -> int:
+        return int(self._lib.dfd_engine_graph_replays(self._h))
 
     @property
     def workspace_bytes(self) -> int:
@@ -228,9 +255,21 @@ class SiglipEngine:
         if ch != 3:
             raise ValueError("pixels must have 3 channels")
         a = self.arch
-        pooled = torch.empty((B, a.hidden_size), dtype=torch.bfloat16, device=self.device)
-        last = (torch.empty((B, a.tokens, a.hidden_size), dtype=torch.bfloat16, device=self.device)
-                if want_last_hidden else None)
+        stable = self.graphs and B <= self.max_batch
+        if stable:   # stable output pointers, so that the call signature repeats and its graph is replayed
+            pooled = self._out.get(("p", B))
+            if pooled is None:
+                pooled = self._out[("p", B)] = torch.empty((B, a.hidden_size), dtype=torch.bfloat16, device=self.device)
+            last = None
+            if want_last_hidden:
+                last = self._out.get(("l", B))
+                if last is None:
+                    last = self._out[("l", B)] = torch.empty((B, a.tokens, a.hidden_size), dtype=torch.bfloat16,
+                                                               device=self.device)
+        else:
+            pooled = torch.empty((B, a.hidden_size), dtype=torch.bfloat16, device=self.device)
+            last = (torch.empty((B, a.tokens, a.hidden_size), dtype=torch.bfloat16, device=self.device)
+                    if want_last_hidden else None)
         if pixels.device != self.device:
             raise RuntimeError(f"pixels live on {pixels.device}, this engine on {self.device}")
         # launch on THIS engine's device and on its current stream, whatever device the caller has selected
@@ -241,6 +280,8 @@ class SiglipEngine:
                 check(self._lib.dfd_engine_forward(self._h, pixels[b0:b0 + nb].data_ptr(), fmt, nb, Hin, Win, resize_mode,
                                                    pooled[b0:b0 + nb].data_ptr(),
                                                    None if last is None else last[b0:b0 + nb].data_ptr(), st))
+        if stable:   # the kept buffers are overwritten by the next call of this batch size: hand out copies
+            return pooled.clone(), (None if last is None else last.clone())
         return pooled, last
 
     __call__ = forward

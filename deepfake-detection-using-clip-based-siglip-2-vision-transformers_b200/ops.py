@@ -28,7 +28,8 @@ def _p(t: Optional[torch.Tensor]):
 
 def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = 0, pos=None, residual=None,
               ln_rowstats=None, ln_colsum=None, ln_dim: int = 0, ln_eps: float = 1e-6, stats_out=None,
-              out: Optional[torch.Tensor] = None, tile_n: int = 0, residual_op: int = 0) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, tile_n: int = 0, residual_op: int = 0,
+              residual_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = epilogue(a[M,K] @ w[N,K].T); bf16 in/out, fp32 accumulate in TMEM (dfd_gemm_bf16).
     act: 0 none, 1 gelu_tanh, 2 gelu_erf, 3 sigmoid; residual_op: 0 add, 1 multiply.
     stats_out: fp32 [ceil(N/64), M, 2] per-chunk (sum, sum of squares) of the bf16 output rows (written, not
@@ -55,6 +56,10 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = 0, pos=
     epi.stats_out = _p(stats_out)
     epi.residual_op = residual_op
     epi.ln_parts = 0
+    # two-bf16 residual stream: residual_lo [M, N] bf16 is read with the residual and rewritten in place with the low half
+    # of the new value (see dfd_gemm_epilogue.residual_lo)
+    epi.residual_lo = _p(residual_lo)
+    epi.ldlo = 0 if residual_lo is None else residual_lo.stride(0)
     if ln_rowstats is not None:
         assert ln_rowstats.dtype == torch.float32 and ln_rowstats.is_contiguous() and ln_rowstats.shape[-2:] == (M, 2)
         epi.ln_parts = ln_rowstats.shape[0] if ln_rowstats.dim() == 3 else 1

@@ -56,10 +56,12 @@ def head_params_from_state(sd: Dict[str, torch.Tensor], dim: int, device) -> "op
 class DetectionPipeline:
     def __init__(self, arch: VisionArch | str, backbone_state: Dict[str, torch.Tensor],
                  head_state: Dict[str, torch.Tensor], scoring: ScoringStack, device: int = 0, max_batch: int = 64,
-                 freq_eps: float = EPS_TRAINER, freq_zscore: Optional[bool] = None, fuse_ln: bool = True):
+                 freq_eps: float = EPS_TRAINER, freq_zscore: Optional[bool] = None, fuse_ln: bool = True,
+                 graphs: bool = False, precise_residual: bool = False):
         self.arch = ARCHS[arch] if isinstance(arch, str) else arch
         self.device = torch.device("cuda", device)
-        self.engine = SiglipEngine(self.arch, device, max_batch, fuse_ln=fuse_ln).load_state_dict(backbone_state)
+        self.engine = SiglipEngine(self.arch, device, max_batch, fuse_ln=fuse_ln, graphs=graphs,
+                                   precise_residual=precise_residual).load_state_dict(backbone_state)
         self.head = head_params_from_state(head_state, self.arch.hidden_size, self.device)
         self.scoring = scoring
         # G1 heads were trained on z-scored vectors (app.py:840-846), G2 on raw ones + learned normaliser

@@ -71,6 +71,23 @@ def random_classifier_head(kind: str, D: int, seed: int = 1) -> Dict[str, torch.
     return sd
 
 
+def random_fast_classifier_head(model_size: str, D: int, seed: int = 4) -> Dict[str, torch.Tensor]:
+    """`FastBinaryClassifier` head (H-D, cifake_binary_classifier.py:643-687) with the reference's key names: layer_norm,
+    attention (qkv + proj for tiny / small, in_proj + out_proj for large, none for medium), size-dependent classifier."""
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s, std=1.0: torch.randn(*s, generator=g) * std  # noqa: E731
+    sd = {"layer_norm.weight": 1.0 + rn(D, std=0.1), "layer_norm.bias": rn(D, std=0.1)}
+    att = {"tiny": ("qkv", "proj"), "small": ("qkv", "proj"), "large": ("in_proj_", "out_proj")}.get(model_size)
+    if att:
+        sep = "" if att[0].endswith("_") else "."
+        sd[f"attention.{att[0]}{sep}weight"], sd[f"attention.{att[0]}{sep}bias"] = rn(3 * D, D, std=D ** -0.5), rn(3 * D, std=0.1)
+        sd[f"attention.{att[1]}.weight"], sd[f"attention.{att[1]}.bias"] = rn(D, D, std=D ** -0.5), rn(D, std=0.1)
+    dims, idx = {"tiny": ([D, 1], [1]), "small": ([D, D // 4, 1], [0, 3])}.get(model_size, ([D, D // 2, D // 4, 1], [0, 3, 6]))
+    for i, n in enumerate(idx):
+        sd[f"classifier.{n}.weight"], sd[f"classifier.{n}.bias"] = rn(dims[i + 1], dims[i], std=dims[i] ** -0.5), rn(dims[i + 1], std=0.1)
+    return sd
+
+
 def random_freq_mlp_g2(seed: int = 2) -> Dict[str, torch.Tensor]:
     g = torch.Generator().manual_seed(seed)
     rn = lambda *s, std=1.0: torch.randn(*s, generator=g) * std  # noqa: E731

@@ -82,6 +82,11 @@ typedef struct dfd_gemm_epilogue {
   float* stats_out;          /* [ceil(N/64)][M][2] fp32 partials (see above), or NULL */
   int residual_op;           /* 0: v += residual (default), 1: v *= residual (gating: Siglip2sidafrozen.py:737) */
   int ln_parts;              /* partial pairs per row in ln_rowstats; 0 or 1 = plain [M,2] (dfd_rowstats_bf16) */
+  void* residual_lo;         /* bf16 [M, ldlo] or NULL: low half of a two-bf16 residual stream.  With it the epilogue value is
+                              * v = ... + residual + residual_lo (read only when residual is given), C = hi = bf16(v) and
+                              * residual_lo = bf16(v - hi) is written back (in place), so the stream carries ~16 mantissa bits
+                              * across layers like the fp32 residual of the reference's autocast path */
+  int64_t ldlo;
 } dfd_gemm_epilogue;
 
 /* C[M,N] (bf16) = epi(A[M,K] (bf16, lda) · W[N,K]ᵀ (bf16, ldw)), fp32 accumulate in TMEM.
@@ -98,7 +103,8 @@ DFD_API int dfd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw
 DFD_API int dfd_gemm_schedule(int num_tiles, int num_n, int units, int unit, int round);
 /* Test / audit hooks: which kernel instantiation the last dfd_gemm_bf16[_tile] call of this process launched, encoded
  * as tile_n + 1000·CTAs-per-tile + 10000·has_residual + 100000·EPI (EPI: 0 generic, 1 LN fold + bias, 2 LN fold + bias +
- * tanh-GELU, 3 bias + residual + row statistics, 4 bias + residual, 5 bias, 6 bias + tanh-GELU), and how often a given
+ * tanh-GELU, 3 bias + residual + row statistics, 4 bias + residual, 5 bias, 6 bias + tanh-GELU, 7 = 3 on a two-bf16
+ * residual stream), and how often a given
  * instantiation has been launched since load (-1: no such kernel).  The parity tests use them to prove that the
  * specialised kernels bench.py times are the ones being compared with the oracle. */
 DFD_API int dfd_gemm_last_variant(void);
@@ -108,6 +114,9 @@ DFD_API int64_t dfd_gemm_variant_launches(int variant);
  * HF:modeling_siglip.py:348,357 (layer_norm1/2), :618 (post_layernorm). */
 DFD_API int dfd_layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,
                                const float* beta, int M, int D, float eps, void* stream);
+/* The same over the two-bf16 row x + lo (see dfd_gemm_epilogue.residual_lo, dfd_engine_set_precise_residual). */
+DFD_API int dfd_layernorm2_bf16(const void* x, int64_t ldx, const void* lo, int64_t ldlo, void* y, int64_t ldy,
+                                const float* gamma, const float* beta, int M, int D, float eps, void* stream);
 /* stats[M,2] = (Σx, Σx²) of bf16 rows (feeds the LN-folded GEMM epilogue when the producer was not a GEMM). */
 DFD_API int dfd_rowstats_bf16(const void* x, int64_t ldx, float* stats, int M, int D, void* stream);
 
@@ -314,6 +323,16 @@ DFD_API int dfd_engine_forward(dfd_engine* e, const void* pixels, int pix_format
  * forwards also copy the embedding output and each encoder layer's output to buf as bf16 [L+1][B][N][D] (B = the
  * batch of that forward).  NULL switches the tap off. */
 DFD_API int dfd_engine_set_hidden_tap(dfd_engine* e, void* buf);
+/* CUDA graphs of the forward: with enable != 0 a call signature (pixels / pooled / last_hidden pointers, batch, input geometry)
+ * runs eagerly the first time, is captured the second time and replayed with one cudaGraphLaunch on the caller's stream
+ * afterwards (tensor maps and arguments baked in; 16 signatures kept, LRU).  Keep the buffers of a serving loop stable to
+ * benefit.  enable == 0 drops every captured graph.  dfd_engine_graph_replays counts replays since creation. */
+DFD_API int dfd_engine_set_graphs(dfd_engine* e, int enable);
+/* Residual-stream precision: 0 (default) one bf16 tensor, rounded after each of the 2·L residual additions; 1 two bf16 tensors
+ * (hi + lo, ~16 mantissa bits), which accumulates the additions like the fp32 residual stream of the reference's autocast path
+ * (HF:modeling_siglip.py:352,359).  Allocates one more [max_batch·N, D] bf16 buffer on first use. */
+DFD_API int dfd_engine_set_precise_residual(dfd_engine* e, int enable);
+DFD_API int64_t dfd_engine_graph_replays(const dfd_engine* e);
 DFD_API int64_t dfd_engine_workspace_bytes(const dfd_engine* e);
 /* Measurement aid (bench.py roofline): dfd_engine_profile(e, n) with n > 0 makes dfd_engine_forward bracket every launch
  * with CUDA events on the caller's stream, with room for n forwards (launches past that are not recorded); n = 0 switches

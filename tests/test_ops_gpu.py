@@ -820,3 +820,58 @@ def test_linear_small():
     w, b = torch.randn(3, 1152, generator=g) / 34, torch.randn(3, generator=g)
     out = ops.linear_small(x.to(DEV), w.to(DEV), b.to(DEV)).cpu()
     assert (out - (x.float() @ w.t() + b)).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K,tile_n", [(46656, 1152, 1152, 0), (20000, 1152, 4304, 0), (777, 768, 768, 0), (300, 264, 64, 1128),
+                                          (1500, 1152, 256, 1192), (9000, 456, 128, 2128)])
+def test_gemm_two_bf16_residual_stream(M, N, K, tile_n):
+    """dfd_gemm_epilogue.residual_lo (EPI 7, every tile shape): v = A·Wᵀ + bias + hi + lo in fp32, C = hi' = bf16(v),
+    lo' = bf16(v - hi') written back in place; hi' + lo' carries ~16 mantissa bits (2^-17 relative) where a bf16 stream keeps 8,
+    and the row statistics are those of hi' (the operand the next LayerNorm-folded GEMM reads)."""
+    from dfd import ops
+
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    a = _bf(torch.randn(M, K, generator=g)).to(DEV)
+    w = _bf(torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    x = (torch.randn(M, N, generator=g) * 3).to(DEV)                    # the "fp32" residual stream
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    ref = a.float() @ w.float().T + bias + hi.float() + lo.float()
+    stats = torch.zeros(((N + 63) // 64, M, 2), dtype=torch.float32, device=DEV)
+    out_hi, out_lo = hi.clone(), lo.clone()
+    ops.gemm_bf16(a, w, bias=bias, residual=out_hi, residual_lo=out_lo, stats_out=stats, out=out_hi, tile_n=tile_n)
+    torch.cuda.synchronize()
+    assert ops.gemm_last_variant()["epi"] == 7
+    got = out_hi.float() + out_lo.float()
+    scale = ref.abs().clamp_min(1.0)
+    # fp32 accumulation order differs from torch's: allow 2e-5 relative for that; a one-tensor bf16 stream would sit at 2e-3
+    assert float(((got - ref).abs() / scale).max()) < 6e-5
+    assert float(((out_hi.float() - ref).abs() / scale).max()) < 4.1e-3          # hi' alone is the bf16 rounding of v
+    st = stats.sum(0)
+    assert torch.allclose(st[:, 0], out_hi.float().sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[:, 1], (out_hi.float() ** 2).sum(1), rtol=1e-4, atol=1e-2)
+    # without statistics (the last layer's fc2)
+    out_hi2, out_lo2 = hi.clone(), lo.clone()
+    ops.gemm_bf16(a, w, bias=bias, residual=out_hi2, residual_lo=out_lo2, out=out_hi2, tile_n=tile_n)
+    torch.cuda.synchronize()
+    assert torch.equal(out_hi2, out_hi) and torch.equal(out_lo2, out_lo)
+
+
+def test_layernorm_two_bf16_input():
+    """layernorm over x = hi + lo (the post-LayerNorm of the precise engine mode) against fp32 torch."""
+    from dfd import _lib, ops
+
+    M, D = 1000, 1152
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = (torch.randn(M, D, generator=g) * 2 + 0.3).to(DEV)
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    gamma, beta = (1 + 0.1 * torch.randn(D, generator=g)).to(DEV), (0.1 * torch.randn(D, generator=g)).to(DEV)
+    y = torch.empty_like(hi)
+    _lib.check(_lib.load().dfd_layernorm2_bf16(hi.data_ptr(), D, lo.data_ptr(), D, y.data_ptr(), D, gamma.data_ptr(), beta.data_ptr(),
+                                               M, D, 1e-6, ops.current_stream()))
+    ref = torch.nn.functional.layer_norm(hi.float() + lo.float(), (D,), gamma, beta, 1e-6)
+    torch.cuda.synchronize()
+    assert float((y.float() - ref).abs().max()) < 2e-2       # bf16 output rounding of values up to ~4
+    assert float((y.float() - ref).abs().mean()) <= float((ops.layernorm_bf16(hi, gamma, beta).float() - ref).abs().mean())
