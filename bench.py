@@ -283,7 +283,8 @@ def run_ours(args):
     e1.record()
     distributed.barrier()
     torch.cuda.synchronize()
-    fam = pipe.engine.profile_read()
+    fam_all = pipe.engine.profile_read(by_gemm_type=True)
+    fam = {k: v for k, v in fam_all.items() if not k.startswith("gemm_")}
     stages = pipe.profile_stages_read()
     pipe.profile_stages(False)
     pipe.engine.profile(0)
@@ -361,6 +362,10 @@ def run_ours(args):
                                 "this command (scripts/collect_profiles.sh -> profiles/); committed capture: "
                                 f"{load_traffic()} B per GEMM launch",
                 "share_of_rank0_busy_time": shares}
+        by_type = pipe.engine.gemm_flops_by_type(my_images)
+        roof["gemm_by_type"] = {k: {"achieved": by_type[k] / (fam_all[k][0] / 1e3) / 1e12, "frac": by_type[k] / (fam_all[k][0] / 1e3) / 1e12 / peak,
+                                    "share_of_rank0_busy_time": fam_all[k][0] / busy_ms, "launches": fam_all[k][1]}
+                                for k in by_type if fam_all[k][0] > 0}
         att_flops = 4.0 * arch.tokens ** 2 * arch.hidden_size * arch.num_hidden_layers * my_images
         if fam["attention"][0] > 0:
             a = att_flops / (fam["attention"][0] / 1e3) / 1e12

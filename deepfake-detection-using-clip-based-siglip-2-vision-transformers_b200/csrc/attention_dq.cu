@@ -328,7 +328,11 @@ attention_dq_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_con
     // on the FMA pipe for every 2nd / 3rd / 4th element (the loop is issue bound for ONE warp, extra instructions cost more
     // than the MUFU slots they free); truncating bf16 conversion by PRMT instead of F2FP (no change); fetching S_{j+1}
     // ahead of tile j's exponentials (it only exists once P_{j-1} has gone through the MMA warp: the warp then waits for
-    // the tensor pipe instead of exponentiating).
+    // the tensor pipe instead of exponentiating); round 2: a speculative tile that takes the exponentials against the current
+    // reference maximum without waiting for the row maximum (tracked on the side with FMNMX3, tile redone if it moved) and
+    // overlaps the second half of the TMEM load with the first half's exponentials — bit-identical, 612-640 against 665 TFLOP/s:
+    // the maximum pass is not on the critical path, the two warps of a scheduler are bound by their own instruction streams
+    // (scripts/ubench_softmax.cu: 1230 cycles per 64-key step for two warps with no MMA or TMEM wait at all).
     const int sw = warp - 3;
     const int t = sw >> 2;                    // query tile of this warp
     const int quad = warp & 3;                // TMEM lane quadrant this warp may access

@@ -515,7 +515,9 @@ extern "C" DFD_API int dfd_engine_profile(dfd_engine* e, int enable) {
 
 // Sums the event-timed durations of every launch recorded since the last read (or since profiling was switched on) per
 // kernel family (ms) and the launch counts, then clears the record.  Synchronises on the last recorded event.
-// Families: 0 GEMM, 1 attention, 2 LayerNorm, 3 patchify, 4 MAP attention; n < 5 folds the higher ones into family n - 1.
+// Families: 0 GEMM (patch embedding, pooling head), 1 attention, 2 LayerNorm, 3 patchify, 4 MAP attention, 5 qkv GEMM,
+// 6 out-projection GEMM, 7 fc1 GEMM, 8 fc2 GEMM.  With n <= 5 the encoder GEMMs (5..8) count as family 0 and families >= n
+// fold into n - 1 (the four- and five-family forms of earlier callers).
 extern "C" DFD_API int dfd_engine_profile_read_families(dfd_engine* e, int n, float* ms, int* count) {
   DFD_REQUIRE(e && ms && count && n > 0, DFD_ERR_BAD_ARG, "profile_read: null pointer");
   DeviceGuard guard(e->device);
@@ -525,7 +527,9 @@ extern "C" DFD_API int dfd_engine_profile_read_families(dfd_engine* e, int n, fl
   for (int i = 0; i < e->prof_n; ++i) {
     float t = 0.f;
     DFD_CUDA(cudaEventElapsedTime(&t, e->prof_ev[2 * i], e->prof_ev[2 * i + 1]));
-    const int f = e->prof_fam[i] < n ? e->prof_fam[i] : n - 1;
+    int f = e->prof_fam[i];
+    if (n <= 5 && f >= 5) f = 0;
+    if (f >= n) f = n - 1;
     ms[f] += t;
     count[f] += 1;
   }
@@ -574,12 +578,12 @@ static int forward_body(dfd_engine* e, const void* pixels, int pix_format, int B
       ep.ln_colsum = l.cs_qkv;
       ep.ln_dim = D;
       ep.ln_eps = eps;
-      DFD_OP(0, gemm_bf16_dispatch(e->x, D, l.w_qkv, D, e->qkv, 3 * D, M, 3 * D, D, &ep, 0, st));
+      DFD_OP(5, gemm_bf16_dispatch(e->x, D, l.w_qkv, D, e->qkv, 3 * D, M, 3 * D, D, &ep, 0, st));
     } else {
       DFD_OP(2, layernorm_bf16(e->x, D, e->h, D, l.ln1_g, l.ln1_b, M, D, eps, st, lo, D));
       dfd_gemm_epilogue ep{};
       ep.bias = l.b_qkv;
-      DFD_OP(0, gemm_bf16_dispatch(e->h, D, l.w_qkv, D, e->qkv, 3 * D, M, 3 * D, D, &ep, 0, st));
+      DFD_OP(5, gemm_bf16_dispatch(e->h, D, l.w_qkv, D, e->qkv, 3 * D, M, 3 * D, D, &ep, 0, st));
     }
     DFD_OP(1, attention_auto_bf16(e->qkv, 3 * D, e->att, D, B, N, H, hd, scale, st));
     {
@@ -590,7 +594,7 @@ static int forward_body(dfd_engine* e, const void* pixels, int pix_format, int B
       ep.residual_lo = lo;
       ep.ldlo = D;
       if (fuse) ep.stats_out = e->stats_b;
-      DFD_OP(0, gemm_bf16_dispatch(e->att, D, l.w_o, D, e->x, D, M, D, D, &ep, 0, st));
+      DFD_OP(6, gemm_bf16_dispatch(e->att, D, l.w_o, D, e->x, D, M, D, D, &ep, 0, st));
     }
     if (fuse) {
       dfd_gemm_epilogue ep{};
@@ -601,13 +605,13 @@ static int forward_body(dfd_engine* e, const void* pixels, int pix_format, int B
       ep.ln_colsum = l.cs_fc1;
       ep.ln_dim = D;
       ep.ln_eps = eps;
-      DFD_OP(0, gemm_bf16_dispatch(e->x, D, l.w_fc1, D, e->mlp, I, M, I, D, &ep, 0, st));
+      DFD_OP(7, gemm_bf16_dispatch(e->x, D, l.w_fc1, D, e->mlp, I, M, I, D, &ep, 0, st));
     } else {
       DFD_OP(2, layernorm_bf16(e->x, D, e->h, D, l.ln2_g, l.ln2_b, M, D, eps, st, lo, D));
       dfd_gemm_epilogue ep{};
       ep.bias = l.b_fc1;
       ep.act = 1;
-      DFD_OP(0, gemm_bf16_dispatch(e->h, D, l.w_fc1, D, e->mlp, I, M, I, D, &ep, 0, st));
+      DFD_OP(7, gemm_bf16_dispatch(e->h, D, l.w_fc1, D, e->mlp, I, M, I, D, &ep, 0, st));
     }
     {
       dfd_gemm_epilogue ep{};
@@ -617,7 +621,7 @@ static int forward_body(dfd_engine* e, const void* pixels, int pix_format, int B
       ep.residual_lo = lo;
       ep.ldlo = D;
       if (fuse && li + 1 < e->L) ep.stats_out = e->stats_a;  // for the next layer's LN1 (the post-LN runs as a kernel)
-      DFD_OP(0, gemm_bf16_dispatch(e->mlp, I, l.w_fc2, I, e->x, D, M, D, I, &ep, 0, st));
+      DFD_OP(8, gemm_bf16_dispatch(e->mlp, I, l.w_fc2, I, e->x, D, M, D, I, &ep, 0, st));
     }
     if (e->hidden_tap)
       DFD_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(e->hidden_tap) + (size_t)(li + 1) * hid_bytes, e->x, hid_bytes,

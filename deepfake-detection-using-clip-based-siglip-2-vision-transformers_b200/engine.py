@@ -292,14 +292,29 @@ class SiglipEngine:
         check(self._lib.dfd_engine_profile(self._h, int(forwards)))
 
     FAMILIES = ("gemm", "attention", "layernorm", "patchify", "map_attention")
+    GEMM_TYPES = ("gemm_other", "gemm_qkv", "gemm_out", "gemm_fc1", "gemm_fc2")
 
-    def profile_read(self) -> dict:
+    def profile_read(self, by_gemm_type: bool = False) -> dict:
         """Per kernel family, summed over every forward since the last read: {'gemm': (ms, launches), 'attention': ...,
-        'layernorm': ..., 'patchify': ..., 'map_attention': ...}.  Waits for the last recorded launch."""
-        n = len(self.FAMILIES)
+        'layernorm': ..., 'patchify': ..., 'map_attention': ...}; with by_gemm_type also 'gemm_qkv' / 'gemm_out' / 'gemm_fc1' /
+        'gemm_fc2' / 'gemm_other' (patch embedding + pooling head), which add up to 'gemm'.  Waits for the last recorded launch."""
+        n = 9
         ms, cnt = (C.c_float * n)(), (C.c_int * n)()
         check(self._lib.dfd_engine_profile_read_families(self._h, n, ms, cnt))
-        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.FAMILIES)}
+        out = {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.FAMILIES)}
+        gm = [0, 5, 6, 7, 8]
+        out["gemm"] = (float(sum(ms[i] for i in gm)), int(sum(cnt[i] for i in gm)))
+        if by_gemm_type:
+            for k, i in zip(self.GEMM_TYPES, gm):
+                out[k] = (float(ms[i]), int(cnt[i]))
+        return out
+
+    def gemm_flops_by_type(self, batch: int) -> dict:
+        a = self.arch
+        N, D, I, L, P = a.tokens, a.hidden_size, a.intermediate_size, a.num_hidden_layers, a.patch_size
+        return {"gemm_qkv": 6.0 * N * D * D * L * batch, "gemm_out": 2.0 * N * D * D * L * batch,
+                "gemm_fc1": 2.0 * N * D * I * L * batch, "gemm_fc2": 2.0 * N * D * I * L * batch,
+                "gemm_other": float(2 * N * 3 * P * P * D + 4 * N * D * D + 2 * D * D + 4 * D * I) * batch}
 
     def gemm_flops(self, batch: int) -> float:
         """Algorithmic FLOPs of all GEMM launches of one forward of `batch` images (2·M·N·K each; the

@@ -340,7 +340,8 @@ DFD_API int64_t dfd_engine_workspace_bytes(const dfd_engine* e);
  * per kernel family (ms4/count4 index: 0 GEMM, 1 attention, 2 LayerNorm, 3 other) and clears the record. */
 DFD_API int dfd_engine_profile(dfd_engine* e, int forwards);
 DFD_API int dfd_engine_profile_read(dfd_engine* e, float* ms4, int* count4);
-/* Same with n families: 0 GEMM, 1 attention, 2 LayerNorm, 3 patchify, 4 MAP attention (n < 5 folds the rest into n - 1). */
+/* Same with n families: 0 GEMM (patch embedding, pooling head; with n <= 5 also the encoder GEMMs), 1 attention, 2 LayerNorm,
+ * 3 patchify, 4 MAP attention, 5 qkv GEMM, 6 out-projection GEMM, 7 fc1 GEMM, 8 fc2 GEMM (families >= n fold into n - 1). */
 DFD_API int dfd_engine_profile_read_families(dfd_engine* e, int n, float* ms, int* count);
 
 #ifdef __cplusplus
