@@ -312,7 +312,10 @@ int patchify(const void* pixels, int pix_format, int B, int Hin, int Win, int S,
   a.pixels = pixels;
   a.fmt = pix_format;
   a.B = B; a.Hin = Hin; a.Win = Win; a.S = S; a.P = P; a.G = S / P; a.K = K;
-  a.mode = (Hin >= GP && Hin < GP + P && Win >= GP && Win < GP + P) ? 0 : resize_mode;
+  // images at the model resolution take the patch grid directly; with a resample mode given, every other size is resampled
+  // to S x S first, exactly like the reference's `if x.shape[-1] != res: F.interpolate(...)` (train_fusion_head_only.py:103-104,
+  // cifake_binary_classifier.py:716-717) — also sizes that happen to cover the patch grid (S < side < GP + P)
+  a.mode = (Hin == S && Win == S) ? 0 : resize_mode;
   a.flip = flip;
   a.sy = (float)Hin / (float)S;
   a.sx = (float)Win / (float)S;

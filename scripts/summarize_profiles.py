@@ -35,7 +35,7 @@ def gz(src, dst):
 
 
 def traffic():
-    path = os.path.join(O, "gemm_dram.csv")
+    path = os.path.join(O, f"{TAG}_gemm_dram.csv")
     if not os.path.exists(path):
         return
     rows = list(csv.reader(open(path)))
@@ -60,7 +60,7 @@ def traffic():
     names = ["qkv", "out+res", "fc1", "fc2+res"]  # launch 0 is the patch embedding, then 4 GEMMs per encoder layer
     meas = {n: sum(tot(1 + 4 * l + j) for l in range(LAYERS)) / LAYERS for j, n in enumerate(names)}
     ms = {n: sum(per[ids[1 + 4 * l + j]]["gpu__time_duration.sum"] for l in range(LAYERS)) / LAYERS / 1e6 for j, n in enumerate(names)}
-    out = os.path.join(P, "gemm_traffic.json")
+    out = os.path.join(P, f"{TAG}_gemm_traffic.json")
     old = json.load(open(out)) if os.path.exists(out) else {}
     old.update({"dram_bytes_per_launch": (rd + wr) / len(ids), "launches": len(ids), "dram_read_bytes_per_step": rd,
                 "dram_write_bytes_per_step": wr, "measured_bytes_per_layer": meas, "ms_under_ncu_per_layer": ms})
@@ -78,19 +78,16 @@ def table(kind, src, dst):
 
 
 if __name__ == "__main__":
-    copy("bench_n1.json", f"{TAG}_bench_so400m_b512.json")
-    copy("bench_n1.json", f"{TAG}_bench_so400m_b512_with_cpu_baseline.json")
-    copy("bench_plain.json", f"{TAG}_bench_plain_for_ncu.json")
-    copy("bench_ref.json", f"{TAG}_bench_reference_arm.json")
-    copy("bench_base224.json", f"{TAG}_bench_base224_b256.json")
-    copy("bench_n2.json", f"{TAG}_bench_so400m_b512_n2.json")
-    copy("bench_n8.json", f"{TAG}_bench_so400m_b512_n8.json")
-    copy("kbench_mem.txt", f"{TAG}_kbench_mem.txt")
-    copy("kbench_gemm_attn.txt", f"{TAG}_kbench_gemm_attn.txt")
-    gz("launches_bench.csv", f"{TAG}_launches_bench.csv.gz")
-    gz("gemm_dram.csv", f"{TAG}_gemm_dram.csv.gz")
+    # scripts/collect_profiles.sh <tag> writes gpurun_out/<tag>_*: bench lines, kbench text and micro-benchmarks are copied as
+    # they are, launch lists are compressed, the --set full reports are reduced to their key metrics
+    for f in sorted(os.listdir(O)):
+        if not f.startswith(TAG + "_"):
+            continue
+        if f.endswith((".json", ".txt")) and os.path.getsize(os.path.join(O, f)) > 0:
+            copy(f, f)
+    gz(f"{TAG}_launches_bench.csv", f"{TAG}_launches_bench.csv.gz")
+    gz(f"{TAG}_gemm_dram.csv", f"{TAG}_gemm_dram.csv.gz")
     traffic()
-    table("launches", "launches_bench.csv", f"{TAG}_auto_launch_table.md")
-    table("full", "prof_bench_gemm.ncu-rep", f"{TAG}_auto_gemm_full.md")
-    table("full", "prof_bench_attn.ncu-rep", f"{TAG}_auto_attention_full.md")
-    table("full", "prof_mem.ncu-rep", f"{TAG}_auto_mem_kernels.md")
+    table("launches", f"{TAG}_launches_bench.csv", f"{TAG}_auto_launch_table.md")
+    table("full", f"{TAG}_prof_bench_gemm.ncu-rep", f"{TAG}_auto_gemm_full.md")
+    table("full", f"{TAG}_prof_bench_attn.ncu-rep", f"{TAG}_auto_attention_full.md")

@@ -321,7 +321,7 @@ def test_patchify_u8_ragged_sides_and_unaligned_base(Hin, Win, skip):
 
 
 @pytest.mark.parametrize("mode,name", [(1, "nearest"), (2, "bilinear")])
-@pytest.mark.parametrize("Hin,S,P", [(32, 224, 16), (100, 60, 14), (300, 224, 16)])
+@pytest.mark.parametrize("Hin,S,P", [(32, 224, 16), (100, 60, 14), (300, 224, 16), (64, 60, 14)])  # 64: covers the 56-pixel patch grid but is not S: resampled, like the reference
 def test_patchify_resize(mode, name, Hin, S, P):
     from dfd import ops
     from oracle import siglip_ref as R
