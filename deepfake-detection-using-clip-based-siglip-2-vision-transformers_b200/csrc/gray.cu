@@ -55,6 +55,18 @@ __global__ void luma_kernel(const uint8_t* __restrict__ rgb, uint8_t* __restrict
   }
 }
 
+// The same for a rectangle of a larger image (a crop given by base pointer + strides): one thread per pixel, rows of the crop
+// are row_stride bytes apart, images image_stride bytes.  Output packed [B, H, W] like luma_kernel's.
+__global__ void __launch_bounds__(256)
+luma_strided_kernel(const uint8_t* __restrict__ rgb, int64_t row_stride, int64_t image_stride, uint8_t* __restrict__ L, int H,
+                    int W) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (x >= W) return;
+  const uint8_t* p = rgb + (int64_t)b * image_stride + (int64_t)y * row_stride + 3 * x;
+  L[((int64_t)b * H + y) * W + x] = (uint8_t)((p[0] * 19595u + p[1] * 38470u + p[2] * 7471u + 0x8000u) >> 16);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // OpenCV CLAHE (8-bit, histSize 256)
 // ---------------------------------------------------------------------------------------------------------
@@ -173,13 +185,14 @@ resample_cols_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, in
 // Generic Pillow 8bpc passes for interleaved images (C = 1 or 3 channels): used by dfd_resize_u8
 // in [B, H, W, C] -> out [B, H, OW, C]
 __global__ void __launch_bounds__(256)
-resize_rows_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int H, int W, int OW, int C,
-                   const int* __restrict__ xmin, const int* __restrict__ count, const int* __restrict__ kk, int ksize) {
+resize_rows_kernel(const uint8_t* __restrict__ in, int64_t row_stride, int64_t image_stride, uint8_t* __restrict__ out, int H,
+                   int OW, int C, const int* __restrict__ xmin, const int* __restrict__ count, const int* __restrict__ kk,
+                   int ksize) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;  // (xx, c) within the output row
   const int y = blockIdx.y, b = blockIdx.z;
   if (e >= OW * C) return;
   const int xx = e / C, c = e - xx * C;
-  const uint8_t* row = in + ((int64_t)b * H + y) * W * C + c;
+  const uint8_t* row = in + (int64_t)b * image_stride + (int64_t)y * row_stride + c;   // dense input: strides W·C and H·W·C
   const int x0 = xmin[xx], n = count[xx];
   const int* k = kk + xx * ksize;
   int acc = 1 << (kPrecisionBits - 1);
@@ -293,15 +306,30 @@ extern "C" DFD_API int dfd_gray256(const void* rgb_u8, int B, int H, int W, int 
                                    const int32_t* count_w, const int32_t* kk_w, int ksize_w, const int32_t* xmin_h,
                                    const int32_t* count_h, const int32_t* kk_h, int ksize_h, void* scratch,
                                    float* gray256, void* stream) {
+  return dfd_gray256_strided(rgb_u8, 0, 0, B, H, W, clahe, xmin_w, count_w, kk_w, ksize_w, xmin_h, count_h, kk_h, ksize_h, scratch,
+                             gray256, stream);
+}
+
+// The same for rectangles of larger images: the crop's rows are row_stride bytes apart and consecutive crops image_stride bytes
+// (0 / 0 = dense [B,H,W,3]).  A crop of a resident image is (base + (y0·W_img + x0)·3, row_stride = W_img·3): the views of
+// detect_core / the patch grid are produced from ONE upload of the original without a copy per view.
+extern "C" DFD_API int dfd_gray256_strided(const void* rgb_u8, int64_t row_stride, int64_t image_stride, int B, int H, int W,
+                                           int clahe, const int32_t* xmin_w, const int32_t* count_w, const int32_t* kk_w,
+                                           int ksize_w, const int32_t* xmin_h, const int32_t* count_h, const int32_t* kk_h,
+                                           int ksize_h, void* scratch, float* gray256, void* stream) {
   using namespace dfd;
+  if (row_stride == 0) row_stride = (int64_t)W * 3;
+  if (image_stride == 0) image_stride = (int64_t)H * row_stride;
+  DFD_REQUIRE(row_stride >= (int64_t)W * 3, DFD_ERR_SHAPE, "gray256: row stride smaller than a row");
+  // the dense kernel reads 12-byte pixel groups as words: packed images at a 4-byte aligned address only
+  const bool dense = row_stride == (int64_t)W * 3 && (B == 1 || image_stride == (int64_t)H * W * 3) && (uintptr_t)rgb_u8 % 4 == 0;
   DFD_REQUIRE(rgb_u8 && scratch && gray256, DFD_ERR_BAD_ARG, "gray256: null pointer");
   DFD_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535 && H <= 65535, DFD_ERR_SHAPE, "gray256: bad shape");
   DFD_REQUIRE(xmin_w && count_w && kk_w && xmin_h && count_h && kk_h, DFD_ERR_BAD_ARG,
               "gray256: resample tables missing");
   DFD_REQUIRE(ksize_w == resample_ksize(W, kOut) && ksize_h == resample_ksize(H, kOut), DFD_ERR_BAD_ARG,
               "gray256: resample tables were built for another size");
-  DFD_REQUIRE((uintptr_t)rgb_u8 % 4 == 0 && (uintptr_t)scratch % 4 == 0, DFD_ERR_BAD_ARG,
-              "gray256: pointers must be 4-byte aligned");
+  DFD_REQUIRE((uintptr_t)scratch % 4 == 0, DFD_ERR_BAD_ARG, "gray256: scratch must be 4-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t npix = (int64_t)B * H * W;
   const int64_t hw = ((int64_t)H * W + 255) / 256 * 256;
@@ -311,8 +339,11 @@ extern "C" DFD_API int dfd_gray256(const void* rgb_u8, int B, int H, int W, int 
   uint8_t* rows = luts + (int64_t)B * kTiles * kTiles * 256;
   DFD_REQUIRE((npix + 3) / 4 / 256 + 1 < (1ll << 31), DFD_ERR_SHAPE, "gray256: batch too large");
   // images are packed back to back in L (B*H*W bytes); the per-image stride hw is only used for sizing
-  luma_kernel<<<(unsigned)(((npix + 3) / 4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(rgb_u8), L,
-                                                                        npix);
+  if (dense)
+    luma_kernel<<<(unsigned)(((npix + 3) / 4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(rgb_u8), L, npix);
+  else
+    luma_strided_kernel<<<dim3((W + 255) / 256, H, B), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(rgb_u8), row_stride,
+                                                                    image_stride, L, H, W);
   DFD_LAUNCH_CHECK();
   int launches = 1;
   const uint8_t* src = L;
@@ -354,7 +385,19 @@ extern "C" DFD_API int dfd_resize_u8(const void* src, int B, int H, int W, int C
                                      const int32_t* count_w, const int32_t* kk_w, int ksize_w, const int32_t* xmin_h,
                                      const int32_t* count_h, const int32_t* kk_h, int ksize_h, void* scratch, void* dst,
                                      void* stream) {
+  return dfd_resize_u8_strided(src, 0, 0, B, H, W, C, OH, OW, xmin_w, count_w, kk_w, ksize_w, xmin_h, count_h, kk_h, ksize_h,
+                               scratch, dst, stream);
+}
+
+// The same for rectangles of larger images (strides in bytes; 0 / 0 = dense), see dfd_gray256_strided.
+extern "C" DFD_API int dfd_resize_u8_strided(const void* src, int64_t row_stride, int64_t image_stride, int B, int H, int W, int C,
+                                             int OH, int OW, const int32_t* xmin_w, const int32_t* count_w, const int32_t* kk_w,
+                                             int ksize_w, const int32_t* xmin_h, const int32_t* count_h, const int32_t* kk_h,
+                                             int ksize_h, void* scratch, void* dst, void* stream) {
   using namespace dfd;
+  if (row_stride == 0) row_stride = (int64_t)W * C;
+  if (image_stride == 0) image_stride = (int64_t)H * row_stride;
+  DFD_REQUIRE(row_stride >= (int64_t)W * C, DFD_ERR_SHAPE, "resize: row stride smaller than a row");
   DFD_REQUIRE(src && dst && scratch, DFD_ERR_BAD_ARG, "resize: null pointer");
   DFD_REQUIRE(B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && (C == 1 || C == 3), DFD_ERR_SHAPE, "resize: bad shape");
   DFD_REQUIRE(B <= 65535 && H <= 65535 && OH <= 65535, DFD_ERR_SHAPE, "resize: B, H, OH must be <= 65535");
@@ -362,8 +405,9 @@ extern "C" DFD_API int dfd_resize_u8(const void* src, int B, int H, int W, int C
               "resize: resample tables missing");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* rows = reinterpret_cast<uint8_t*>(scratch);
-  resize_rows_kernel<<<dim3((OW * C + 255) / 256, H, B), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(src), rows, H, W,
-                                                                      OW, C, xmin_w, count_w, kk_w, ksize_w);
+  resize_rows_kernel<<<dim3((OW * C + 255) / 256, H, B), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(src), row_stride,
+                                                                      image_stride, rows, H, OW, C, xmin_w, count_w, kk_w,
+                                                                      ksize_w);
   DFD_LAUNCH_CHECK();
   resize_cols_kernel<<<dim3((OW * C + 255) / 256, OH, B), 256, 0, st>>>(rows, reinterpret_cast<uint8_t*>(dst), H, OH,
                                                                        OW * C, xmin_h, count_h, kk_h, ksize_h);

@@ -262,32 +262,42 @@ def _resample_tables(size: int, device, out_size: int = 256, filter: str = "bicu
     return _RESAMPLE_TABLES[key]
 
 
+def _rect_strides(images: torch.Tensor):
+    """(tensor, row_stride_bytes, image_stride_bytes) of a u8 [B,H,W,C] tensor whose pixels are contiguous within a row — a dense
+    batch or a rectangle cut out of a larger image (`img[y0:y1, x0:x1][None]`); anything else is copied."""
+    B, H, W, Cn = images.shape
+    if images.stride(3) != 1 or images.stride(2) != Cn or (H > 1 and images.stride(1) < W * Cn):
+        images = images.contiguous()
+    return images, images.stride(1) if H > 1 else W * Cn, images.stride(0) if B > 1 else 0
+
+
 def resize_u8(images: torch.Tensor, out_h: int, out_w: int, filter: str = "bilinear") -> torch.Tensor:
-    """u8 images [B,H,W,C] (C = 1 or 3, device) -> [B,out_h,out_w,C] u8, bit-exact with PIL `Image.resize((out_w, out_h),
-    BILINEAR|BICUBIC)` — torchvision `transforms.Resize` on PIL inputs (inference_ai_human_images.py:200-204)."""
+    """u8 images [B,H,W,C] (C = 1 or 3, device; dense or a rectangle view of a larger image) -> [B,out_h,out_w,C] u8, bit-exact
+    with PIL `Image.resize((out_w, out_h), BILINEAR|BICUBIC)` — torchvision `transforms.Resize` on PIL inputs
+    (inference_ai_human_images.py:200-204)."""
     _need_cuda(images)
-    assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[3] in (1, 3) and images.is_contiguous()
+    assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[3] in (1, 3)
+    images, rs, ims = _rect_strides(images)
     B, H, W, C = images.shape
     xw, cw, kw = _resample_tables(W, images.device, out_w, filter)
     xh, ch, kh = _resample_tables(H, images.device, out_h, filter)
     scratch = torch.empty((B, H, out_w, C), dtype=torch.uint8, device=images.device)
     out = torch.empty((B, out_h, out_w, C), dtype=torch.uint8, device=images.device)
-    check(_lib.load().dfd_resize_u8(images.data_ptr(), B, H, W, C, out_h, out_w, xw.data_ptr(), cw.data_ptr(), kw.data_ptr(),
-                                    kw.shape[1], xh.data_ptr(), ch.data_ptr(), kh.data_ptr(), kh.shape[1], scratch.data_ptr(),
-                                    out.data_ptr(), current_stream()))
+    check(_lib.load().dfd_resize_u8_strided(images.data_ptr(), rs, ims, B, H, W, C, out_h, out_w, xw.data_ptr(), cw.data_ptr(),
+                                            kw.data_ptr(), kw.shape[1], xh.data_ptr(), ch.data_ptr(), kh.data_ptr(), kh.shape[1],
+                                            scratch.data_ptr(), out.data_ptr(), current_stream()))
     return out
 
 
 def gray256_from_rgb(images: torch.Tensor, clahe: bool, scratch: Optional[torch.Tensor] = None,
                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """u8 RGB images [B,H,W,3] (NHWC, device) -> gray256 f32 [B,256,256] in [0,1] (dfd_gray256): Pillow 'L' luma,
-    optional OpenCV CLAHE(2.0, 8x8), Pillow bicubic resize, /255 — train_fusion_head_only.py:142-148 (clahe=True),
-    deepfake-detector-v2/app.py:736-749.  EXIF orientation is the decoder's business (apply ImageOps.exif_transpose
-    before handing pixels over, as the reference does)."""
+    """u8 RGB images [B,H,W,3] (NHWC, device; dense or a rectangle view of a larger image) -> gray256 f32 [B,256,256] in [0,1]
+    (dfd_gray256[_strided]): Pillow 'L' luma, optional OpenCV CLAHE(2.0, 8x8), Pillow bicubic resize, /255 —
+    train_fusion_head_only.py:142-148 (clahe=True), deepfake-detector-v2/app.py:736-749.  EXIF orientation is the decoder's
+    business (apply ImageOps.exif_transpose before handing pixels over, as the reference does)."""
     _need_cuda(images)
-    assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[3] == 3 and images.is_contiguous()
-    if images.data_ptr() % 4:   # a contiguous row slice of a larger image (full-width crop) may start at any byte
-        images = images.clone()
+    assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[3] == 3
+    images, rs, ims = _rect_strides(images)
     B, H, W, _ = images.shape
     lib = _lib.load()
     need = lib.dfd_gray256_scratch_bytes(B, H, W)
@@ -297,9 +307,9 @@ def gray256_from_rgb(images: torch.Tensor, clahe: bool, scratch: Optional[torch.
     xh, ch, kh = _resample_tables(H, images.device)
     if out is None:
         out = torch.empty((B, 256, 256), dtype=torch.float32, device=images.device)
-    check(lib.dfd_gray256(images.data_ptr(), B, H, W, int(clahe), xw.data_ptr(), cw.data_ptr(), kw.data_ptr(),
-                          kw.shape[1], xh.data_ptr(), ch.data_ptr(), kh.data_ptr(), kh.shape[1], scratch.data_ptr(),
-                          out.data_ptr(), current_stream()))
+    check(lib.dfd_gray256_strided(images.data_ptr(), rs, ims, B, H, W, int(clahe), xw.data_ptr(), cw.data_ptr(), kw.data_ptr(),
+                                  kw.shape[1], xh.data_ptr(), ch.data_ptr(), kh.data_ptr(), kh.shape[1], scratch.data_ptr(),
+                                  out.data_ptr(), current_stream()))
     return out
 
 

@@ -323,8 +323,8 @@ class DetectionPipeline:
                 gs.append(ops.gray256_from_rgb(v, clahe))
             else:
                 x0, y0, x1, y1 = r
-                crop = img[y0:y1, x0:x1].contiguous()[None]
-                xs.append(crop if crop.shape[1:3] == (S, S) else ops.resize_u8(crop, S, S, filter))
+                crop = img[y0:y1, x0:x1][None]        # a view: the kernels take the rectangle's base pointer and strides
+                xs.append(crop.contiguous() if crop.shape[1:3] == (S, S) else ops.resize_u8(crop, S, S, filter))
                 gs.append(ops.gray256_from_rgb(crop, clahe))
         return torch.cat(xs, 0), torch.cat(gs, 0)
 

@@ -215,6 +215,18 @@ enum { DFD_FILTER_BILINEAR = 2, DFD_FILTER_BICUBIC = 3 };   /* PIL.Image.BILINEA
 DFD_API int dfd_resample_ksize_filter(int in_size, int out_size, int filter);
 DFD_API int dfd_resample_coeffs_filter_host(int in_size, int out_size, int filter, int32_t* xmin_host,
                                             int32_t* count_host, int32_t* kk_host);
+/* Strided forms of dfd_resize_u8 / dfd_gray256: the source is a rectangle of a larger image — rows row_stride bytes apart,
+ * consecutive rectangles image_stride bytes apart (0 / 0 = dense).  A crop (x0, y0, w, h) of a resident u8 RGB image of width Wi is
+ * (base + (y0·Wi + x0)·3, row_stride = Wi·3): the multicrop views of detect_core (deepfake-detector-v2/app.py:1418-1430,
+ * appv3.py:3315-3350) and the patch-grid cells (:1461-1485) come from one upload, without a copy per view. */
+DFD_API int dfd_resize_u8_strided(const void* src, int64_t row_stride, int64_t image_stride, int B, int H, int W, int C, int OH,
+                                  int OW, const int32_t* xmin_w, const int32_t* count_w, const int32_t* kk_w, int ksize_w,
+                                  const int32_t* xmin_h, const int32_t* count_h, const int32_t* kk_h, int ksize_h, void* scratch,
+                                  void* dst, void* stream);
+DFD_API int dfd_gray256_strided(const void* rgb_u8, int64_t row_stride, int64_t image_stride, int B, int H, int W, int clahe,
+                                const int32_t* xmin_w, const int32_t* count_w, const int32_t* kk_w, int ksize_w,
+                                const int32_t* xmin_h, const int32_t* count_h, const int32_t* kk_h, int ksize_h, void* scratch,
+                                float* gray256, void* stream);
 DFD_API int dfd_resize_u8(const void* src, int B, int H, int W, int C, int OH, int OW, const int32_t* xmin_w,
                           const int32_t* count_w, const int32_t* kk_w, int ksize_w, const int32_t* xmin_h,
                           const int32_t* count_h, const int32_t* kk_h, int ksize_h, void* scratch, void* dst,

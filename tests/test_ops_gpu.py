@@ -875,3 +875,26 @@ def test_layernorm_two_bf16_input():
     torch.cuda.synchronize()
     assert float((y.float() - ref).abs().max()) < 2e-2       # bf16 output rounding of values up to ~4
     assert float((y.float() - ref).abs().mean()) <= float((ops.layernorm_bf16(hi, gamma, beta).float() - ref).abs().mean())
+
+
+@pytest.mark.parametrize("clahe", [False, True])
+def test_gray256_and_resize_on_rectangles_of_a_resident_image(clahe):
+    """dfd_gray256_strided / dfd_resize_u8_strided: a crop handed over as base pointer + strides (a torch view of the resident
+    image, no copy) gives bit for bit what the dense kernels give on a contiguous copy of the crop — odd offsets, odd sizes,
+    full-width slices at unaligned addresses, and a batch of same-size crops of a [B,H,W,3] stack."""
+    from dfd import ops
+
+    g = torch.Generator().manual_seed(3)
+    img = torch.randint(0, 256, (301, 413, 3), dtype=torch.uint8, generator=g).to(DEV)
+    for (x0, y0, x1, y1) in [(0, 0, 413, 301), (7, 3, 260, 200), (101, 55, 413, 301), (0, 151, 413, 301), (33, 0, 34, 301),
+                             (5, 9, 205, 10)]:
+        view = img[y0:y1, x0:x1][None]
+        dense = view.contiguous().clone()
+        assert torch.equal(ops.gray256_from_rgb(view, clahe), ops.gray256_from_rgb(dense, clahe)), (x0, y0, x1, y1)
+        for filt in ("bilinear", "bicubic"):
+            assert torch.equal(ops.resize_u8(view, 60, 60, filt), ops.resize_u8(dense, 60, 60, filt)), (x0, y0, x1, y1, filt)
+    stack = torch.randint(0, 256, (3, 120, 200, 3), dtype=torch.uint8, generator=g).to(DEV)
+    view = stack[:, 11:97, 20:175]
+    assert not view.is_contiguous()
+    assert torch.equal(ops.gray256_from_rgb(view, clahe), ops.gray256_from_rgb(view.contiguous(), clahe))
+    assert torch.equal(ops.resize_u8(view, 64, 48), ops.resize_u8(view.contiguous(), 64, 48))
