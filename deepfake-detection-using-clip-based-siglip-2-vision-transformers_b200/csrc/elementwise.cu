@@ -44,7 +44,9 @@ layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __
   if (row >= M) return;
   const int nvec = D >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)row * ldx);
-  const uint4* lr = LO ? reinterpret_cast<const uint4*>(lo + (int64_t)row * ldlo) : nullptr;
+  // the low halves are stored in the GEMM epilogue's order: [row block of 128][64-column chunk][8-column group][row][8]
+  const int nch = (D + 63) >> 6;
+  const uint4* lr = LO ? reinterpret_cast<const uint4*>(lo) + (int64_t)(row >> 7) * nch * 1024 + (row & 127) : nullptr;
   uint4 v[kMaxVec], w[LO ? kMaxVec : 1];
   w[0] = make_uint4(0u, 0u, 0u, 0u);
   float sum = 0.f;
@@ -53,7 +55,7 @@ layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __
     const int c = lane + i * 32;
     if (c < nvec) {
       v[i] = __ldg(xr + c);
-      if (LO) w[i] = __ldg(lr + c);
+      if (LO) w[i] = __ldg(lr + (c >> 3) * 1024 + (c & 7) * 128);
       const float2 a = ln_val<LO>(v[i], w[LO ? i : 0], 0), b = ln_val<LO>(v[i], w[LO ? i : 0], 1), c2 = ln_val<LO>(v[i], w[LO ? i : 0], 2),
                    d = ln_val<LO>(v[i], w[LO ? i : 0], 3);
       sum += ((a.x + a.y) + (b.x + b.y)) + ((c2.x + c2.y) + (d.x + d.y));
@@ -264,7 +266,7 @@ int layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const float
               "layernorm: D must be a multiple of 8 and <= %d (D=%d)", kMaxVec * 256, D);
   DFD_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= D && ldy >= D, DFD_ERR_SHAPE,
               "layernorm: leading dimensions must be multiples of 8 and >= D");
-  DFD_REQUIRE(lo == nullptr || (ldlo % 8 == 0 && ldlo >= D), DFD_ERR_SHAPE, "layernorm: bad leading dimension of lo");
+  (void)ldlo;   // the low halves are tiled: their layout is a function of D
   const int rows_per_cta = kRowThreads / 32;
   const int grid = (M + rows_per_cta - 1) / rows_per_cta;
   if (lo != nullptr)

@@ -565,7 +565,7 @@ static int forward_body(dfd_engine* e, const void* pixels, int pix_format, int B
   // precise mode: x = hi + lo.  The patch embedding leaves lo = 0 (one bf16 rounding, as for every branch input); each
   // residual GEMM then reads and rewrites both halves, so the additions of all 2·L branches accumulate at ~16 mantissa bits
   __nv_bfloat16* lo = e->precise ? e->x_lo : nullptr;
-  if (lo) DFD_CUDA(cudaMemsetAsync(lo, 0, hid_bytes, st));
+  if (lo) DFD_CUDA(cudaMemsetAsync(lo, 0, (size_t)((M + 127) / 128) * 128 * ((D + 63) / 64) * 64 * sizeof(__nv_bfloat16), st));
   if (e->hidden_tap) DFD_CUDA(cudaMemcpyAsync(e->hidden_tap, e->x, hid_bytes, cudaMemcpyDeviceToDevice, st));
   for (int li = 0; li < e->L; ++li) {
     const Layer& l = e->layers[li];
@@ -685,7 +685,8 @@ extern "C" DFD_API int dfd_engine_set_precise_residual(dfd_engine* e, int enable
   DeviceGuard guard(e->device);
   DFD_REQUIRE(guard.ok, DFD_ERR_CUDA, "set_precise_residual: cudaSetDevice failed");
   if (enable && e->x_lo == nullptr)
-    DFD_CUDA(cudaMalloc(&e->x_lo, (size_t)e->max_batch * e->N * e->D * sizeof(__nv_bfloat16)));
+    DFD_CUDA(cudaMalloc(&e->x_lo, (size_t)(((int64_t)e->max_batch * e->N + 127) / 128) * 128 * ((e->D + 63) / 64) * 64 *
+                                      sizeof(__nv_bfloat16)));   // tiled: whole 128-row x 64-column blocks
   if ((enable != 0) != e->precise) {   // captured graphs bake the mode in
     cudaDeviceSynchronize();
     for (auto& g : e->graphs)

@@ -17,9 +17,19 @@ from ._lib import GemmEpilogue, HeadWeights, ScoreWeights, Scores, check, curren
 
 
 def _need_cuda(*ts):
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("dfd ops need CUDA tensors (there is no CPU fallback)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            # the kernels are launched on the current device's stream: pointers of another device would fault (or go
+            # through peer access) instead of failing here
+            raise RuntimeError(f"dfd ops launch on the current device (cuda:{cur}) but an argument lives on {t.device}; "
+                               f"wrap the call in `with torch.cuda.device({t.device.index}):`")
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -56,10 +66,13 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = 0, pos=
     epi.stats_out = _p(stats_out)
     epi.residual_op = residual_op
     epi.ln_parts = 0
-    # two-bf16 residual stream: residual_lo [M, N] bf16 is read with the residual and rewritten in place with the low half
-    # of the new value (see dfd_gemm_epilogue.residual_lo)
+    # two-bf16 residual stream: residual_lo (tiled, ops.lo_to_tiled) is read with the residual and rewritten in place with the
+    # low half of the new value (see dfd_gemm_epilogue.residual_lo)
     epi.residual_lo = _p(residual_lo)
-    epi.ldlo = 0 if residual_lo is None else residual_lo.stride(0)
+    epi.ldlo = 0
+    if residual_lo is not None:
+        assert residual_lo.dtype == torch.bfloat16 and residual_lo.is_contiguous() and \
+            tuple(residual_lo.shape) == ((M + 127) // 128, (N + 63) // 64, 8, 128, 8), "residual_lo: see ops.lo_to_tiled"
     if ln_rowstats is not None:
         assert ln_rowstats.dtype == torch.float32 and ln_rowstats.is_contiguous() and ln_rowstats.shape[-2:] == (M, 2)
         epi.ln_parts = ln_rowstats.shape[0] if ln_rowstats.dim() == 3 else 1
@@ -75,6 +88,21 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = 0, pos=
                                out.stride(0), M, N, K, C.byref(epi), current_stream())
     check(rc)
     return out
+
+
+def lo_to_tiled(lo: torch.Tensor) -> torch.Tensor:
+    """Row-major bf16 [M, N] -> the tiled layout of dfd_gemm_epilogue.residual_lo: [ceil(M/128)][ceil(N/64)][8][128][8]."""
+    M, N = lo.shape
+    Mp, Np = (M + 127) // 128 * 128, (N + 63) // 64 * 64
+    pad = torch.zeros((Mp, Np), dtype=lo.dtype, device=lo.device)
+    pad[:M, :N] = lo
+    return pad.view(Mp // 128, 128, Np // 64, 8, 8).permute(0, 2, 3, 1, 4).contiguous()
+
+
+def lo_from_tiled(t: torch.Tensor, M: int, N: int) -> torch.Tensor:
+    """Inverse of lo_to_tiled."""
+    mb, nc = t.shape[0], t.shape[1]
+    return t.permute(0, 3, 1, 2, 4).reshape(mb * 128, nc * 64)[:M, :N].contiguous()
 
 
 def layernorm_bf16(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:

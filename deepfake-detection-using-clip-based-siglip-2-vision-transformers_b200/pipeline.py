@@ -53,6 +53,19 @@ def head_params_from_state(sd: Dict[str, torch.Tensor], dim: int, device) -> "op
     return ops.HeadParams(1, dim, 0.0, device, ln=ln, layers=layers)
 
 
+def _on_own_device(fn):
+    """Run a pipeline method with the pipeline's GPU as the current device (its kernels are launched on the current device's
+    stream), whatever device the caller has selected."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+
+    return wrapped
+
+
 class DetectionPipeline:
     def __init__(self, arch: VisionArch | str, backbone_state: Dict[str, torch.Tensor],
                  head_state: Dict[str, torch.Tensor], scoring: ScoringStack, device: int = 0, max_batch: int = 64,
@@ -98,6 +111,7 @@ class DetectionPipeline:
         return r
 
     # ---- device-resident path ---------------------------------------------------------------------
+    @_on_own_device
     def detect_device(self, images: torch.Tensor, gray256: Optional[torch.Tensor] = None, resize_mode: int = 0,
                       clahe: bool = True, pil_resize: Optional[str] = None) -> Dict[str, torch.Tensor]:
         """images: u8 NHWC on the device.  gray256 None = derive it from the same (original-size) pixels on the device
@@ -140,6 +154,7 @@ class DetectionPipeline:
                 pil.crop((0, h2, w2, h)), pil.crop((w2, h2, w, h))]
 
     @torch.no_grad()
+    @_on_own_device
     def detect_core(self, pils, multicrop: bool = True, clahe: bool = False, preprocess=None, freq_temp: float = 1.25):
         """Batched `detect_core`: every crop of every image goes through ONE backbone / feature batch, crop logits
         are combined with the reference's weights (on logits, app.py:1346-1347), then one score epilogue per image.
@@ -179,6 +194,7 @@ class DetectionPipeline:
         return res
 
     # ---- streaming host-buffer path: the public throughput API ---------------------------------------------------------
+    @_on_own_device
     def detect_many(self, batches, resize_mode: int = 0, clahe: bool = True, pil_resize: Optional[str] = None,
                     in_flight: int = 2, on_result=None):
         """Host u8 NHWC batches (an iterable; pinned tensors copy asynchronously) -> list of numpy [B_i,14] score records,
@@ -311,6 +327,7 @@ class DetectionPipeline:
         out[~ok] = 0
         return out.contiguous()
 
+    @_on_own_device
     def views_on_device(self, img: torch.Tensor, rects, clahe: bool, filter: str = "bilinear"):
         """img: u8 [H,W,3] on the device.  rects: (x0,y0,x1,y1) crops, or "bicubic" = the whole image resized to S x S with
         PIL's bicubic filter.  Returns (model input u8 [V,S,S,3], gray256 f32 [V,256,256])."""
@@ -340,6 +357,7 @@ class DetectionPipeline:
         return t.contiguous()
 
     @torch.no_grad()
+    @_on_own_device
     def detect_core_device(self, images, views: Optional[str] = "v2", rot90: bool = False, clahe: bool = False,
                            freq_temp: float = 1.25):
         """`detect_core` for a list of images with every view produced on the device.
@@ -397,6 +415,7 @@ class DetectionPipeline:
         return res
 
     @torch.no_grad()
+    @_on_own_device
     def patch_grid(self, image, rows: int = 4, cols: int = 4, clahe: bool = False, min_side: int = 64):
         """`compute_patch_grid` (deepfake-detector-v2/app.py:1461-1485): p_fake_raw of every grid cell, all rows x cols cells
         of the image in ONE batch (the reference runs one batch-1 detect_core per cell).  Returns (grid [rows,cols] f32,
@@ -420,6 +439,7 @@ class DetectionPipeline:
         return grid, [float(v) for v in grid.reshape(-1)]
 
     @torch.no_grad()
+    @_on_own_device
     def frame_features(self, frames: torch.Tensor, filter: str = "bilinear") -> torch.Tensor:
         """Video path (hidf_video_classifier.py:299-320): u8 frames [F,H,W,3] (host or device, one upload) -> L2-normalised
         per-frame embeddings f32 [F,D]; `frame_features(...).mean(0)` is the reference's temporal average pool."""
@@ -431,6 +451,7 @@ class DetectionPipeline:
         return ops.head_fwd(ops.HeadParams(0, self.arch.hidden_size, 0.0, self.device), pooled, want_features=True)[0]
 
     # ---- host-buffer path (what a caller of the reference loops sees) -----------------------------------
+    @_on_own_device
     def detect(self, images_host: torch.Tensor, gray256_host: Optional[torch.Tensor] = None, resize_mode: int = 0,
                clahe: bool = True, pil_resize: Optional[str] = None) -> np.ndarray:
         """Host (ideally pinned) u8 NHWC images [+ f32 gray256; None = computed on the device from the same

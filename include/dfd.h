@@ -82,11 +82,13 @@ typedef struct dfd_gemm_epilogue {
   float* stats_out;          /* [ceil(N/64)][M][2] fp32 partials (see above), or NULL */
   int residual_op;           /* 0: v += residual (default), 1: v *= residual (gating: Siglip2sidafrozen.py:737) */
   int ln_parts;              /* partial pairs per row in ln_rowstats; 0 or 1 = plain [M,2] (dfd_rowstats_bf16) */
-  void* residual_lo;         /* bf16 [M, ldlo] or NULL: low half of a two-bf16 residual stream.  With it the epilogue value is
+  void* residual_lo;         /* bf16 or NULL: low half of a two-bf16 residual stream.  With it the epilogue value is
                               * v = ... + residual + residual_lo (read only when residual is given), C = hi = bf16(v) and
                               * residual_lo = bf16(v - hi) is written back (in place), so the stream carries ~16 mantissa bits
-                              * across layers like the fp32 residual of the reference's autocast path */
-  int64_t ldlo;
+                              * across layers like the fp32 residual of the reference's autocast path.  Layout (private to the
+                              * epilogue and dfd_layernorm2_bf16, coalesced for the epilogue's row-per-lane mapping):
+                              * [ceil(M/128)][ceil(N/64)][8][128][8] = (row block, 64-column chunk, 8-column group, row, column) */
+  int64_t ldlo;              /* unused */
 } dfd_gemm_epilogue;
 
 /* C[M,N] (bf16) = epi(A[M,K] (bf16, lda) · W[N,K]ᵀ (bf16, ldw)), fp32 accumulate in TMEM.
@@ -114,7 +116,7 @@ DFD_API int64_t dfd_gemm_variant_launches(int variant);
  * HF:modeling_siglip.py:348,357 (layer_norm1/2), :618 (post_layernorm). */
 DFD_API int dfd_layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,
                                const float* beta, int M, int D, float eps, void* stream);
-/* The same over the two-bf16 row x + lo (see dfd_gemm_epilogue.residual_lo, dfd_engine_set_precise_residual). */
+/* The same over the two-bf16 row x + lo, lo in the tiled layout of dfd_gemm_epilogue.residual_lo (ldlo unused). */
 DFD_API int dfd_layernorm2_bf16(const void* x, int64_t ldx, const void* lo, int64_t ldlo, void* y, int64_t ldy,
                                 const float* gamma, const float* beta, int M, int D, float eps, void* stream);
 /* stats[M,2] = (Σx, Σx²) of bf16 rows (feeds the LN-folded GEMM epilogue when the producer was not a GEMM). */

@@ -839,10 +839,12 @@ def test_gemm_two_bf16_residual_stream(M, N, K, tile_n):
     lo = (x - hi.float()).to(torch.bfloat16)
     ref = a.float() @ w.float().T + bias + hi.float() + lo.float()
     stats = torch.zeros(((N + 63) // 64, M, 2), dtype=torch.float32, device=DEV)
-    out_hi, out_lo = hi.clone(), lo.clone()
-    ops.gemm_bf16(a, w, bias=bias, residual=out_hi, residual_lo=out_lo, stats_out=stats, out=out_hi, tile_n=tile_n)
+    out_hi, lo_t = hi.clone(), ops.lo_to_tiled(lo)
+    assert torch.equal(ops.lo_from_tiled(lo_t, M, N), lo)
+    ops.gemm_bf16(a, w, bias=bias, residual=out_hi, residual_lo=lo_t, stats_out=stats, out=out_hi, tile_n=tile_n)
     torch.cuda.synchronize()
     assert ops.gemm_last_variant()["epi"] == 7
+    out_lo = ops.lo_from_tiled(lo_t, M, N)
     got = out_hi.float() + out_lo.float()
     scale = ref.abs().clamp_min(1.0)
     # fp32 accumulation order differs from torch's: allow 2e-5 relative for that; a one-tensor bf16 stream would sit at 2e-3
@@ -852,10 +854,10 @@ def test_gemm_two_bf16_residual_stream(M, N, K, tile_n):
     assert torch.allclose(st[:, 0], out_hi.float().sum(1), rtol=1e-4, atol=1e-2)
     assert torch.allclose(st[:, 1], (out_hi.float() ** 2).sum(1), rtol=1e-4, atol=1e-2)
     # without statistics (the last layer's fc2)
-    out_hi2, out_lo2 = hi.clone(), lo.clone()
-    ops.gemm_bf16(a, w, bias=bias, residual=out_hi2, residual_lo=out_lo2, out=out_hi2, tile_n=tile_n)
+    out_hi2, lo_t2 = hi.clone(), ops.lo_to_tiled(lo)
+    ops.gemm_bf16(a, w, bias=bias, residual=out_hi2, residual_lo=lo_t2, out=out_hi2, tile_n=tile_n)
     torch.cuda.synchronize()
-    assert torch.equal(out_hi2, out_hi) and torch.equal(out_lo2, out_lo)
+    assert torch.equal(out_hi2, out_hi) and torch.equal(lo_t2, lo_t)
 
 
 def test_layernorm_two_bf16_input():
@@ -869,7 +871,8 @@ def test_layernorm_two_bf16_input():
     lo = (x - hi.float()).to(torch.bfloat16)
     gamma, beta = (1 + 0.1 * torch.randn(D, generator=g)).to(DEV), (0.1 * torch.randn(D, generator=g)).to(DEV)
     y = torch.empty_like(hi)
-    _lib.check(_lib.load().dfd_layernorm2_bf16(hi.data_ptr(), D, lo.data_ptr(), D, y.data_ptr(), D, gamma.data_ptr(), beta.data_ptr(),
+    lo_t = ops.lo_to_tiled(lo)
+    _lib.check(_lib.load().dfd_layernorm2_bf16(hi.data_ptr(), D, lo_t.data_ptr(), 0, y.data_ptr(), D, gamma.data_ptr(), beta.data_ptr(),
                                                M, D, 1e-6, ops.current_stream()))
     ref = torch.nn.functional.layer_norm(hi.float() + lo.float(), (D,), gamma, beta, 1e-6)
     torch.cuda.synchronize()
