@@ -154,12 +154,13 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    path = Path(os.environ.get("DFD_LIB", LIB_PATH))   # development hook: A/B a second build of the same ABI
+    if not path.exists():
         raise ImportError(
-            f"{LIB_PATH} not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
             f"or `make -C {_PKG_DIR / 'csrc'}`. There is no CPU fallback."
         )
-    lib = C.CDLL(os.fspath(LIB_PATH))
+    lib = C.CDLL(os.fspath(path))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
         fn.restype = res

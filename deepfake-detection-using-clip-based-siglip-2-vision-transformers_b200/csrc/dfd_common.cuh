@@ -135,21 +135,38 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// The same with a suspend-time hint: the hardware parks the thread until the phase completes or the hint (ns) runs out, instead of
+// returning after its short default window.  Without it the waiting warps of a warp-specialised kernel (TMA producer, MMA issuer,
+// idle epilogue / softmax warps) poll: a third of all instructions the attention kernel issued in round 2 were SYNCS / BRA / the
+// loop's bookkeeping (profiles/r02_attention.md), taking issue slots from the working warps of the same scheduler and power from
+// a power-capped step.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ uint64_t global_timer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
   return t;
 }
+#ifndef DFD_MBAR_SUSPEND_NS
+#define DFD_MBAR_SUSPEND_NS 1000000u   // 1 ms per hardware-suspended attempt
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  uint32_t spins = 0;
   uint64_t t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xFFFu) == 0) {
-      const uint64_t now = global_timer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > DFD_SPIN_TIMEOUT_NS) __trap();
-    }
+  while (!mbar_try_wait_hint(bar, parity, DFD_MBAR_SUSPEND_NS)) {
+    // (an attempt only fails after its suspend window: this path runs about once per millisecond of waiting)
+    const uint64_t now = global_timer_ns();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > DFD_SPIN_TIMEOUT_NS) __trap();
   }
 }
 
