@@ -268,3 +268,22 @@ def test_pipeline_host_helpers_without_a_device():
     views = p.make_multicrops(Image.new("RGB", (301, 200), (10, 20, 30)))
     assert [v.size for v in views] == [(301, 200), (224, 224), (150, 100), (151, 100), (150, 100), (151, 100)]
     assert len(pipeline.DetectionPipeline.MULTICROP_WEIGHTS) == 6 and abs(sum(pipeline.DetectionPipeline.MULTICROP_WEIGHTS) - 1.0) < 1e-12
+
+
+def test_tiled_layout_of_the_low_halves_round_trips():
+    """ops.lo_to_tiled / lo_from_tiled: the [row block][64-column chunk][8-column group][row][8] order the GEMM epilogue and
+    dfd_layernorm2_bf16 address (element (r, c) at (((r/128·nch + c/64)·8 + (c%64)/8)·128 + r%128)·8 + c%8)."""
+    import torch
+
+    from dfd import ops
+
+    for M, N in ((300, 200), (128, 64), (1, 8), (777, 1152)):
+        lo = torch.randn(M, N).to(torch.bfloat16)
+        t = ops.lo_to_tiled(lo)
+        nch = (N + 63) // 64
+        assert tuple(t.shape) == ((M + 127) // 128, nch, 8, 128, 8)
+        assert torch.equal(ops.lo_from_tiled(t, M, N), lo)
+        flat = t.reshape(-1)
+        for r, c in ((0, 0), (M - 1, N - 1), (M // 2, N // 3), (min(M - 1, 129), min(N - 1, 70))):
+            idx = (((r // 128 * nch + c // 64) * 8 + (c % 64) // 8) * 128 + r % 128) * 8 + c % 8
+            assert flat[idx] == lo[r, c], (M, N, r, c)
