@@ -42,13 +42,16 @@ def load_peaks():
 
 
 def load_traffic():
-    """dram bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the step's GEMM launches)
-    from the committed ncu --set full capture, profiles/gemm_traffic.json; None if absent."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as f:
-            return float(json.load(f)["dram_bytes_per_launch"])
-    except Exception:
-        return None
+    """dram bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the 113 GEMM launches of one step)
+    from the committed ncu capture of this command, profiles/r02_gemm_traffic.json; None if absent.  Reported beside
+    `roofline.traffic` (which stays null unless --gemm-traffic is given): it was not measured in this run."""
+    for name in ("r02_gemm_traffic.json", "gemm_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return {"dram_bytes_per_launch": float(json.load(f)["dram_bytes_per_launch"]), "source": "profiles/" + name}
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -184,12 +187,36 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def hbm_entry(name, bytes_per_call, ms, calls, peak):
+def hbm_entry(name, bytes_per_image, images, ms, calls, peak):
     if not calls or ms <= 0:
         return None
-    ach = bytes_per_call * calls / (ms / 1e3) / 1e9
-    return {"kernel": name, "bound": "hbm", "algorithmic_bytes_per_call": int(bytes_per_call), "calls": calls,
-            "avg_ms": ms / calls, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
+    ach = bytes_per_image * images / (ms / 1e3) / 1e9
+    return {"kernel": name, "bound": "hbm", "algorithmic_bytes_per_image": int(bytes_per_image), "images": int(images),
+            "calls": calls, "avg_ms": ms / calls, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
+
+
+def unit_plan(total_images: int, world: int, B: int, sub: int):
+    """The work queue's units as (first image, images).  One GPU: whole batches.  Several GPUs: `sub`-image units for the bulk
+    of the work, then a tail of half- and quarter-size units (2 x world of each), so that the ranks finish within a quarter
+    unit of each other instead of a whole one (guided self-scheduling; sizes stay aligned to their offsets)."""
+    if world == 1 or sub >= B and world == 1:
+        return [(o, min(sub, total_images - o)) for o in range(0, total_images, sub)]
+    sizes = [sub // 2, sub // 4] if sub >= 4 and sub % 4 == 0 else []
+    tail = sum(sz * 2 * world for sz in sizes)
+    plan, off = [], 0
+    while total_images - off >= tail + sub:
+        plan.append((off, sub))
+        off += sub
+    for sz in sizes:
+        for _ in range(2 * world):
+            if total_images - off >= sz:
+                plan.append((off, sz))
+                off += sz
+    while off < total_images:
+        sz = min(sizes[-1] if sizes else sub, total_images - off)
+        plan.append((off, sz))
+        off += sz
+    return plan
 
 
 def run_ours(args):
@@ -210,11 +237,10 @@ def run_ours(args):
     arch = ARCHS[arch_name]
     peaks = load_peaks()
     lib = _lib.load()
-    # sub-batch = the unit of the work queue.  One GPU: the whole batch in one call.  Several GPUs: quarters of the per-GPU
-    # batch, so that a step of world x B images is 4 x world units which the ranks share dynamically.
-    sub = args.sub_batch or (B if world == 1 else max(1, B // 4))
+    # sub-batch = the unit of the work queue.  One GPU: the whole batch in one call.  Several GPUs: halves of the per-GPU batch
+    # (256 images run within 0.1 % of a 512-image call, 128 cost 0.6 %), with a tail of shorter units (unit_plan).
+    sub = args.sub_batch or (B if world == 1 else max(1, B // 2))
     sub = min(sub, B)
-    units_per_step = world * ((B + sub - 1) // sub)
 
     bsd = weights.random_vision_state_dict(arch, seed=0, device=dev)
     st = scoring.ScoringStack(dev, weights.random_freq_mlp_g2(2), weights.random_fusion_g2(3), [-1.0, -0.2, 0.3, 1.5], 1.0)
@@ -225,30 +251,32 @@ def run_ours(args):
     S = arch.image_size
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     images = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8, device=dev, generator=g)
-    local_units = (B + sub - 1) // sub
     F = len(pipeline.PACKED_FIELDS)
 
-    def unit_images(u: int, src):
-        j = u % local_units
-        return src[j * sub: min(B, (j + 1) * sub)]
+    def unit_images(unit, src):
+        off, n = unit
+        lo = off % B                       # every rank holds B resident images; a unit is a slice of them
+        return src[lo: lo + n] if lo + n <= B else src[:n]
 
-    def drain_device(n_units: int, key: str, slab):
-        """This rank's share of a queue of n_units sub-batches, inputs resident in HBM; records land in slab[u]."""
+    def drain_device(plan, key: str, slab):
+        """This rank's share of the queue of units `plan`, inputs resident in HBM; the records of unit (off, n) land in
+        slab[off : off + n].  Returns (units, images) taken."""
         q = distributed.WorkQueue(key)
-        inflight, done = [], 0
+        inflight, done, imgs = [], 0, 0
         while True:
             u = q.next()
-            if u >= n_units:
+            if u >= len(plan):
                 break
-            if len(inflight) >= 2:            # keep the host at most two sub-batches ahead of the device
+            if len(inflight) >= 2:            # keep the host at most two units ahead of the device
                 inflight.pop(0).synchronize()
-            x = unit_images(u, images)
-            slab[u, : x.shape[0]] = pipe.pack(pipe.detect_device(x, None, clahe=True))
+            off, n = plan[u]
+            slab[off: off + n] = pipe.pack(pipe.detect_device(unit_images(plan[u], images), None, clahe=True))
             ev = torch.cuda.Event()
             ev.record()
             inflight.append(ev)
             done += 1
-        return done
+            imgs += n
+        return done, imgs
 
     def gather(slab):
         # every unit was filled by exactly one rank and is zero elsewhere: a sum over ranks IS the all-gather of the score
@@ -258,15 +286,26 @@ def run_ours(args):
         return slab
 
     warm = max(args.warmup, 3)
-    slab = torch.zeros((warm * units_per_step, sub, F), dtype=torch.float32, device=dev)
-    drain_device(warm * units_per_step, "dfd_bench_warm", slab)
+    per_step = world * B
+    slab = torch.zeros((warm * per_step, F), dtype=torch.float32, device=dev)
+    t_w = time.perf_counter()
+    drain_device(unit_plan(warm * per_step, world, B, sub), "dfd_bench_warm", slab)
     gather(slab)
     torch.cuda.synchronize()
+    # short steps (base-224: 10 ms) would start the timed region while the clocks are still ramping: warm up for at least ~1.5 s
+    step_s = max((time.perf_counter() - t_w) / warm, 1e-4)
+    extra = int(distributed.max_over_ranks(max(0.0, 1.5 - warm * step_s) / step_s, dev))
+    if extra > 0:
+        slab = torch.zeros((extra * per_step, F), dtype=torch.float32, device=dev)
+        drain_device(unit_plan(extra * per_step, world, B, sub), "dfd_bench_warm2", slab)
+        gather(slab)
+        torch.cuda.synchronize()
+        warm += extra
 
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------------
     # no instrumentation inside: the engine forward runs as it does in production (CUDA-graph replay when --graphs 1)
-    n_units = args.steps * units_per_step
-    slab = torch.zeros((n_units, sub, F), dtype=torch.float32, device=dev)
+    plan = unit_plan(args.steps * per_step, world, B, sub)
+    slab = torch.zeros((args.steps * per_step, F), dtype=torch.float32, device=dev)
     sampler = ClockSampler(local)
     launches0 = lib.dfd_launch_count()
     replays0 = pipe.engine.graph_replays
@@ -274,7 +313,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e0, eb, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
-    mine = drain_device(n_units, "dfd_bench_timed", slab)
+    mine, mine_images = drain_device(plan, "dfd_bench_timed", slab)
     eb.record()                      # this rank's own kernels end here; what follows is waiting for the others
     gather(slab)
     e1.record()
@@ -288,15 +327,15 @@ def run_ours(args):
 
     # ---- profiled pass (not part of `value`): the same work with every launch of the engine bracketed by CUDA events on its
     # stream (eager launches), read back once at the end — per-family / per-GEMM-type durations for the roofline entries
-    slab_p = torch.zeros((n_units, sub, F), dtype=torch.float32, device=dev)
+    slab_p = torch.zeros((args.steps * per_step, F), dtype=torch.float32, device=dev)
     chunks_per_unit = (sub + pipe.engine.max_batch - 1) // pipe.engine.max_batch
-    pipe.engine.profile(n_units * chunks_per_unit)   # room for the case that this rank takes every unit
+    pipe.engine.profile(len(plan) * chunks_per_unit)   # room for the case that this rank takes every unit
     pipe.profile_stages(True)
     distributed.barrier()
     torch.cuda.synchronize()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
-    mine_p = drain_device(n_units, "dfd_bench_profiled", slab_p)
+    _, images_p = drain_device(plan, "dfd_bench_profiled", slab_p)
     p1.record()
     torch.cuda.synchronize()
     fam_all = pipe.engine.profile_read(by_gemm_type=True)
@@ -307,9 +346,9 @@ def run_ours(args):
     prof_busy_ms = p0.elapsed_time(p1)
     distributed.barrier()
     del slab_p
-    mine_rec = {"rank": rank, "units": mine, "images": mine * sub, "busy_ms": e0.elapsed_time(eb),
+    mine_rec = {"rank": rank, "units": mine, "images": mine_images, "busy_ms": e0.elapsed_time(eb),
                 "wait_ms": eb.elapsed_time(e1), "graph_replays": replays,
-                "profiled_pass": {"images": mine_p * sub, "busy_ms": prof_busy_ms,
+                "profiled_pass": {"images": images_p, "busy_ms": prof_busy_ms,
                                   "kernel_ms": sum(v[0] for v in fam.values()) + sum(v[0] for v in stages.values())},
                 "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons")}
     per_rank = [mine_rec]
@@ -325,31 +364,32 @@ def run_ours(args):
     h_img = torch.empty((B, S, S, 3), dtype=torch.uint8).pin_memory()
     h_img.copy_(images)
 
-    def drain_host(n: int, key: str):
+    def drain_host(plan_h, key: str):
         q = distributed.WorkQueue(key)
         taken = []
 
         def feed():
             while True:
                 u = q.next()
-                if u >= n:
+                if u >= len(plan_h):
                     return
-                taken.append(u)
-                yield unit_images(u, h_img)
+                taken.append(plan_h[u])
+                yield unit_images(plan_h[u], h_img)
 
         recs = pipe.detect_many(feed(), clahe=True)
-        out = torch.zeros((n, sub, F), dtype=torch.float32)
-        for u, r in zip(taken, recs):
-            out[u, : r.shape[0]] = torch.from_numpy(r)
+        total = plan_h[-1][0] + plan_h[-1][1]
+        out = torch.zeros((total, F), dtype=torch.float32)
+        for (off, n), r in zip(taken, recs):
+            out[off: off + n] = torch.from_numpy(r)
         if world > 1:   # the all-gather of the records (dynamic ownership, see gather())
             out = gather(out.to(dev)).cpu()
         return out, sum(r.shape[0] for r in recs)
 
-    drain_host(4 * units_per_step, "dfd_bench_e2e_warm")   # every input slab of detect_many has been seen twice: graphs captured
+    drain_host(unit_plan(4 * per_step, world, B, sub), "dfd_bench_e2e_warm")   # every input slab of detect_many seen twice: graphs captured
     distributed.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    rec, n_mine = drain_host(n_units, "dfd_bench_e2e")
+    rec, n_mine = drain_host(plan, "dfd_bench_e2e")
     torch.cuda.synchronize()
     dt_e2e = distributed.max_over_ranks(time.perf_counter() - t0, dev)
     distributed.barrier()
@@ -362,7 +402,7 @@ def run_ours(args):
         return
     step_ms = dt / args.steps * 1e3
     busy_ms = prof_busy_ms                   # shares and achieved rates below refer to rank 0's profiled pass
-    my_images = max(mine_p * sub, 1)
+    my_images = max(images_p, 1)
     roof, hbm = None, []
     if fam["gemm"][0] > 0:
         gemm_flops = pipe.engine.gemm_flops(1) * my_images
@@ -376,8 +416,8 @@ def run_ours(args):
                 "launches_per_step": fam["gemm"][1] // args.steps, "avg_launch_ms": fam["gemm"][0] / max(fam["gemm"][1], 1),
                 "traffic": args.gemm_traffic,
                 "traffic_note": "dram bytes are not measurable inside a plain run: pass --gemm-traffic from the ncu capture of "
-                                "this command (scripts/collect_profiles.sh -> profiles/); committed capture: "
-                                f"{load_traffic()} B per GEMM launch",
+                                "this command (scripts/collect_profiles.sh -> profiles/)",
+                "traffic_committed_capture": load_traffic() if args.workload == "so400m-384" else None,
                 "share_of_rank0_busy_time": shares}
         by_type = pipe.engine.gemm_flops_by_type(my_images)
         roof["gemm_by_type"] = {k: {"achieved": by_type[k] / (fam_all[k][0] / 1e3) / 1e12, "frac": by_type[k] / (fam_all[k][0] / 1e3) / 1e12 / peak,
@@ -391,14 +431,13 @@ def run_ours(args):
         # memory-bound kernels: algorithmic bytes per call / CUDA-event time, against the measured copy rate
         hb = float(peaks["hbm_gbs"])
         N, D, Kp = arch.tokens, arch.hidden_size, (3 * arch.patch_size ** 2 + 63) // 64 * 64
-        nb = min(sub, pipe.engine.max_batch)
-        for e in (hbm_entry("patchify_u8_rows_kernel", nb * (3 * S * S + N * Kp * 2), *fam["patchify"], hb),
-                  hbm_entry("map_attention_kernel", nb * N * 2 * D * 2, *fam["map_attention"], hb),
+        for e in (hbm_entry("patchify_u8_rows_kernel", 3 * S * S + N * Kp * 2, my_images, *fam["patchify"], hb),
+                  hbm_entry("map_attention_kernel", N * 2 * D * 2, my_images, *fam["map_attention"], hb),
                   hbm_entry("layernorm_bf16_kernel (post-LN of all tokens + the pooling head's LN)",
-                            (nb * N + nb) * D * 4 / 2, *fam["layernorm"], hb),
+                            (N + 1) * D * 4, my_images, *fam["layernorm"], hb),
                   hbm_entry("gray256: luma + clahe_lut + clahe_apply + resample_rows + resample_cols",
-                            sub * (3 * S * S + 256 * 256 * 4), *stages.get("gray256", (0, 0)), hb),
-                  hbm_entry("freq_rows_kernel + freq_cols_kernel", sub * (256 * 256 * 4 + 96), *stages.get("freq", (0, 0)), hb)):
+                            3 * S * S + 256 * 256 * 4, my_images, *stages.get("gray256", (0, 0)), hb),
+                  hbm_entry("freq_rows_kernel + freq_cols_kernel", 256 * 256 * 4 + 96, my_images, *stages.get("freq", (0, 0)), hb)):
             if e:
                 hbm.append(e)
     line = {
@@ -408,8 +447,9 @@ def run_ours(args):
         "config": {"workload": f"{args.workload}: {arch_name} detect (backbone+H-B head+gray256/CLAHE+freq features+G2 fusion+CORAL)",
                    "per_gpu_batch": B, "global_batch": B * world, "tokens": arch.tokens, "parallelism": f"dp{world}",
                    "sub_batch": sub, "schedule": "one call per step" if world == 1 else
-                   f"work queue of {units_per_step} sub-batches per step shared by the ranks; one all-reduce(sum) of the zero-filled "
-                   "record slab (= all-gather under dynamic ownership) after the last step",
+                   f"work queue of {len(plan)} units ({sub}-image units, then a tail of {sub // 2}- and {sub // 4}-image ones) shared "
+                   "by the ranks; one all-reduce(sum) of the zero-filled record slab (= all-gather under dynamic ownership) after "
+                   "the last step",
                    "l2": f"per-step inputs ({B * S * S * 3 / 1e6:.0f} MB of u8 images) and activations are >> the 126 MB L2; no flush needed",
                    "weights": "random init (seeded), bf16", "fuse_ln": bool(args.fuse_ln),
                    "residual_stream": "two bf16 tensors (hi + lo)" if args.precise_residual else "bf16",

@@ -5,7 +5,7 @@ set -u
 O=gpurun_out
 T=${1:-r02}
 mkdir -p $O
-BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --graphs 0"   # eager launches: ncu sees the same kernels, one by one
 timeout 600 python bench.py --steps 5 --warmup 3 > $O/${T}_bench_so400m_b512.json 2> $O/${T}_bench_n1.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/${T}_bench_reference_arm.json 2> $O/${T}_bench_ref.err; echo "ref rc=$?"
 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --precise-residual 1 > $O/${T}_bench_so400m_b512_precise.json 2> $O/${T}_bench_precise.err; echo "precise rc=$?"
