@@ -608,7 +608,7 @@ int attention_dq_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, in
   const float scale_log2 = scale * 1.4426950408889634f;
   const int n_items = (int)items64;
   const int grid = n_items < kNumSMs ? n_items : kNumSMs;
-  static SmemOptIn smem_once[2][8];
+  static SmemOptIn smem_once[2][3];
 #define DFD_DQ_LAUNCH(HD_, POLY_, HO_, SLOT_)                                                                              \
   do {                                                                                                                      \
     if (int rc2 = ensure_dynamic_smem(smem_once[HD_ == 64 ? 0 : 1][SLOT_], attention_dq_kernel<HD_, POLY_, HO_>,            \
@@ -617,17 +617,14 @@ int attention_dq_bf16(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, in
     attention_dq_kernel<HD_, POLY_, HO_><<<grid, kThreads, DqSmem<HD_>::kTotal, st>>>(tmMain, tmTail, tmOut, N, H, n_items, \
                                                                                      scale_log2);                          \
   } while (0)
-  // variant = 100 * poly + handoff (development A/B hook; the product uses kDqVariantDefault)
+  // variant = 100 * poly + handoff.  The product is kDqVariantDefault (every 4th pair of exponentials on the FMA pipe, turn
+  // hand-over after 16 pairs); 16 (all exponentials on the MUFU unit) and 316 stay as A/B hooks.  Hand-over after 8 / 24 pairs,
+  // no turns, and every 2nd pair were measured and dropped (profiles/r02_attention.md §C).
 #define DFD_DQ_VARIANTS(HD_)                                         \
   switch (variant) {                                                 \
     case 16: DFD_DQ_LAUNCH(HD_, 0, 16, 0); break;                    \
     case 316: DFD_DQ_LAUNCH(HD_, 3, 16, 1); break;                   \
     case 416: DFD_DQ_LAUNCH(HD_, 4, 16, 2); break;                   \
-    case 308: DFD_DQ_LAUNCH(HD_, 3, 8, 3); break;                    \
-    case 324: DFD_DQ_LAUNCH(HD_, 3, 24, 4); break;                   \
-    case 300: DFD_DQ_LAUNCH(HD_, 3, 0, 5); break;                    \
-    case 216: DFD_DQ_LAUNCH(HD_, 2, 16, 6); break;                   \
-    case 400: DFD_DQ_LAUNCH(HD_, 4, 0, 7); break;                    \
     default:                                                         \
       set_last_error("attention: unknown dq variant %d", variant);   \
       return DFD_ERR_BAD_ARG;                                        \
@@ -669,7 +666,6 @@ extern "C" DFD_API int dfd_attention_bf16_impl(const void* qkv, int64_t ldqkv, v
   if (impl == 5) return dfd::attention_dq_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, st, 16);
   if (impl == 6) return dfd::attention_dq_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, st, 316);
   if (impl == 7) return dfd::attention_dq_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, st, 416);
-  if (impl >= 100) return dfd::attention_dq_bf16(qkv, ldqkv, out, ldo, B, N, H, hd, scale, st, impl - 100);
   dfd::set_last_error("attention: impl must be 2 (single-tile persistent) or 5 / 6 / 7 (dual-query-tile: exponentials all on the MUFU unit / every 3rd / every 4th pair on the FMA pipe)");
   return DFD_ERR_BAD_ARG;
 }
