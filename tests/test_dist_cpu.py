@@ -116,3 +116,27 @@ def test_shard_bounds_cover_everything():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_bench_unit_plan_covers_every_image_once_with_a_short_tail():
+    """bench.py:unit_plan — the work queue's units: contiguous, each aligned to its own size (so that it is a slice of a rank's
+    resident batch), whole batches on one GPU, and on several GPUs a tail of half- and quarter-size units (2 x world each)."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                          "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for world, steps, B in ((1, 5, 512), (2, 5, 512), (4, 3, 512), (8, 20, 512), (8, 5, 256), (3, 2, 512)):
+        sub = B if world == 1 else B // 2
+        plan = bench.unit_plan(steps * world * B, world, B, sub)
+        assert plan[0][0] == 0 and plan[-1][0] + plan[-1][1] == steps * world * B
+        assert all(a[0] + a[1] == b[0] for a, b in zip(plan, plan[1:]))
+        assert all(off % n == 0 and off % B + n <= B for off, n in plan)
+        sizes = [n for _, n in plan]
+        if world == 1:
+            assert sizes == [B] * steps
+        else:
+            assert sizes.count(sub // 2) == 2 * world and sizes.count(sub // 4) >= 2 * world   # (a remainder goes out as quarter units)
+            assert sizes == sorted(sizes, reverse=True)      # big units first, the short ones at the end
