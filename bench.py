@@ -608,15 +608,57 @@ def run_head_train(args):
                           "gpu_launches": int(_lib.load().dfd_launch_count())}), flush=True)
 
 
+def run_library(args):
+    """The 'library' comparison point of SURVEY.md §8(d): the SAME HF model the reference calls (transformers.SiglipVisionModel,
+    Siglip2sidafrozen.py:753,787) run eagerly by PyTorch on this B200 — bf16 autocast, SDPA attention, inference_mode, normalised
+    fp32 NCHW input resident on the device.  None of this repository's kernels is on that path (gpu_launches = 0): the line says
+    what stock PyTorch + cuBLAS + its attention library deliver on the hardware the product is measured on."""
+    import torch
+    from transformers import SiglipVisionConfig, SiglipVisionModel
+
+    from dfd.engine import ARCHS
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    peaks = load_peaks()
+    table = {}
+    for wl, B in (("so400m-384", args.batch or 64), ("base-224", args.batch or 256)):
+        a = ARCHS[WORKLOADS[wl][0]]
+        cfg = SiglipVisionConfig(hidden_size=a.hidden_size, intermediate_size=a.intermediate_size, num_hidden_layers=a.num_hidden_layers,
+                                 num_attention_heads=a.num_attention_heads, image_size=a.image_size, patch_size=a.patch_size)
+        cfg._attn_implementation = "sdpa"
+        torch.manual_seed(0)
+        m = SiglipVisionModel(cfg).to(dev).eval()
+        x = torch.randint(0, 256, (B, a.image_size, a.image_size, 3), dtype=torch.uint8, device=dev)
+        x = x.permute(0, 3, 1, 2).float().div_(255.0).mul_(2.0).sub_(1.0).contiguous()
+
+        def step():
+            with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+                return m(pixel_values=x).pooler_output
+
+        ms = _event_ms(step, iters=max(args.steps, 5), warm=max(args.warmup, 3))
+        ips = B / ms * 1e3
+        table[wl] = {"batch": B, "ms_per_step": ms, "images_per_s": ips,
+                     "tensor_pipe_frac_of_sustained": a.flops_per_image() * ips / 1e12 / float(peaks["bf16_tflops_sustained"])}
+        del m, x
+        torch.cuda.empty_cache()
+    print(json.dumps({"metric": "images/sec, backbone only, transformers.SiglipVisionModel eager on one B200 (library comparison point)",
+                      "impl": "library", "unit": "images/s", "value": table["so400m-384"]["images_per_s"], "higher_is_better": True,
+                      "n_gpus": 1, "steps": max(args.steps, 5), "warmup": max(args.warmup, 3), "dtype": "bf16 autocast", "data": "synthetic",
+                      "config": {"workload": "library: HF SiglipVisionModel, bf16 autocast + SDPA, inference_mode, fp32 NCHW input on the device; "
+                                             "so400m-384 and base-224"},
+                      "gpu_launches": 0, "table": table}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["latency", "cifake", "head-train"], default="so400m-384",
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["latency", "cifake", "head-train", "library"], default="so400m-384",
                     help="so400m-384 (the driver's headline, BASELINE configs[2]) | base-224 (configs[1]) | latency | cifake "
-                         "(configs[3]) | head-train (configs[4])")
+                         "(configs[3]) | head-train (configs[4]) | library (stock PyTorch eager run of the HF model on the same GPU)")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--max-batch", type=int, default=512, help="engine workspace batch (larger batches are chunked)")
     ap.add_argument("--sub-batch", type=int, default=0,
@@ -640,6 +682,8 @@ def main():
         run_cifake(args)
     elif args.workload == "head-train":
         run_head_train(args)
+    elif args.workload == "library":
+        run_library(args)
     else:
         run_ours(args)
     try:

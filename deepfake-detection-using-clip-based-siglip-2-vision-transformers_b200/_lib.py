@@ -125,6 +125,8 @@ SIGNATURES = {
     "dfd_gray256": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P]),
     "dfd_gray256_strided": (_I, [_P, _L, _L, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P]),
     "dfd_resize_u8_strided": (_I, [_P, _L, _L, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P]),
+    "dfd_clahe_scratch_bytes": (_L, [_I, _I]),
+    "dfd_clahe_u8": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "dfd_score_epilogue": (_I, [C.POINTER(ScoreWeights), _P, _P, _P, _I, C.POINTER(Scores), _P]),
     "dfd_fusion_fwd_bwd": (_I, [_P, _P, _P, _P, _I, _F, _P, _P, _P, _P]),
     "dfd_dwconv3x3_bf16": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _P]),

@@ -76,22 +76,24 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   return i;
 }
 
-// grid (64 tiles, B), 256 threads.  tile (tw x th) of the image extended by BORDER_REFLECT_101 to a multiple of 8.
+// grid (64 tiles, B·C planes), 256 threads.  tile (tw x th) of the image extended by BORDER_REFLECT_101 to a multiple of 8.
+// C = interleaved channels of the input (1: the luma plane of gray256; 3: one plane per colour channel of an RGB image, the
+// per-channel CLAHE of train_fusion_head_only.py:60-65); plane p = image p / C, channel p % C.
 __global__ void __launch_bounds__(256)
-clahe_lut_kernel(const uint8_t* __restrict__ L, uint8_t* __restrict__ luts, int H, int W, int tw, int th, int clip,
+clahe_lut_kernel(const uint8_t* __restrict__ L, uint8_t* __restrict__ luts, int H, int W, int C, int tw, int th, int clip,
                  float lut_scale) {
   __shared__ int hist[256];
   __shared__ int scan[256];
   __shared__ int s_clipped;
   const int tile = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
   const int ty = tile / kTiles, tx = tile % kTiles;
-  const uint8_t* img = L + (int64_t)b * H * W;
+  const uint8_t* img = L + (int64_t)(b / C) * H * W * C + (b % C);
   hist[t] = 0;
   if (t == 0) s_clipped = 0;
   __syncthreads();
   for (int i = t; i < tw * th; i += 256) {
     const int y = reflect101(ty * th + i / tw, H), x = reflect101(tx * tw + i % tw, W);
-    atomicAdd(&hist[img[(int64_t)y * W + x]], 1);
+    atomicAdd(&hist[img[((int64_t)y * W + x) * C]], 1);
   }
   __syncthreads();
   int h = hist[t];
@@ -127,8 +129,8 @@ clahe_lut_kernel(const uint8_t* __restrict__ L, uint8_t* __restrict__ luts, int 
 
 __global__ void __launch_bounds__(256)
 clahe_apply_kernel(const uint8_t* __restrict__ L, const uint8_t* __restrict__ luts, uint8_t* __restrict__ out, int H,
-                   int W, float inv_tw, float inv_th) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+                   int W, int C, float inv_tw, float inv_th) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;   // b = plane (image, channel)
   if (x >= W) return;
   const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
   const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
@@ -138,7 +140,7 @@ clahe_apply_kernel(const uint8_t* __restrict__ L, const uint8_t* __restrict__ lu
   const int tx2 = min(tx1 + 1, kTiles - 1), ty2 = min(ty1 + 1, kTiles - 1);
   tx1 = max(tx1, 0);
   ty1 = max(ty1, 0);
-  const int64_t pix = ((int64_t)b * H + y) * W + x;
+  const int64_t pix = (((int64_t)(b / C) * H + y) * W + x) * C + (b % C);
   const int v = L[pix];
   const uint8_t* lb = luts + (int64_t)b * kTiles * kTiles * 256 + v;
   const float l11 = (float)__ldg(lb + (ty1 * kTiles + tx1) * 256), l12 = (float)__ldg(lb + (ty1 * kTiles + tx2) * 256);
@@ -360,9 +362,9 @@ extern "C" DFD_API int dfd_gray256_strided(const void* rgb_u8, int64_t row_strid
     const float lut_scale = 255.0f / (float)area;
     int clip = (int)(2.0 * area / 256);
     if (clip < 1) clip = 1;
-    clahe_lut_kernel<<<dim3(kTiles * kTiles, B), 256, 0, st>>>(L, luts, H, W, tw, th, clip, lut_scale);
+    clahe_lut_kernel<<<dim3(kTiles * kTiles, B), 256, 0, st>>>(L, luts, H, W, 1, tw, th, clip, lut_scale);
     DFD_LAUNCH_CHECK();
-    clahe_apply_kernel<<<dim3((W + 255) / 256, H, B), 256, 0, st>>>(L, luts, C, H, W, 1.0f / (float)tw,
+    clahe_apply_kernel<<<dim3((W + 255) / 256, H, B), 256, 0, st>>>(L, luts, C, H, W, 1, 1.0f / (float)tw,
                                                                   1.0f / (float)th);
     DFD_LAUNCH_CHECK();
     launches += 2;
@@ -375,6 +377,46 @@ extern "C" DFD_API int dfd_gray256_strided(const void* rgb_u8, int64_t row_strid
   resample_cols_kernel<<<dim3(kOut, B), kOut, 0, st>>>(rows, gray256, H, xmin_h, count_h, kk_h, ksize_h);
   DFD_LAUNCH_CHECK();
   g_launches.fetch_add(launches + 2, std::memory_order_relaxed);
+  return DFD_OK;
+}
+
+// OpenCV CLAHE(clipLimit 2.0, tileGridSize 8x8) of every channel of dense u8 images [B, H, W, C] (C = 1 or 3), each channel on
+// its own: the `apply_clahe` that precedes Resize in the reference's training preprocess (train_fusion_head_only.py:60-65:
+// `for chan in range(3): arr[:, :, chan] = clahe.apply(arr[:, :, chan])`).  Same kernels as the gray256 stage, one plane per
+// (image, channel); bit-exact with the library.  scratch: dfd_clahe_scratch_bytes(B, C) bytes (the tile LUTs).  src != dst.
+extern "C" DFD_API int64_t dfd_clahe_scratch_bytes(int B, int C) {
+  if (B <= 0 || C <= 0) return 0;
+  return (int64_t)B * C * dfd::kTiles * dfd::kTiles * 256;
+}
+
+extern "C" DFD_API int dfd_clahe_u8(const void* src, int B, int H, int W, int C, void* scratch, void* dst, void* stream) {
+  using namespace dfd;
+  DFD_REQUIRE(src && dst && scratch, DFD_ERR_BAD_ARG, "clahe: null pointer");
+  DFD_REQUIRE(src != dst, DFD_ERR_BAD_ARG, "clahe: in-place operation is not supported (every pixel reads four tile LUTs built from the input)");
+  DFD_REQUIRE(B > 0 && H > 0 && W > 0 && (C == 1 || C == 3), DFD_ERR_SHAPE, "clahe: bad shape (B, H, W > 0; C = 1 or 3)");
+  DFD_REQUIRE((int64_t)B * C <= 65535 && H <= 65535, DFD_ERR_SHAPE, "clahe: B*C and H must be <= 65535");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int tw, th;
+  if (W % kTiles == 0 && H % kTiles == 0) {
+    tw = W / kTiles;
+    th = H / kTiles;
+  } else {
+    tw = (W + (kTiles - W % kTiles)) / kTiles;
+    th = (H + (kTiles - H % kTiles)) / kTiles;
+  }
+  const int area = tw * th;
+  const float lut_scale = 255.0f / (float)area;
+  int clip = (int)(2.0 * area / 256);
+  if (clip < 1) clip = 1;
+  uint8_t* luts = reinterpret_cast<uint8_t*>(scratch);
+  clahe_lut_kernel<<<dim3(kTiles * kTiles, B * C), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(src), luts, H, W, C, tw, th,
+                                                                clip, lut_scale);
+  DFD_LAUNCH_CHECK();
+  clahe_apply_kernel<<<dim3((W + 255) / 256, H, B * C), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(src), luts,
+                                                                     reinterpret_cast<uint8_t*>(dst), H, W, C,
+                                                                     1.0f / (float)tw, 1.0f / (float)th);
+  DFD_LAUNCH_CHECK();
+  g_launches.fetch_add(2, std::memory_order_relaxed);
   return DFD_OK;
 }
 

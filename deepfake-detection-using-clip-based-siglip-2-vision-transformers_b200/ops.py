@@ -317,6 +317,20 @@ def resize_u8(images: torch.Tensor, out_h: int, out_w: int, filter: str = "bilin
     return out
 
 
+def clahe_u8(images: torch.Tensor) -> torch.Tensor:
+    """Per-channel cv2 CLAHE(clipLimit 2.0, 8x8 tiles) of dense u8 images [B,H,W,C] (C = 1 or 3, device) -> u8 of the same shape,
+    bit-exact with `for c in range(3): arr[:, :, c] = clahe.apply(arr[:, :, c])` (train_fusion_head_only.py:60-65) (dfd_clahe_u8)."""
+    _need_cuda(images)
+    assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[3] in (1, 3)
+    images = images.contiguous()
+    B, H, W, C = images.shape
+    lib = _lib.load()
+    scratch = torch.empty((lib.dfd_clahe_scratch_bytes(B, C),), dtype=torch.uint8, device=images.device)
+    out = torch.empty_like(images)
+    check(lib.dfd_clahe_u8(images.data_ptr(), B, H, W, C, scratch.data_ptr(), out.data_ptr(), current_stream()))
+    return out
+
+
 def gray256_from_rgb(images: torch.Tensor, clahe: bool, scratch: Optional[torch.Tensor] = None,
                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """u8 RGB images [B,H,W,3] (NHWC, device; dense or a rectangle view of a larger image) -> gray256 f32 [B,256,256] in [0,1]

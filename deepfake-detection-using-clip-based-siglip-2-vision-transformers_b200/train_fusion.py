@@ -4,7 +4,9 @@ logits of a frozen SigLIP classifier + FreqMLP, and write `fusion_head.safetenso
 
 Differences from the reference, on purpose:
   * the two extraction loops (train_fusion_head_only.py:329-347: one image, one sync at a time) run batched on the
-    GPU engine; the host preprocessing (CLAHE, PIL resize, gray256) is the reference's own;
+    GPU engine, and so does their preprocessing: the host decodes the files, then per-channel CLAHE, the PIL Resize and the
+    gray256 stage are the bit-exact device kernels (dfd_clahe_u8 / dfd_resize_u8 / dfd_gray256; `on_device=False` keeps the
+    reference's own cv2 / PIL / torchvision chain);
   * the head's forward+backward is one CUDA kernel (dfd_fusion_fwd_bwd) that returns the batch's loss/gradient
     partial sums; with torch.distributed initialised every rank takes a contiguous shard of each mini-batch and
     one all-reduce of the flat 196-float bucket (195 grads + loss) precedes the identical clip + AdamW step;
@@ -124,12 +126,46 @@ def make_preprocess(img_size: int = IMG_SIZE):
                                transforms.ToTensor(), transforms.Normalize([0.5] * 3, [0.5] * 3)])
 
 
+def _decode_rgb_u8(path: str, exif_transpose: bool = False) -> np.ndarray:
+    """Decoded pixels of a file, [H,W,3] u8.  exif_transpose: the gray256 stage honours the EXIF orientation
+    (`ImageOps.exif_transpose`, train_fusion_head_only.py:143), the SigLIP preprocess does not (:60-74)."""
+    from PIL import Image, ImageOps
+
+    with Image.open(path) as pil:
+        rgb = pil.convert("RGB")
+        if exif_transpose:
+            rgb = ImageOps.exif_transpose(rgb)
+        return np.array(rgb, dtype=np.uint8)   # a writable copy: torch.from_numpy refuses read-only buffers
+
+
+def preprocess_on_device(rgb_u8: np.ndarray, img_size: int, device) -> torch.Tensor:
+    """train_fusion_head_only.py:60-74 on the GPU, for one decoded image [H,W,3] u8: ONE upload, per-channel CLAHE
+    (dfd_clahe_u8, bit-exact with cv2) -> PIL-exact bilinear Resize((S,S)) (dfd_resize_u8) -> u8 [S,S,3] on the device.
+    ToTensor + Normalize(.5,.5) happen inside the patch kernel when the batch enters the engine, so the backbone sees exactly
+    the bf16 pixels the host chain `make_preprocess` would have produced."""
+    img = torch.from_numpy(np.ascontiguousarray(rgb_u8)).to(device, non_blocking=True)[None]
+    return ops.resize_u8(ops.clahe_u8(img), img_size, img_size, "bilinear")[0]
+
+
 @torch.no_grad()
-def extract_siglip_logits(siglip, paths: Sequence[str], batch_size: int = 32, preprocess=None) -> torch.Tensor:
+def extract_siglip_logits(siglip, paths: Sequence[str], batch_size: int = 32, preprocess=None,
+                          on_device: Optional[bool] = None) -> torch.Tensor:
+    """z_sig of every image (train_fusion_head_only.py:339-347, batched).  on_device (default: whenever no custom `preprocess`
+    is passed): the reference's preprocess runs on the GPU (`preprocess_on_device`); the host only decodes the files.
+    on_device=False keeps the reference's own host chain (cv2 + PIL + torchvision)."""
     from PIL import Image
 
-    pre = preprocess or make_preprocess(siglip.resolution)
+    if on_device is None:
+        on_device = preprocess is None
     out = []
+    if on_device:
+        S, dev = siglip.resolution, siglip.device
+        with torch.cuda.device(dev):
+            for i in range(0, len(paths), batch_size):
+                xs = torch.stack([preprocess_on_device(_decode_rgb_u8(p), S, dev) for p in paths[i:i + batch_size]])
+                out.append(siglip(xs).float().cpu())
+        return torch.cat(out) if out else torch.zeros(0)
+    pre = preprocess or make_preprocess(siglip.resolution)
     for i in range(0, len(paths), batch_size):
         xs = []
         for p in paths[i:i + batch_size]:
@@ -140,17 +176,27 @@ def extract_siglip_logits(siglip, paths: Sequence[str], batch_size: int = 32, pr
 
 
 @torch.no_grad()
-def extract_freq_logits(freq_model: FreqMLP, paths: Sequence[str], device, batch_size: int = 64) -> torch.Tensor:
+def extract_freq_logits(freq_model: FreqMLP, paths: Sequence[str], device, batch_size: int = 64,
+                        on_device: bool = True) -> torch.Tensor:
+    """z_freq of every image (train_fusion_head_only.py:329-337, batched).  on_device: gray256 (Pillow luma, cv2 CLAHE, Pillow
+    bicubic resize — dfd_gray256, bit-exact) is produced on the GPU from one upload per decoded image; on_device=False runs the
+    libraries themselves on the host (`scoring.pil_to_gray256`)."""
     from PIL import Image
 
     fx = FreqFeatureExtractor(device, zscore=False, clahe=True)
     out = []
     for i in range(0, len(paths), batch_size):
-        gs = []
-        for p in paths[i:i + batch_size]:
-            with Image.open(p) as pil:
-                gs.append(pil_to_gray256(pil.convert("RGB"), clahe=True))
-        feats = fx.from_gray(torch.from_numpy(np.stack(gs)).to(fx.device))
+        if on_device:
+            with torch.cuda.device(fx.device):
+                gray = torch.cat([ops.gray256_from_rgb(torch.from_numpy(_decode_rgb_u8(p, True)).to(fx.device, non_blocking=True)[None],
+                                                       True) for p in paths[i:i + batch_size]])
+        else:
+            gs = []
+            for p in paths[i:i + batch_size]:
+                with Image.open(p) as pil:
+                    gs.append(pil_to_gray256(pil.convert("RGB"), clahe=True))
+            gray = torch.from_numpy(np.stack(gs)).to(fx.device)
+        feats = fx.from_gray(gray)
         out.append(freq_model(feats).float().cpu())
     return torch.cat(out) if out else torch.zeros(0)
 

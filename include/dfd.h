@@ -238,6 +238,13 @@ DFD_API int dfd_gray256(const void* rgb_u8, int B, int H, int W, int clahe, cons
                         const int32_t* count_h, const int32_t* kk_h, int ksize_h, void* scratch,
                         float* gray256 /*[B,256,256]*/, void* stream);
 
+/* Per-channel CLAHE of dense u8 images [B,H,W,C] (C = 1 or 3): cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8,8)).apply on
+ * every channel separately — `apply_clahe`, the first stage of the reference's training preprocess
+ * (train_fusion_head_only.py:60-65), ahead of Resize (dfd_resize_u8) and ToTensor + Normalize (the patch kernel).  Bit-exact with
+ * OpenCV 4.13 (oracle/gray_ref.py:clahe_u8).  scratch: dfd_clahe_scratch_bytes(B, C) bytes; src and dst must differ. */
+DFD_API int64_t dfd_clahe_scratch_bytes(int B, int C);
+DFD_API int dfd_clahe_u8(const void* src, int B, int H, int W, int C, void* scratch, void* dst, void* stream);
+
 /* FreqMLP (generation 2) forward + backward of mean BCE-with-logits: one training step's
  * `logits = model(xb); loss = criterion(logits, yb); loss.backward()` ("FreqMLP trainer.py":366-369; model :218-301).
  * params6494 = the state dict without its two buffers, flattened in order: contrast.alpha[24], contrast.beta[24],

@@ -300,6 +300,50 @@ def test_train_fusion_head_end_to_end(tmp_path):
     assert st.gen == 2
 
 
+def test_extract_logits_device_preprocess_equals_host_chain(tmp_path):
+    """Entry point #2's two extraction loops (train_fusion_head_only.py:329-347) with the preprocess on the GPU — per-channel CLAHE,
+    PIL Resize, gray256 from one upload per decoded file — against the reference's own host chain (cv2 + PIL + torchvision,
+    `on_device=False`): the device kernels are bit-exact, so the logits agree to the last bit for the frequency branch and to
+    fp32 round-off of ToTensor / Normalize (folded into one multiply-add in the patch kernel) before bf16 for SigLIP."""
+    from PIL import Image
+    from safetensors.torch import load_file, save_file  # noqa: F401
+
+    from dfd import scoring, train_fusion
+    from dfd.dropin import BinaryClassifier
+    from oracle import scoring_ref as S
+    from oracle import siglip_ref as R
+
+    rng = np.random.default_rng(4)
+    paths = []
+    for i, (h, w) in enumerate([(48, 64), (100, 37), (64, 64), (131, 77), (224, 224), (17, 300)]):
+        arr = np.clip(rng.normal(120, 50, (h, w, 3)), 0, 255).astype(np.uint8)
+        arr[: h // 2, : w // 2] //= 3      # a dark quadrant: CLAHE has something to equalise
+        Image.fromarray(arr).save(tmp_path / f"{i}.png")
+        paths.append(str(tmp_path / f"{i}.png"))
+    c = R.CONFIGS["tiny-hd64"]
+    siglip = BinaryClassifier(device=DEV, head="B", arch="tiny-hd64", max_batch=8)
+    ck = {"backbone.vision_model." + k: v for k, v in R.init_state_dict(c, 0).items()}
+    ck.update(R.init_head("B", c.hidden_size, 1))
+    siglip.load_state_dict(ck, strict=False)
+    # the preprocessed pixels themselves: u8 on the device == the host chain before ToTensor
+    pre_host = train_fusion.make_preprocess(siglip.resolution)
+    for p in paths:
+        with Image.open(p) as pil:
+            host = pre_host(pil.convert("RGB"))                      # f32 [3,S,S] in [-1,1]
+        dev = train_fusion.preprocess_on_device(train_fusion._decode_rgb_u8(p), siglip.resolution, siglip.device)
+        want_u8 = torch.round((host * 0.5 + 0.5) * 255.0).permute(1, 2, 0).to(torch.uint8)
+        assert torch.equal(dev.cpu(), want_u8), p
+    z_dev = train_fusion.extract_siglip_logits(siglip, paths, batch_size=4)
+    z_host = train_fusion.extract_siglip_logits(siglip, paths, batch_size=4, on_device=False)
+    assert z_dev.shape == z_host.shape == (len(paths),)
+    assert float((z_dev - z_host).abs().max()) <= 2e-3, (z_dev, z_host)   # same bf16 pixels up to fp32 round-off of the normalise
+    fm = scoring.FreqMLP()
+    fm.load_state_dict(S.init_freq_mlp_g2(2), strict=True)
+    f_dev = train_fusion.extract_freq_logits(fm, paths, DEV, batch_size=4)
+    f_host = train_fusion.extract_freq_logits(fm, paths, DEV, batch_size=4, on_device=False)
+    assert torch.equal(f_dev, f_host)
+
+
 def _reference_fit_freq(features, labels, batch_size, epochs, lr, seed):
     """"FreqMLP trainer.py":330-396 restated with torch autograd, dropout off (the only stochastic part)."""
     import torch.nn as nn

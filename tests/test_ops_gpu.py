@@ -664,6 +664,44 @@ def test_gray256_full_size_properties():
     assert float((k - k.round()).abs().max()) < 1e-4   # every value is k/255
 
 
+@pytest.mark.parametrize("B,H,W,C", [(2, 384, 384, 3), (3, 100, 37, 3), (1, 257, 255, 3), (2, 64, 64, 1), (1, 8, 9, 3), (1, 1, 1, 3),
+                                     (2, 480, 640, 3)])
+def test_clahe_u8_per_channel_is_bit_exact(B, H, W, C):
+    """dfd_clahe_u8 = `for c in range(3): arr[:, :, c] = clahe.apply(arr[:, :, c])` (train_fusion_head_only.py:60-65): against the
+    numpy restatement of OpenCV's CLAHE (pinned to the library in tests/test_oracle_cpu.py) and, where installed, cv2 itself."""
+    from dfd import ops
+    from oracle import gray_ref as G
+
+    imgs = np.stack([G.synthetic_rgb(H, W, ("noise", "waves", "edges")[b % 3], 300 + b) for b in range(B)])
+    if C == 1:
+        imgs = np.ascontiguousarray(imgs[..., 1:2])
+    got = ops.clahe_u8(torch.from_numpy(imgs).to(DEV)).cpu().numpy()
+    assert got.shape == imgs.shape and got.dtype == np.uint8
+    for b in range(B):
+        for c in range(C):
+            want = G.clahe_u8(np.ascontiguousarray(imgs[b, :, :, c]))
+            assert np.array_equal(got[b, :, :, c], want), (b, c, int((got[b, :, :, c] != want).sum()))
+    try:
+        import cv2
+    except ImportError:
+        return
+    cl = cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8))
+    for b in range(B):
+        for c in range(C):
+            assert np.array_equal(got[b, :, :, c], cl.apply(np.ascontiguousarray(imgs[b, :, :, c])))
+
+
+def test_clahe_u8_rejects_in_place_and_bad_shapes():
+    from dfd import _lib
+
+    lib = _lib.load()
+    x = torch.zeros(1, 16, 16, 3, dtype=torch.uint8, device=DEV)
+    scr = torch.empty(lib.dfd_clahe_scratch_bytes(1, 3), dtype=torch.uint8, device=DEV)
+    assert lib.dfd_clahe_u8(x.data_ptr(), 1, 16, 16, 3, scr.data_ptr(), x.data_ptr(), None) == -1    # DFD_ERR_BAD_ARG
+    assert lib.dfd_clahe_u8(x.data_ptr(), 1, 16, 16, 2, scr.data_ptr(), scr.data_ptr(), None) == -2  # DFD_ERR_SHAPE
+    assert lib.dfd_clahe_scratch_bytes(2, 3) == 2 * 3 * 64 * 256 and lib.dfd_clahe_scratch_bytes(0, 3) == 0
+
+
 @pytest.mark.parametrize("B,H,W,OH,OW,C", [(3, 480, 640, 384, 384, 3), (4, 224, 224, 384, 384, 3), (2, 100, 37, 224, 224, 3),
                                            (1, 1080, 1920, 384, 384, 3), (2, 384, 384, 384, 384, 3), (3, 97, 211, 64, 48, 1)])
 @pytest.mark.parametrize("filt", ["bilinear", "bicubic"])
