@@ -482,13 +482,41 @@ class FastBinaryClassifier(BinaryClassifier):
         return _IncompatibleKeys(missing, unexpected)
 
 
+def decode_only(pil) -> torch.Tensor:
+    """Dataset transform for the device-side preprocess: the decoded pixels as a u8 [H,W,3] tensor, nothing else.  With
+    `ragged_collate` the DataLoader workers only decode; `Resize((S,S))` (bit-exact PIL bilinear, dfd_resize_u8) runs on the GPU
+    and ToTensor + Normalize(.5,.5) inside the patch kernel — inference_ai_human_images.py:200-204 without its host resize."""
+    return torch.from_numpy(np.array(pil.convert("RGB"), dtype=np.uint8))
+
+
+def ragged_collate(batch):
+    """collate_fn for `decode_only` samples: images of different sizes stay a list; labels / filenames as the default collate."""
+    imgs, labels, names = zip(*batch)
+    return list(imgs), torch.as_tensor(labels), list(names)
+
+
+def resize_on_device(model: "BinaryClassifier", images) -> torch.Tensor:
+    """A ragged list of u8 [H,W,3] host tensors -> u8 [B,S,S,3] on the model's device: one upload per image at its decoded size,
+    PIL-exact bilinear resize there (images that already are SxS are taken as they are, like PIL's no-op resize)."""
+    S = model.resolution
+    out = []
+    with torch.cuda.device(model.device):
+        for im in images:
+            d = im.to(model.device, non_blocking=True)[None]
+            out.append(d if tuple(d.shape[1:3]) == (S, S) else ops.resize_u8(d, S, S, "bilinear"))
+        return torch.cat(out)
+
+
 @torch.no_grad()
 def run_inference(model: BinaryClassifier, dataloader, device=None, use_amp: bool = True, desc: str = "Inference",
                   invert_logits: bool = False, prototypes: Optional[dict] = None):
     """inference_ai_human_images.py:250-318: loader of (images, labels, filenames) -> (labels, P(fake), filenames).
-    One D2H read per batch, like the reference loop."""
+    One D2H read per batch, like the reference loop.  `images` is either the reference's normalised float batch [B,3,S,S] or,
+    from a `decode_only` / `ragged_collate` loader, a list of decoded u8 images that are resized on the device."""
     all_labels, all_probs, all_files = [], [], []
     for images, labels, filenames in dataloader:
+        if isinstance(images, (list, tuple)):
+            images = resize_on_device(model, images)
         if prototypes is not None:
             probs = model.prototype_probs(images, prototypes)
         else:
@@ -571,31 +599,35 @@ def create_tta_transforms(image_size: int, num_augments: int = 5):
 
 
 def run_tta_inference(model, data_dir, metadata_csv, tta_transforms, batch_size, num_workers=0, device=None,
-                      use_amp: bool = True, invert_logits: bool = False, prototypes: Optional[dict] = None):
+                      use_amp: bool = True, invert_logits: bool = False, prototypes: Optional[dict] = None,
+                      device_resize: bool = False):
     """inference_ai_human_images.py:321-360: one pass per TTA transform, probabilities averaged.
     Returns (y_true, mean probabilities, [per-transform probabilities], filenames).
 
     The reference decodes, resizes and uploads the dataset once per transform.  For the default configuration
     (NUM_TTA_AUGMENTS = 2: "Original" + "H-Flip", :731-732) and a dfd BinaryClassifier the mirrored view is produced by
     the patch kernel from the pixels that are already resident (DFD_FLIP_H), so both views cost one decode and one
-    upload per image; the remaining transforms (CLAHE / sharpen, host PIL ops in the reference too) run as extra passes."""
+    upload per image; the remaining transforms (CLAHE / sharpen, host PIL ops in the reference too) run as extra passes.
+    device_resize: the fused "Original" + "H-Flip" pass decodes on the host only (`decode_only` + `ragged_collate`) and does the
+    `Resize((S,S))` on the GPU as well (bit-exact with PIL, see `resize_on_device`)."""
     from torch.utils.data import DataLoader
 
     names = [n for n, _ in tta_transforms]
     fused = (isinstance(model, BinaryClassifier) and len(names) >= 2 and names[0] == "Original" and names[1] == "H-Flip")
     all_probs, y_true, filenames = [], None, None
 
-    def loader(tf):
+    def loader(tf, ragged=False):
         ds = AIHumanDataset(data_dir, metadata_csv, transform=tf)
         return DataLoader(ds, batch_size=batch_size, shuffle=False, num_workers=num_workers,
-                          pin_memory=torch.cuda.is_available(), persistent_workers=False)
+                          pin_memory=torch.cuda.is_available() and not ragged, persistent_workers=False,
+                          collate_fn=ragged_collate if ragged else None)
 
     start = 0
     if fused:
         labs, p0, p1, files = [], [], [], []
         with torch.no_grad():
-            for images, labels, fn in loader(tta_transforms[0][1]):
-                images = images.to(model.device, non_blocking=True)
+            for images, labels, fn in (loader(decode_only, True) if device_resize else loader(tta_transforms[0][1])):
+                images = resize_on_device(model, images) if device_resize else images.to(model.device, non_blocking=True)
                 for flags, acc in ((0, p0), (ops.FLIP_H, p1)):
                     model.tta_flags = flags
                     try:

@@ -653,6 +653,20 @@ def test_run_tta_inference_fused_flip_equals_two_host_passes(tmp_path):
     y3, p3, per3, _ = dropin.run_tta_inference(m, tmp_path, csv, dropin.create_tta_transforms(c.image_size, 3), 4, 0, torch.device(DEV))
     assert len(per3) == 3 and np.array_equal(per3[0], per[0]) and np.array_equal(per3[1], per[1])
     assert np.allclose(p3, np.mean(per3, axis=0))
+    # Resize((S,S)) on the device too: the workers only decode (decode_only + ragged_collate), dfd_resize_u8 is bit-exact with PIL
+    # and the patch kernel's ToTensor + Normalize lands on the same bf16 pixels as the host transform
+    yd, pd_, perd, filesd = dropin.run_tta_inference(m, tmp_path, csv, tfs, batch_size=3, num_workers=0, device=torch.device(DEV),
+                                                     device_resize=True)
+    assert yd.tolist() == y.tolist() and filesd == files
+    assert np.abs(perd[0] - per[0]).max() < 1e-3 and np.abs(perd[1] - per[1]).max() < 1e-3, (perd[0], per[0])
+    ds_r = dropin.AIHumanDataset(tmp_path, csv, transform=dropin.decode_only)
+    ld = torch.utils.data.DataLoader(ds_r, batch_size=3, shuffle=False, collate_fn=dropin.ragged_collate)
+    assert np.abs(dropin.run_inference(m, ld, torch.device(DEV))[1] - per[0]).max() < 1e-3
+    S_ = c.image_size
+    for i in range(len(ds_r)):     # the resized pixels themselves, against the host transform's (before ToTensor)
+        host = torch.round((dropin.AIHumanDataset(tmp_path, csv, transform=tfs[0][1])[i][0] * 0.5 + 0.5) * 255.0)
+        dev = dropin.resize_on_device(m, [ds_r[i][0]])[0].cpu()
+        assert dev.shape == (S_, S_, 3) and torch.equal(dev, host.permute(1, 2, 0).to(torch.uint8))
 
 
 @pytest.mark.parametrize("fmt", ["u8", "f32"])
