@@ -152,6 +152,141 @@ clahe_apply_kernel(const uint8_t* __restrict__ L, const uint8_t* __restrict__ lu
   out[pix] = (uint8_t)min(max(__float2int_rn(res), 0), 255);
 }
 
+// Fast paths for single-channel images whose tiles divide the image (W % 8 == 0, H % 8 == 0 — no border extension) and whose
+// tile width is a multiple of 4 bytes: the shapes of the detection step (384², 224², any 32-aligned crop).  The generic kernels
+// above issue one byte load / shared atomic / byte gather per thread and pixel and ran at 11 % of the HBM roofline
+// (profiles/r01_mem_kernels.md); here
+//   * clahe_lut_rows_kernel: one CTA per (tile row, image), one WARP per tile with a private histogram — word loads, no
+//     block-wide barrier; clip / redistribute / prefix sum run on 8 bins per lane with shuffles;
+//   * clahe_apply_band_kernel: one CTA per (band of rows with the same tile-row pair, image).  The four LUT values a pixel
+//     blends — (ty1,tx1) (ty1,tx2) (ty2,tx1) (ty2,tx2) at its gray level — are packed into ONE 32-bit word of a shared table
+//     built per band ([9 tile-column pairs][256 levels]), so a pixel costs one shared-memory gather instead of four byte
+//     gathers; four pixels per thread through 32-bit loads / stores, row-wise factors hoisted.
+// Same arithmetic in the same order as the generic kernels: bit-exact with OpenCV (tests/test_ops_gpu.py).
+__global__ void __launch_bounds__(256)
+clahe_lut_rows_kernel(const uint8_t* __restrict__ L, uint8_t* __restrict__ luts, int H, int W, int tw, int th, int clip,
+                      float lut_scale) {
+  __shared__ int hist[kTiles][256];
+  const int ty = blockIdx.x, b = blockIdx.y;
+  const int tx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* h = hist[tx];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) h[lane + 32 * i] = 0;
+  __syncwarp();
+  const int wq = tw >> 2;                       // 32-bit words per tile row
+  const int rows_per_it = 32 / wq > 0 ? 32 / wq : 1;
+  const uint8_t* base = L + ((int64_t)b * H + (int64_t)ty * th) * W + tx * tw;
+  if (wq <= 32) {
+    const int r_off = lane / wq, w_off = lane - r_off * wq;
+    if (r_off < rows_per_it) {
+      for (int r = r_off; r < th; r += rows_per_it) {
+        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)r * W) + w_off);
+        atomicAdd(&h[v & 255u], 1);
+        atomicAdd(&h[(v >> 8) & 255u], 1);
+        atomicAdd(&h[(v >> 16) & 255u], 1);
+        atomicAdd(&h[v >> 24], 1);
+      }
+    }
+  } else {
+    for (int r = 0; r < th; ++r)
+      for (int w = lane; w < wq; w += 32) {
+        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)r * W) + w);
+        atomicAdd(&h[v & 255u], 1);
+        atomicAdd(&h[(v >> 8) & 255u], 1);
+        atomicAdd(&h[(v >> 16) & 255u], 1);
+        atomicAdd(&h[v >> 24], 1);
+      }
+  }
+  __syncwarp();
+  // lane owns bins 8·lane .. 8·lane+7 (contiguous: the prefix sum is a per-lane running sum plus an exclusive warp scan)
+  int v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = h[lane * 8 + i];
+  if (clip > 0) {
+    int clipped = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (v[i] > clip) { clipped += v[i] - clip; v[i] = clip; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) clipped += __shfl_xor_sync(0xffffffffu, clipped, o);
+    const int batch = clipped / 256;
+    const int residual = clipped - batch * 256;
+    const int step = residual != 0 ? max(256 / residual, 1) : 1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = lane * 8 + i;
+      v[i] += batch;
+      if (residual != 0 && t % step == 0 && t / step < residual) v[i] += 1;
+    }
+  }
+  int run = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { run += v[i]; v[i] = run; }
+  int incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  const int excl = incl - run;
+  uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = __float2int_rn(__fmul_rn((float)(v[i] + excl), lut_scale));
+    const uint32_t byte = (uint32_t)min(max(r, 0), 255);
+    if (i < 4) w0 |= byte << (8 * i); else w1 |= byte << (8 * (i - 4));
+  }
+  uint2* dst = reinterpret_cast<uint2*>(luts + ((int64_t)b * kTiles * kTiles + ty * kTiles + tx) * 256) + lane;
+  *dst = make_uint2(w0, w1);
+}
+
+__global__ void __launch_bounds__(256)
+clahe_apply_band_kernel(const uint8_t* __restrict__ L, const uint8_t* __restrict__ luts, uint8_t* __restrict__ out, int H,
+                        int W, int th, float inv_tw, float inv_th) {
+  __shared__ uint32_t tab[(kTiles + 1) * 256];   // [tile-column pair p = tx1 + 1][gray level] = l11 | l12 << 8 | l21 << 16 | l22 << 24
+  const int band = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+  const int ty1u = band - 1;                     // unclamped upper tile row of this band
+  const int ty1 = max(ty1u, 0), ty2 = min(ty1u + 1, kTiles - 1);
+  const uint8_t* lb = luts + (int64_t)b * kTiles * kTiles * 256;
+  for (int p = 0; p <= kTiles; ++p) {
+    const int tx1 = max(p - 1, 0), tx2 = min(p, kTiles - 1);
+    tab[p * 256 + t] = (uint32_t)__ldg(lb + (ty1 * kTiles + tx1) * 256 + t) | ((uint32_t)__ldg(lb + (ty1 * kTiles + tx2) * 256 + t) << 8) |
+                       ((uint32_t)__ldg(lb + (ty2 * kTiles + tx1) * 256 + t) << 16) |
+                       ((uint32_t)__ldg(lb + (ty2 * kTiles + tx2) * 256 + t) << 24);
+  }
+  __syncthreads();
+  // candidate rows of the band (one spare row on either side; every row re-checks its own tile row with the generic kernel's
+  // float expression, so the split into bands cannot disagree with it)
+  const int y_lo = max(ty1u * th + th / 2 - 1, 0), y_hi = min((ty1u + 1) * th + th / 2 + 1, H - 1);
+  const int wq = W >> 2;
+  const int items = (y_hi - y_lo + 1) * wq;
+  for (int idx = t; idx < items; idx += 256) {
+    const int yr = idx / wq, q = idx - yr * wq;
+    const int y = y_lo + yr;
+    const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+    const int tyi = (int)floorf(tyf);
+    if (tyi != ty1u) continue;
+    const float ya = __fsub_rn(tyf, (float)tyi), ya1 = __fsub_rn(1.0f, ya);
+    const int64_t off = ((int64_t)b * H + y) * W + 4 * q;
+    const uint32_t px = __ldg(reinterpret_cast<const uint32_t*>(L + off));
+    uint32_t res4 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int x = 4 * q + i;
+      const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
+      const int txi = (int)floorf(txf);
+      const float xa = __fsub_rn(txf, (float)txi), xa1 = __fsub_rn(1.0f, xa);
+      const uint32_t e = tab[(txi + 1) * 256 + ((px >> (8 * i)) & 255u)];
+      const float l11 = (float)(e & 255u), l12 = (float)((e >> 8) & 255u), l21 = (float)((e >> 16) & 255u), l22 = (float)(e >> 24);
+      const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+      const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+      const float r = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+      res4 |= (uint32_t)min(max(__float2int_rn(r), 0), 255) << (8 * i);
+    }
+    *reinterpret_cast<uint32_t*>(out + off) = res4;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Pillow 8bpc resample passes.  Coefficient tables (host: dfd_resample_coeffs_host): xmin[o], count[o], kk[o][ksize].
 // ---------------------------------------------------------------------------------------------------------
@@ -182,6 +317,72 @@ resample_cols_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, in
   int acc = 1 << (kPrecisionBits - 1);
   for (int i = 0; i < n; ++i) acc += (int)img[(int64_t)(y0 + i) * kOut + x] * __ldg(k + i);
   out[((int64_t)b * kOut + yy) * kOut + x] = __fdiv_rn((float)clip8(acc), 255.0f);
+}
+
+// Fast forms of the two passes for tables with at most kTapMax taps (384 -> 256: 7, 224 -> 256: 5).  Rows pass: a thread owns
+// one output column, keeps that column's window and coefficients in registers and walks kRowsPerCta image rows staged in shared
+// memory by word loads (the generic kernel re-reads the table for every output pixel and runs one tiny CTA per row).  Columns
+// pass: a thread produces 4 adjacent pixels of 4 output rows from 32-bit loads and writes float4s.
+constexpr int kTapMax = 8;
+constexpr int kRowsPerCta = 16;
+__global__ void __launch_bounds__(kOut)
+resample_rows_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int H, int W,
+                          const int* __restrict__ xmin, const int* __restrict__ count, const int* __restrict__ kk, int ksize) {
+  extern __shared__ uint8_t rows_s[];            // [kRowsPerCta][W]  (W % 4 == 0)
+  const int xx = threadIdx.x, y0 = blockIdx.x * kRowsPerCta, b = blockIdx.y;
+  const int nrows = min(kRowsPerCta, H - y0);
+  const int wq = W >> 2;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(in + ((int64_t)b * H + y0) * W);
+  uint32_t* dst_s = reinterpret_cast<uint32_t*>(rows_s);
+  for (int i = xx; i < nrows * wq; i += kOut) dst_s[i] = __ldg(src + i);
+  const int x0 = xmin[xx], n = count[xx];
+  int k[kTapMax];
+#pragma unroll
+  for (int i = 0; i < kTapMax; ++i) k[i] = (i < n) ? __ldg(kk + xx * ksize + i) : 0;
+  __syncthreads();
+  // taps past the window multiply a clamped (in-row) byte by a zero coefficient
+  int xi[kTapMax];
+#pragma unroll
+  for (int i = 0; i < kTapMax; ++i) xi[i] = min(x0 + i, W - 1);
+  uint8_t* o = out + ((int64_t)b * H + y0) * kOut + xx;
+  for (int r = 0; r < nrows; ++r) {
+    const uint8_t* row = rows_s + r * W;
+    int acc = 1 << (kPrecisionBits - 1);
+#pragma unroll
+    for (int i = 0; i < kTapMax; ++i) acc += (int)row[xi[i]] * k[i];
+    o[(int64_t)r * kOut] = (uint8_t)clip8(acc);
+  }
+}
+
+// grid (256 / 16, B), 256 threads: thread = (x quad 0..63, row group 0..3); output rows 16·blockIdx.x + 4·group + j
+__global__ void __launch_bounds__(256)
+resample_cols_fast_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int H, const int* __restrict__ ymin,
+                          const int* __restrict__ count, const int* __restrict__ kk, int ksize) {
+  const int xq = threadIdx.x & 63, grp = threadIdx.x >> 6, b = blockIdx.y;
+  const uint32_t* img = reinterpret_cast<const uint32_t*>(in + (int64_t)b * H * kOut) + xq;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int yy = blockIdx.x * 16 + grp * 4 + j;
+    const int y0 = __ldg(ymin + yy), n = __ldg(count + yy);
+    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+    for (int i = 0; i < kTapMax; ++i) {
+      if (i < n) {
+        const int c = __ldg(kk + yy * ksize + i);
+        const uint32_t v = __ldg(img + (int64_t)(y0 + i) * (kOut / 4));
+        a0 += (int)(v & 255u) * c;
+        a1 += (int)((v >> 8) & 255u) * c;
+        a2 += (int)((v >> 16) & 255u) * c;
+        a3 += (int)(v >> 24) * c;
+      }
+    }
+    float4 o;
+    o.x = __fdiv_rn((float)clip8(a0), 255.0f);
+    o.y = __fdiv_rn((float)clip8(a1), 255.0f);
+    o.z = __fdiv_rn((float)clip8(a2), 255.0f);
+    o.w = __fdiv_rn((float)clip8(a3), 255.0f);
+    reinterpret_cast<float4*>(out + ((int64_t)b * kOut + yy) * kOut)[xq] = o;
+  }
 }
 
 // Generic Pillow 8bpc passes for interleaved images (C = 1 or 3 channels): used by dfd_resize_u8
@@ -362,19 +563,36 @@ extern "C" DFD_API int dfd_gray256_strided(const void* rgb_u8, int64_t row_strid
     const float lut_scale = 255.0f / (float)area;
     int clip = (int)(2.0 * area / 256);
     if (clip < 1) clip = 1;
-    clahe_lut_kernel<<<dim3(kTiles * kTiles, B), 256, 0, st>>>(L, luts, H, W, 1, tw, th, clip, lut_scale);
-    DFD_LAUNCH_CHECK();
-    clahe_apply_kernel<<<dim3((W + 255) / 256, H, B), 256, 0, st>>>(L, luts, C, H, W, 1, 1.0f / (float)tw,
-                                                                  1.0f / (float)th);
-    DFD_LAUNCH_CHECK();
+    // tiles that divide the image and are whole words wide (384², 224², ...): the warp-per-tile / band kernels; images are packed
+    // back to back, so every row start is word aligned when W % 4 == 0
+    const bool fast = (W % kTiles == 0) && (H % kTiles == 0) && (tw % 4 == 0) && ((uintptr_t)scratch % 8 == 0);
+    if (fast) {
+      clahe_lut_rows_kernel<<<dim3(kTiles, B), 256, 0, st>>>(L, luts, H, W, tw, th, clip, lut_scale);
+      DFD_LAUNCH_CHECK();
+      clahe_apply_band_kernel<<<dim3(kTiles + 1, B), 256, 0, st>>>(L, luts, C, H, W, th, 1.0f / (float)tw, 1.0f / (float)th);
+      DFD_LAUNCH_CHECK();
+    } else {
+      clahe_lut_kernel<<<dim3(kTiles * kTiles, B), 256, 0, st>>>(L, luts, H, W, 1, tw, th, clip, lut_scale);
+      DFD_LAUNCH_CHECK();
+      clahe_apply_kernel<<<dim3((W + 255) / 256, H, B), 256, 0, st>>>(L, luts, C, H, W, 1, 1.0f / (float)tw,
+                                                                    1.0f / (float)th);
+      DFD_LAUNCH_CHECK();
+    }
     launches += 2;
     src = C;
   }
   // Pillow skips a pass whose size does not change; here the identity tables (count 1, weight 2^22) reproduce the
   // input exactly, so both passes always run
-  resample_rows_kernel<<<dim3(H, B), kOut, 0, st>>>(src, rows, H, W, xmin_w, count_w, kk_w, ksize_w);
+  if (ksize_w <= kTapMax && W % 4 == 0 && (int64_t)kRowsPerCta * W <= 48 * 1024 && (uintptr_t)scratch % 4 == 0)
+    resample_rows_fast_kernel<<<dim3((H + kRowsPerCta - 1) / kRowsPerCta, B), kOut, kRowsPerCta * W, st>>>(src, rows, H, W, xmin_w,
+                                                                                                            count_w, kk_w, ksize_w);
+  else
+    resample_rows_kernel<<<dim3(H, B), kOut, 0, st>>>(src, rows, H, W, xmin_w, count_w, kk_w, ksize_w);
   DFD_LAUNCH_CHECK();
-  resample_cols_kernel<<<dim3(kOut, B), kOut, 0, st>>>(rows, gray256, H, xmin_h, count_h, kk_h, ksize_h);
+  if (ksize_h <= kTapMax)
+    resample_cols_fast_kernel<<<dim3(kOut / 16, B), 256, 0, st>>>(rows, gray256, H, xmin_h, count_h, kk_h, ksize_h);
+  else
+    resample_cols_kernel<<<dim3(kOut, B), kOut, 0, st>>>(rows, gray256, H, xmin_h, count_h, kk_h, ksize_h);
   DFD_LAUNCH_CHECK();
   g_launches.fetch_add(launches + 2, std::memory_order_relaxed);
   return DFD_OK;

@@ -637,7 +637,9 @@ def test_gray256_matches_reference_golden(golden_gray):
             assert np.array_equal(got, want), (h, w, kind, clahe, int((got != want).sum()))
 
 
-@pytest.mark.parametrize("B,H,W", [(5, 384, 384), (3, 224, 224), (2, 100, 37), (1, 1, 1), (2, 600, 9)])
+@pytest.mark.parametrize("B,H,W", [(5, 384, 384), (3, 224, 224), (2, 100, 37), (1, 1, 1), (2, 600, 9),
+                                   # the word-wide CLAHE / resample kernels: tile rows of 16 / 1 / 34 words, more than 8 taps per axis
+                                   (2, 256, 512), (2, 40, 32), (1, 64, 1088), (2, 96, 160), (1, 768, 512)])
 def test_gray256_batched_matches_oracle(B, H, W):
     from dfd import ops
     from oracle import gray_ref as G
