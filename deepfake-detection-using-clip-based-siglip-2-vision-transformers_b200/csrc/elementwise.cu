@@ -203,19 +203,16 @@ __global__ void __launch_bounds__(256) patchify_kernel(PatchArgs a) {
 // Fast path for the case every shipped caller hits (u8 NHWC input already on the patch grid, no resample): one CTA per
 // (image, patch row).  The P image rows of a patch row are one contiguous span of P*Win*3 bytes, and its G output rows
 // one contiguous span of G*lda bf16 — both are moved with 16-byte accesses through shared memory; the k -> (c, ky, kx)
-// index arithmetic becomes a table built once per CTA and the u8 -> normalised fp32 conversion a 256-entry table filled
-// with the same expression as fetch_pixel, so the result is bit-identical to the generic kernel.
+// index arithmetic becomes a table built once per CTA; the bf16 result is bit-identical to the generic kernel's.
 __global__ void __launch_bounds__(256) patchify_u8_rows_kernel(PatchArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int span = a.P * a.Win * 3;
-  float* val = reinterpret_cast<float*>(smem);                         // [256]
-  uint16_t* koff = reinterpret_cast<uint16_t*>(smem + 1024);           // [lda] (0xffff = K padding)
+  uint16_t* koff = reinterpret_cast<uint16_t*>(smem + 1024);           // [lda] (0xffff = K padding); 16-byte aligned
   uint8_t* pix = smem + 1024 + (((int)a.lda * 2 + 15) & ~15);          // [span + 16]
   const int b = blockIdx.x / a.G, gy = blockIdx.x - b * a.G;
   const uint8_t* src = reinterpret_cast<const uint8_t*>(a.pixels) + ((int64_t)b * a.Hin + (int64_t)gy * a.P) * a.Win * 3;
   const int head = (int)(reinterpret_cast<uintptr_t>(src) & 15);       // pix[head + i] = src[i]
   const int tid = threadIdx.x;
-  val[tid] = ((float)tid / 255.0f - 0.5f) / 0.5f;
   const int PP = a.P * a.P;
   for (int k = tid; k < (int)a.lda; k += 256) {
     if (k < a.K) {
@@ -241,11 +238,17 @@ __global__ void __launch_bounds__(256) patchify_u8_rows_kernel(PatchArgs a) {
   for (int idx = tid; idx < a.G * vec_per_row; idx += 256) {
     const int gx = idx / vec_per_row, vcol = idx - gx * vec_per_row;
     const uint8_t* base = a.flip ? pix + head - gx * a.P * 3 : pix + head + gx * a.P * 3;
+    // the eight source offsets of this 16-byte output piece come as ONE 16-byte shared load; ToTensor + Normalize is one FMA:
+    // fmaf(x, 2/255, -1) differs from fetch_pixel's ((x / 255) - 0.5) / 0.5 by an fp32 ulp for some x but rounds to the same
+    // bf16 for all 256 byte values (checked exhaustively, tests/test_abi_cpu.py).  The first version did three shared loads per
+    // element (offset, byte, a 256-entry value table) and sat at the L1 / shared-memory pipe's limit (ncu: l1tex 99 % busy)
+    const uint4 kq = *reinterpret_cast<const uint4*>(koff + vcol * 8);
+    const uint32_t kw[4] = {kq.x, kq.y, kq.z, kq.w};
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const uint32_t o = koff[vcol * 8 + j];
-      v[j] = o == 0xffffu ? 0.f : val[base[o]];
+      const uint32_t o = (kw[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+      v[j] = o == 0xffffu ? 0.f : fmaf((float)base[o], 2.0f / 255.0f, -1.0f);
     }
     uint4 o;
     o.x = pack_bf16x2(v[0], v[1]);

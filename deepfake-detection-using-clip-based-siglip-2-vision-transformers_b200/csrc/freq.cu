@@ -7,13 +7,13 @@
 //                      (Σy..Σy⁴, double), (b) the 2-level Haar energies, (c) 256-point row FFTs — two real
 //                      rows packed into one complex Stockham radix-4 FFT per warp — written as the
 //                      129-column half spectrum to scratch.
-//   freq_cols_kernel   grid (P, B), P = 1..4 CTAs per image so that small batches still fill the SMs (one CTA per
+//   freq_cols_kernel   grid (P, B), P = 1..8 CTAs per image so that small batches still fill the SMs (one CTA per
 //                      image left a 256-image batch latency bound at < 2 CTAs per SM); the CTAs interleave the 129
 //                      columns, write their partial accumulators to scratch, and the last one to finish (ticket) adds
 //                      them in a fixed order.  Each warp runs 256-point column FFTs over its stored columns and folds
-//                      |F|, log|F| and angle(F) of every bin AND of its Hermitian mirror into the band /
-//                      log-radius / sector / phase-histogram accumulators through host-built LUTs of the
-//                      (fft-shifted) 256² grid; thread 0 then finishes the 24 features.
+//                      |F|, log|F| and angle(F) of every bin TOGETHER WITH its Hermitian mirror into the band /
+//                      log-radius / sector / phase-histogram accumulators (lane-private shared-memory bins) through
+//                      host-built LUTs of the (fft-shifted) 256² grid; thread 0 then finishes the 24 features.
 //
 // Per image: 262 144 B read + 264 192 B scratch write + read (L2 resident at these sizes) + 96 B out.
 #include "dfd_common.cuh"
@@ -34,7 +34,7 @@ constexpr int kThreads = 256;
 constexpr int kAccDoubles = 32;  // per-image spatial accumulators: 8 srm moments (2 stencils x 4) + 8 haar + pad
 constexpr int64_t kSpecBytes = (int64_t)kN * kHalf * 8;
 constexpr int kMaxColParts = 8;          // CTAs that may share one image's column pass
-constexpr int kColPartBytes = 2048;      // one CTA's partial accumulators: ColAcc (1928 B) + 3 band energies (double)
+constexpr int kColPartBytes = 2048;      // slot of one CTA's partial accumulators (ColPart, 424 B)
 // per image: half spectrum | spatial accumulators (zeroed per call) | ticket counter (zeroed) + pad | column partials
 constexpr int64_t kZeroBytes = kAccDoubles * 8 + 16;
 constexpr int64_t kImgScratch = kSpecBytes + kZeroBytes + kMaxColParts * kColPartBytes;
@@ -208,47 +208,33 @@ freq_rows_kernel(const float* __restrict__ gray, uint8_t* __restrict__ scratch) 
 }
 
 // ------------------------------------------------------------------------------------------------
-struct ColAcc {
-  float logsum[kThreads / 32][40];
-  float secsum[kThreads / 32][8];
-  int hist[50];
+constexpr int kColWarps = 4;
+constexpr int kColThreads = kColWarps * 32;
+constexpr int kBins = 48;                  // 40 log-radius bins (39 used) + 8 sectors
+// one CTA's contribution to an image, as published to the last CTA of the image
+struct ColPart {
+  float sums[kBins];                       // log-magnitude sums per log-radius bin, then magnitude sums per sector
+  int hist[50];                            // phase histogram
+  int pad[2];
+  double E[3];                             // band energies
 };
-
-static_assert(sizeof(ColAcc) + 24 <= kColPartBytes && sizeof(ColAcc) % 4 == 0, "column-pass partials must fit their slot");
-static_assert(offsetof(ColAcc, hist) == (kThreads / 32) * 48 * 4, "float sums first, integer counts after");
-
-// bins[key] += val for every lane with key >= 0, where `bins` belongs to this warp alone: lanes that share a key are summed
-// with shuffles and one lane adds the total (consecutive bins of a column fall into 1-3 distinct log-radius bins / sectors,
-// so this loop runs 1-3 times; shared-memory float atomics would serialise up to 32-way).  Convergent call required.
-__device__ __forceinline__ void warp_bin_add(float* bins, int key, float val, int lane) {
-  unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
-  while (todo) {
-    const int leader = __ffs(todo) - 1;
-    const int k = __shfl_sync(0xffffffffu, key, leader);
-    const bool mine = key == k;
-    float v = mine ? val : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == leader) bins[k] += v;
-    todo &= ~__ballot_sync(0xffffffffu, mine);
-  }
-  __syncwarp();
-}
+static_assert(sizeof(ColPart) <= kColPartBytes && offsetof(ColPart, E) % 8 == 0, "column-pass partials must fit their slot");
 
 // lut word of the shifted grid position (sy, sx), stored TRANSPOSED (index sx*256 + sy: the lanes of a warp walk sy, so a
 // warp reads 128 contiguous bytes): bits 0-7 band, 8-15 log-radius bin (int8, -1 = not counted), 16-23 sector (int8).
-__device__ __forceinline__ void fold_bin(float re, float im, int sy, int sx, const int32_t* __restrict__ lut, ColAcc* A,
-                                         int* whist, int warp, int lane, double (&eb)[3]) {
-  const int w = __ldg(lut + sx * kN + sy);
-  const float mag = hypotf(re, im);
-  const float ph = atan2f(im, re);
-  const int band = w & 0xff;
-  const double dm = (double)mag;
-  eb[0] += band == 0 ? dm : 0.0;
-  eb[1] += band == 1 ? dm : 0.0;
-  eb[2] += band == 2 ? dm : 0.0;
-  warp_bin_add(A->logsum[warp], (int)(int8_t)(w >> 8), logf(mag + 1e-6f), lane);
-  warp_bin_add(A->secsum[warp], (int)(int8_t)(w >> 16), mag, lane);
+//
+// A bin F(ky, kx) and its Hermitian mirror F(-ky, -kx) = conj(F) are folded TOGETHER (mirrored = true): |F|, log|F| and the
+// angle are computed once — hypotf / logf / atan2f were evaluated twice per stored bin before — the mirror's angle is the
+// negated one, and because the mirror sits at the same radius it shares the band and the log-radius bin
+// (tests/test_oracle_cpu.py checks that symmetry of the host-built table), so those sums take the doubled value in one step.
+// Only the sector (an angle of the grid POSITION) differs: it is read from the mirror's own table word.
+//
+// Accumulators: every LANE owns a private copy of the 48 float bins in shared memory, laid out [bin][lane] (bank = lane: no
+// conflicts, no atomics, no shuffles — a bin update is one load, one add, one store, and the order of a lane's additions is
+// fixed, so the result is bit-reproducible).  The first version reduced every update across the warp with shuffles (lanes that
+// share a key summed, one lane adds): 6-12 shuffles per update, three updates per bin — more instructions than the
+// transcendental functions.  The lanes' copies are summed once per CTA, in a fixed tree.
+__device__ __forceinline__ void phase_count(int* whist, float ph) {
   // torch.histc(bins=50, min=-pi, max=pi): pos = (int)((x - min) / (max - min) * bins), x == max -> last bin
   const float minv = -3.14159274101257324f, maxv = 3.14159274101257324f;
   if (ph >= minv && ph <= maxv) {
@@ -257,17 +243,41 @@ __device__ __forceinline__ void fold_bin(float re, float im, int sy, int sx, con
     atomicAdd(&whist[pos], 1);
   }
 }
+__device__ __forceinline__ void fold_bin(float re, float im, int w, int wm, bool mirrored, float* bins /* [kBins][32] + lane */,
+                                         int* whist, double (&eb)[3]) {
+  const float mag = hypotf(re, im);
+  const float ph = atan2f(im, re);
+  const float lg = logf(mag + 1e-6f);
+  const int band = w & 0xff;
+  const double dm = mirrored ? (double)mag + (double)mag : (double)mag;
+  eb[0] += band == 0 ? dm : 0.0;
+  eb[1] += band == 1 ? dm : 0.0;
+  eb[2] += band == 2 ? dm : 0.0;
+  const int rb = (int)(int8_t)(w >> 8), sc = (int)(int8_t)(w >> 16);
+  if (rb >= 0) bins[rb * 32] += mirrored ? lg + lg : lg;
+  if (sc >= 0) bins[(40 + sc) * 32] += mag;
+  phase_count(whist, ph);
+  if (mirrored) {   // warp-uniform
+    const int scm = (int)(int8_t)(wm >> 16);
+    if (scm >= 0) bins[(40 + scm) * 32] += mag;
+    phase_count(whist, -ph);   // angle(conj F): atan2f is odd in its first argument
+  }
+}
 
-// four CTAs per SM (64 registers): the single-thread finishing stage with its double arrays set the allocation to 116 registers
-// for all 256 threads (two CTAs per SM); with the bound its spills stay in that stage: 0.957 -> 0.765 ms per 512 images
-__global__ void __launch_bounds__(kThreads, 4)
+// five CTAs per SM (<= 102 registers, 45 KB of shared memory each): the kernel is latency bound — ncu at four CTAs: issue slots
+// 31 % busy, 3.4 warps per scheduler — so resident warps, not instructions, set its speed
+__global__ void __launch_bounds__(kColThreads, 5)
 freq_cols_kernel(uint8_t* __restrict__ scratch, const int32_t* __restrict__ lut, float eps, int zscore,
                  float* __restrict__ feats) {
-  __shared__ __align__(16) float2 fbuf[kThreads / 32][2][kN];
+  __shared__ __align__(16) float2 fbuf[kColWarps][2][kN];
   __shared__ float2 tw[kN];
-  __shared__ ColAcc A;
-  __shared__ int whist[kThreads / 32][50];   // phase histogram, one copy per warp
-  __shared__ double ered[kThreads / 32][3];
+  __shared__ float lanebins[kColWarps][kBins][32];
+  __shared__ int whist[kColWarps][50];       // phase histogram, one copy per warp
+  // per-warp sums of the final reduction reuse the FFT buffers (free after the column loop's last barrier): the CTA stays under
+  // 227 KB / 5 of shared memory
+  float (*wsum)[kBins] = reinterpret_cast<float (*)[kBins]>(&fbuf[0][0][0]);
+  double (*ered)[3] = reinterpret_cast<double (*)[3]>(&fbuf[1][0][0]);
+  __shared__ ColPart A;                      // this CTA's totals, then (last CTA of the image) the image's
 
   const int part = blockIdx.x, nparts = gridDim.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -275,21 +285,22 @@ freq_cols_kernel(uint8_t* __restrict__ scratch, const int32_t* __restrict__ lut,
   const float2* spec = reinterpret_cast<const float2*>(img_scratch);
 
   fill_twiddles(tw);
-  for (int i = threadIdx.x; i < (int)(sizeof(ColAcc) / 4); i += kThreads) reinterpret_cast<int*>(&A)[i] = 0;
-  for (int i = threadIdx.x; i < (kThreads / 32) * 50; i += kThreads) (&whist[0][0])[i] = 0;
+  for (int i = threadIdx.x; i < kColWarps * kBins * 32; i += kColThreads) (&lanebins[0][0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < kColWarps * 50; i += kColThreads) (&whist[0][0])[i] = 0;
   __syncthreads();
 
   double eb[3] = {0.0, 0.0, 0.0};
   float2* fa = fbuf[warp][0];
   float2* fb = fbuf[warp][1];
-  // the CTA takes 8 adjacent columns at a time (one per warp): loaded together, every row contributes 64 contiguous bytes
-  for (int kx0 = part * (kThreads / 32); kx0 < kHalf; kx0 += nparts * (kThreads / 32)) {
+  float* bins = &lanebins[warp][0][lane];
+  // the CTA takes kColWarps adjacent columns at a time (one per warp): loaded together, every row contributes 32 contiguous bytes
+  for (int kx0 = part * kColWarps; kx0 < kHalf; kx0 += nparts * kColWarps) {
     {
-      const int c = threadIdx.x & 7, r_in = threadIdx.x >> 3;
+      const int c = threadIdx.x & (kColWarps - 1), r_in = threadIdx.x / kColWarps;
       if (kx0 + c < kHalf) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r_in + 32 * i;
+        for (int i = 0; i < kN / (kColThreads / kColWarps); ++i) {
+          const int r = r_in + (kColThreads / kColWarps) * i;
           fbuf[c][0][r] = __ldg(spec + (int64_t)r * kHalf + kx0 + c);
         }
       }
@@ -297,31 +308,35 @@ freq_cols_kernel(uint8_t* __restrict__ scratch, const int32_t* __restrict__ lut,
     __syncthreads();
     const int kx = kx0 + warp;
     if (kx < kHalf) {
-    fft256_warp(fa, fb, tw, lane);
-    const bool self_col = (kx == 0) || (kx == kN / 2);
-    const int sx = (kx + kN / 2) & (kN - 1);
-    const int sxm = ((kN - kx) + kN / 2) & (kN - 1);
+      const bool self_col = (kx == 0) || (kx == kN / 2);
+      const int sx = (kx + kN / 2) & (kN - 1);
+      const int sxm = ((kN - kx) + kN / 2) & (kN - 1);
+      // the column's table words (its own and its mirror's) are fetched ahead of the FFT: their latency ends under it
+      int w[8], wm[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int ky = lane + 32 * i;
-      float2 v = fa[ky];
-      // the 4 self-conjugate bins of a real image have an exactly-zero imaginary part (torch yields +0)
-      if (self_col && (ky == 0 || ky == kN / 2)) v.y = 0.0f;
-      const int sy = (ky + kN / 2) & (kN - 1);
-      fold_bin(v.x, v.y, sy, sx, lut, &A, whist[warp], warp, lane, eb);
-      if (!self_col) {
-        const int sym = ((kN - ky) + kN / 2) & (kN - 1);
-        fold_bin(v.x, -v.y, sym, sxm, lut, &A, whist[warp], warp, lane, eb);
+      for (int i = 0; i < 8; ++i) {
+        const int ky = lane + 32 * i;
+        w[i] = __ldg(lut + sx * kN + ((ky + kN / 2) & (kN - 1)));
+        wm[i] = __ldg(lut + sxm * kN + (((kN - ky) + kN / 2) & (kN - 1)));
       }
-    }
+      fft256_warp(fa, fb, tw, lane);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int ky = lane + 32 * i;
+        float2 v = fa[ky];
+        // the 4 self-conjugate bins of a real image have an exactly-zero imaginary part (torch yields +0)
+        if (self_col && (ky == 0 || ky == kN / 2)) v.y = 0.0f;
+        fold_bin(v.x, v.y, w[i], wm[i], !self_col, bins, whist[warp], eb);
+      }
     }
     __syncthreads();
   }
-  if (threadIdx.x < 50) {
-    int t = 0;
+  // lanes' private bins -> one sum per warp (fixed shuffle tree) -> one per CTA (warps in order)
+  for (int k = 0; k < kBins; ++k) {
+    float v = bins[k * 32];
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) t += whist[w][threadIdx.x];
-    A.hist[threadIdx.x] = t;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) wsum[warp][k] = v;
   }
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -329,45 +344,58 @@ freq_cols_kernel(uint8_t* __restrict__ scratch, const int32_t* __restrict__ lut,
     if (lane == 0) ered[warp][i] = v;
   }
   __syncthreads();
-  double E[3] = {0.0, 0.0, 0.0};
+  if (threadIdx.x < kBins) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kColWarps; ++w) t += wsum[w][threadIdx.x];
+    A.sums[threadIdx.x] = t;
+  } else if (threadIdx.x < kBins + 50) {
+    const int i = threadIdx.x - kBins;
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < kColWarps; ++w) t += whist[w][i];
+    A.hist[i] = t;
+  } else if (threadIdx.x < kBins + 50 + 3) {
+    const int i = threadIdx.x - kBins - 50;
+    double t = 0.0;
+    for (int w = 0; w < kColWarps; ++w) t += ered[w][i];
+    A.E[i] = t;
+  }
+  __syncthreads();
   if (nparts > 1) {
-    // publish this CTA's partials, take a ticket; the last CTA of the image adds all partials in part order
+    // publish this CTA's totals, take a ticket; the last CTA of the image adds all parts in part order
     __shared__ int s_ticket;
     uint8_t* parts = img_scratch + kSpecBytes + kZeroBytes;
+    constexpr int kWords = (int)(sizeof(ColPart) / 4);
     int* mine = reinterpret_cast<int*>(parts + part * kColPartBytes);
-    for (int i = threadIdx.x; i < (int)(sizeof(ColAcc) / 4); i += kThreads) mine[i] = reinterpret_cast<int*>(&A)[i];
-    if (threadIdx.x < 3) {
-      double t = 0.0;
-      for (int w = 0; w < kThreads / 32; ++w) t += ered[w][threadIdx.x];
-      reinterpret_cast<double*>(parts + part * kColPartBytes + 2048 - 24)[threadIdx.x] = t;
-    }
+    for (int i = threadIdx.x; i < kWords; i += kColThreads) mine[i] = reinterpret_cast<const int*>(&A)[i];
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_ticket = atomicAdd(reinterpret_cast<int*>(img_scratch + kSpecBytes + kAccDoubles * 8), 1);
     __syncthreads();
     if (s_ticket != nparts - 1) return;
     __threadfence();
-    constexpr int kFloatWords = (kThreads / 32) * 48;  // logsum + secsum are float sums, the rest integer counts
-    for (int i = threadIdx.x; i < (int)(sizeof(ColAcc) / 4); i += kThreads) {
-      if (i < kFloatWords) {
-        float t = 0.f;
-        for (int q = 0; q < nparts; ++q) t += __ldcg(reinterpret_cast<const float*>(parts + q * kColPartBytes) + i);
-        reinterpret_cast<float*>(&A)[i] = t;
-      } else {
-        int t = 0;
-        for (int q = 0; q < nparts; ++q) t += __ldcg(reinterpret_cast<const int*>(parts + q * kColPartBytes) + i);
-        reinterpret_cast<int*>(&A)[i] = t;
-      }
+    if (threadIdx.x < kBins) {
+      float t = 0.f;
+      for (int q = 0; q < nparts; ++q) t += __ldcg(reinterpret_cast<const float*>(parts + q * kColPartBytes) + threadIdx.x);
+      A.sums[threadIdx.x] = t;
+    } else if (threadIdx.x < kBins + 50) {
+      const int i = threadIdx.x - kBins;
+      int t = 0;
+      for (int q = 0; q < nparts; ++q)
+        t += __ldcg(reinterpret_cast<const int*>(parts + q * kColPartBytes + offsetof(ColPart, hist)) + i);
+      A.hist[i] = t;
+    } else if (threadIdx.x < kBins + 50 + 3) {
+      const int i = threadIdx.x - kBins - 50;
+      double t = 0.0;
+      for (int q = 0; q < nparts; ++q)
+        t += __ldcg(reinterpret_cast<const double*>(parts + q * kColPartBytes + offsetof(ColPart, E)) + i);
+      A.E[i] = t;
     }
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    for (int q = 0; q < nparts; ++q)
-      for (int i = 0; i < 3; ++i) E[i] += __ldcg(reinterpret_cast<const double*>(parts + q * kColPartBytes + 2048 - 24) + i);
-  } else {
-    if (threadIdx.x != 0) return;
-    for (int w = 0; w < kThreads / 32; ++w)
-      for (int i = 0; i < 3; ++i) E[i] += ered[w][i];
   }
+  if (threadIdx.x != 0) return;
+  const double E[3] = {A.E[0], A.E[1], A.E[2]};
 
   // ---- finish the 24 features (double scalars, like the reference's python floats) ----------------
   const double EPS = (double)eps;
@@ -380,8 +408,7 @@ freq_cols_kernel(uint8_t* __restrict__ scratch, const int32_t* __restrict__ lut,
   {  // slope of mean log-magnitude over the 39 log-radius bins (np.polyfit deg 1, closed form)
     double mu[39], mbar = 0.0;
     for (int i = 0; i < 39; ++i) {
-      double s = 0.0;
-      for (int w = 0; w < kThreads / 32; ++w) s += (double)A.logsum[w][i];
+      const double s = (double)A.sums[i];
       const int cnt = __ldg(lut + kN * kN + i);  // bins per log-radius ring: geometry only, counted by the host
       mu[i] = cnt > 0 ? (double)(float)(s / (double)cnt) : 0.0;
       mbar += mu[i];
@@ -398,8 +425,7 @@ freq_cols_kernel(uint8_t* __restrict__ scratch, const int32_t* __restrict__ lut,
   {  // anisotropy: population variance of the 8 sector means
     double sm[8], mbar = 0.0;
     for (int k = 0; k < 8; ++k) {
-      double s = 0.0;
-      for (int w = 0; w < kThreads / 32; ++w) s += (double)A.secsum[w][k];
+      const double s = (double)A.sums[40 + k];
       const int cnt = __ldg(lut + kN * kN + 40 + k);
       sm[k] = cnt > 0 ? (double)(float)(s / (double)cnt) : 0.0;
       mbar += sm[k];
@@ -469,19 +495,19 @@ int freq_features(const float* gray256, int B, const int32_t* lut, float eps, in
   if (int rc = ensure_dynamic_smem(smem_once, freq_rows_kernel, kRowsSmem)) return rc;
   freq_rows_kernel<<<dim3(kN / kBand, B), kThreads, kRowsSmem, st>>>(gray256, sc);
   DFD_LAUNCH_CHECK();
-  // An image's column pass is 17 groups of 8 columns, dealt round-robin to `parts` CTAs; 4 CTAs fit an SM (64 registers).  Take the
-  // split with the fewest (waves of CTAs) x (groups per CTA): e.g. 512 images -> 3 parts (2 waves x 6 groups, not 2 x 9).
+  // An image's column pass is 33 groups of 4 columns, dealt round-robin to `parts` CTAs; 5 CTAs fit an SM (launch bounds, 45 KB of shared
+  // memory).  Take the split with the fewest (waves of CTAs) x (groups per CTA): e.g. 256 images -> 2 parts (1 wave x 17 groups).
   int parts = 1;
   {
-    const int64_t slots = (int64_t)kNumSMs * 4;
-    const int groups = (kHalf + kThreads / 32 - 1) / (kThreads / 32);
+    const int64_t slots = (int64_t)kNumSMs * 5;
+    const int groups = (kHalf + kColWarps - 1) / kColWarps;
     int64_t best = -1;
     for (int p = 1; p <= kMaxColParts; ++p) {
       const int64_t cost = (((int64_t)B * p + slots - 1) / slots) * ((groups + p - 1) / p);
       if (best < 0 || cost < best) { best = cost; parts = p; }
     }
   }
-  freq_cols_kernel<<<dim3(parts, B), kThreads, 0, st>>>(sc, lut, eps, zscore, feats);
+  freq_cols_kernel<<<dim3(parts, B), kColThreads, 0, st>>>(sc, lut, eps, zscore, feats);
   DFD_LAUNCH_CHECK();
   g_launches.fetch_add(2, std::memory_order_relaxed);
   return DFD_OK;

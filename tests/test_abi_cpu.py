@@ -270,6 +270,20 @@ def test_pipeline_host_helpers_without_a_device():
     assert len(pipeline.DetectionPipeline.MULTICROP_WEIGHTS) == 6 and abs(sum(pipeline.DetectionPipeline.MULTICROP_WEIGHTS) - 1.0) < 1e-12
 
 
+def test_fused_normalise_rounds_to_the_reference_bf16_for_every_byte():
+    """patchify_u8_rows_kernel computes ToTensor + Normalize(.5,.5) as ONE fp32 FMA, fmaf(x, 2/255, -1); the reference chain is
+    ((x / 255) - 0.5) / 0.5 with three fp32 roundings (inference_ai_human_images.py:200-204).  The two differ by an ulp for most
+    bytes but round to the same bf16 for all 256 of them — the exhaustive check behind the kernel's comment."""
+    x = np.arange(256, dtype=np.float32)
+    ref = ((x / np.float32(255.0)) - np.float32(0.5)) / np.float32(0.5)
+    fma = (x.astype(np.float64) * np.float64(np.float32(2.0 / 255.0)) - 1.0).astype(np.float32)   # one rounding, like fmaf
+    assert torch.equal(torch.from_numpy(ref).to(torch.bfloat16), torch.from_numpy(fma).to(torch.bfloat16))
+    tt = torch.arange(256, dtype=torch.uint8).reshape(1, 256, 1).numpy()
+    from torchvision import transforms
+    tv = transforms.Normalize([0.5], [0.5])(transforms.ToTensor()(tt.transpose(1, 2, 0))).reshape(-1)
+    assert torch.equal(tv.to(torch.bfloat16), torch.from_numpy(fma).to(torch.bfloat16))
+
+
 def test_tiled_layout_of_the_low_halves_round_trips():
     """ops.lo_to_tiled / lo_from_tiled: the [row block][64-column chunk][8-column group][row][8] order the GEMM epilogue and
     dfd_layernorm2_bf16 address (element (r, c) at (((r/128·nch + c/64)·8 + (c%64)/8)·128 + r%128)·8 + c%8)."""

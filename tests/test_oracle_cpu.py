@@ -110,6 +110,21 @@ def test_grid_tables_known_answers():
     assert band[128, 128] == 0 and band[0, 0] == 2
 
 
+def test_grid_tables_are_mirror_symmetric_in_band_and_radius():
+    """freq_cols_kernel folds a spectrum bin and its Hermitian mirror together and lets them share the band and the log-radius
+    bin (csrc/freq.cu:fold_bin): the tables of the shifted grid — the oracle's and the product's host-built ones — must be
+    symmetric under (ky, kx) -> (-ky, -kx); the sector is not (it is read per position)."""
+    from dfd import scoring
+
+    band, rbin, sector = S.grid_tables()
+    ky = (np.arange(256) - 128) % 256
+    sym = ((256 - ky) + 128) % 256
+    assert np.array_equal(band[sym][:, sym], band) and np.array_equal(rbin[sym][:, sym], rbin)
+    assert not np.array_equal(sector[sym][:, sym], sector)
+    tb, tr, _ = scoring.build_freq_tables()
+    assert torch.equal(tb[sym][:, sym], tb) and torch.equal(tr[sym][:, sym], tr)
+
+
 def test_heads_and_fusion_oracle(golden_scoring, shipped):
     assert np.abs(S.freq_mlp_g1(shipped["freq"], golden_scoring["feats_zscore"]) - golden_scoring["zfreq_g1"]).max() < 1e-5
     assert np.abs(S.freq_mlp_g2(S.init_freq_mlp_g2(2), golden_scoring["feats_raw"]) - golden_scoring["zfreq_g2"]).max() < 1e-5
