@@ -455,7 +455,10 @@ class DetectionPipeline:
     def detect(self, images_host: torch.Tensor, gray256_host: Optional[torch.Tensor] = None, resize_mode: int = 0,
                clahe: bool = True, pil_resize: Optional[str] = None) -> np.ndarray:
         """Host (ideally pinned) u8 NHWC images [+ f32 gray256; None = computed on the device from the same
-        pixels] -> numpy [B,14] score records."""
+        pixels] -> numpy [B,14] score records.  An empty batch gives an empty [0,14] array (the reference's loops simply do not
+        iterate); the C ABI itself rejects B = 0 with DFD_ERR_SHAPE."""
+        if images_host.shape[0] == 0:
+            return np.zeros((0, len(PACKED_FIELDS)), dtype=np.float32)
         img = images_host.to(self.device, non_blocking=True)
         gray = None if gray256_host is None else gray256_host.to(self.device, non_blocking=True)
         packed = self.pack(self.detect_device(img, gray, resize_mode, clahe, pil_resize))

@@ -941,3 +941,41 @@ def test_gray256_and_resize_on_rectangles_of_a_resident_image(clahe):
     assert not view.is_contiguous()
     assert torch.equal(ops.gray256_from_rgb(view, clahe), ops.gray256_from_rgb(view.contiguous(), clahe))
     assert torch.equal(ops.resize_u8(view, 64, 48), ops.resize_u8(view.contiguous(), 64, 48))
+
+
+# ---------------------------------------------------------------------------------------------------
+# edge cases: empty / out-of-range inputs come back as status codes with a message, never as a launch
+# ---------------------------------------------------------------------------------------------------
+def test_c_abi_rejects_empty_and_out_of_range_inputs():
+    """Every compute entry point validates its shape arguments before it touches the device: B = 0, M = 0, zero-sized images and
+    unsupported head dims return DFD_ERR_SHAPE / DFD_ERR_UNSUPPORTED / DFD_ERR_BAD_ARG with text in dfd_last_error()."""
+    from dfd import _lib
+
+    lib = _lib.load()
+    x = torch.zeros(4096, dtype=torch.uint8, device=DEV)
+    p = x.data_ptr()
+    launches = lib.dfd_launch_count()
+    assert lib.dfd_gemm_bf16(p, 64, p, 64, p, 64, 0, 64, 64, None, None) == -2           # M = 0
+    assert lib.dfd_gemm_bf16(p, 64, p, 64, p, 64, 8, 60, 64, None, None) == -2           # N not a multiple of 8
+    assert lib.dfd_layernorm_bf16(p, 64, p, 64, p, p, 0, 64, 1e-6, None) == -2
+    assert lib.dfd_attention_bf16(p, 192, p, 64, 0, 200, 1, 64, 0.125, None) == -2       # B = 0
+    assert lib.dfd_attention_bf16(p, 3 * 80, p, 80, 1, 200, 1, 80, 0.1, None) == -3      # head dim 80: unsupported
+    assert lib.dfd_freq_features(p, 0, p, 1e-8, 0, p, p, None) == -2
+    assert lib.dfd_clahe_u8(p, 0, 8, 8, 3, p + 2048, p + 1024, None) == -2
+    assert lib.dfd_gray256(p, 1, 0, 8, 1, p, p, p, 5, p, p, p, 5, p, p, None) == -2      # zero-height image
+    assert lib.dfd_gray256_scratch_bytes(0, 8, 8) == 0 and lib.dfd_freq_scratch_bytes(0) == 0
+    assert b":" in lib.dfd_last_error() or len(lib.dfd_last_error()) > 0
+    assert lib.dfd_launch_count() == launches                                              # nothing was launched
+    torch.cuda.synchronize()
+
+
+def test_empty_batches_in_the_python_drivers():
+    """The reference's loops over an empty loader / file list return empty results; so do the drop-in drivers."""
+    from dfd import dropin, train_fusion
+
+    class _M:
+        resolution, device = 64, torch.device(DEV)
+
+    assert train_fusion.extract_siglip_logits(_M(), []).shape == (0,)
+    y, p, f = dropin.run_inference(None, [])
+    assert y.shape == (0,) and p.shape == (0,) and f == []
