@@ -265,11 +265,14 @@ def run_ours(args):
         q = distributed.WorkQueue(key)
         inflight, done, imgs = [], 0, 0
         while True:
+            # claim only when at most one unit is still outstanding on the device (the host stays at most two units ahead): a rank
+            # that claimed first and waited afterwards held up to three units — at the end of the queue those are tail units a
+            # faster GPU could have taken (8 GPUs, 5 steps: 65-71 ms of 1.67 s waiting at the final collective)
+            while len(inflight) >= 2:
+                inflight.pop(0).synchronize()
             u = q.next()
             if u >= len(plan):
                 break
-            if len(inflight) >= 2:            # keep the host at most two units ahead of the device
-                inflight.pop(0).synchronize()
             off, n = plan[u]
             slab[off: off + n] = pipe.pack(pipe.detect_device(unit_images(plan[u], images), None, clahe=True))
             ev = torch.cuda.Event()
