@@ -235,12 +235,15 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     arch_name, default_batch = WORKLOADS[args.workload]
     B = args.batch or default_batch
+    strong = args.global_batch > 0
+    if strong:   # strong scaling: the global batch is fixed, every GPU holds its share of it
+        B = max(1, args.global_batch // world)
     arch = ARCHS[arch_name]
     peaks = load_peaks()
     lib = _lib.load()
     # sub-batch = the unit of the work queue.  One GPU: the whole batch in one call.  Several GPUs: halves of the per-GPU batch
     # (256 images run within 0.1 % of a 512-image call, 128 cost 0.6 %), with a tail of shorter units (unit_plan).
-    sub = args.sub_batch or (B if world == 1 else max(1, B // 2))
+    sub = args.sub_batch or (B if (world == 1 or strong) else max(1, B // 2))
     sub = min(sub, B)
 
     bsd = weights.random_vision_state_dict(arch, seed=0, device=dev)
@@ -447,7 +450,7 @@ def run_ours(args):
     line = {
         "metric": METRICS.get(args.workload, METRIC), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": warm, "ms_per_step": step_ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {arch_name} detect (backbone+H-B head+gray256/CLAHE+freq features+G2 fusion+CORAL)",
                    "per_gpu_batch": B, "global_batch": B * world, "tokens": arch.tokens, "parallelism": f"dp{world}",
                    "sub_batch": sub, "schedule": "one call per step" if world == 1 else
@@ -664,6 +667,8 @@ def main():
                     help="so400m-384 (the driver's headline, BASELINE configs[2]) | base-224 (configs[1]) | latency | cifake "
                          "(configs[3]) | head-train (configs[4]) | library (stock PyTorch eager run of the HF model on the same GPU)")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: fix the GLOBAL batch (e.g. 512) and give every GPU global/N images per step; 0 = weak scaling")
     ap.add_argument("--max-batch", type=int, default=512, help="engine workspace batch (larger batches are chunked)")
     ap.add_argument("--sub-batch", type=int, default=0,
                     help="images per work-queue unit (default: the whole batch on one GPU, a quarter of it on several)")
