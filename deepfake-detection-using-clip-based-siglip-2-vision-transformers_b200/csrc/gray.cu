@@ -589,7 +589,7 @@ extern "C" DFD_API int dfd_gray256_strided(const void* rgb_u8, int64_t row_strid
   else
     resample_rows_kernel<<<dim3(H, B), kOut, 0, st>>>(src, rows, H, W, xmin_w, count_w, kk_w, ksize_w);
   DFD_LAUNCH_CHECK();
-  if (ksize_h <= kTapMax)
+  if (ksize_h <= kTapMax && (uintptr_t)gray256 % 16 == 0)   // float4 stores
     resample_cols_fast_kernel<<<dim3(kOut / 16, B), 256, 0, st>>>(rows, gray256, H, xmin_h, count_h, kk_h, ksize_h);
   else
     resample_cols_kernel<<<dim3(kOut, B), kOut, 0, st>>>(rows, gray256, H, xmin_h, count_h, kk_h, ksize_h);

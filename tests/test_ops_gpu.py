@@ -651,6 +651,24 @@ def test_gray256_batched_matches_oracle(B, H, W):
             assert np.array_equal(got[b], G.gray256_from_rgb_u8(imgs[b], clahe)), (b, clahe)
 
 
+def test_gray256_into_a_4_byte_aligned_output_and_scratch():
+    """The word-wide kernels need 16-byte aligned output rows / 8-byte aligned scratch; pointers that are only 4-byte aligned take
+    the generic kernels — same bits, no misaligned access."""
+    from dfd import _lib, ops
+    from oracle import gray_ref as G
+
+    lib = _lib.load()
+    B, H, W = 2, 64, 64
+    imgs = np.stack([G.synthetic_rgb(H, W, "waves", 40 + b) for b in range(B)])
+    want = np.stack([G.gray256_from_rgb_u8(im, True) for im in imgs])
+    d = torch.from_numpy(imgs).to(DEV)
+    out_buf = torch.zeros(B * 256 * 256 + 1, device=DEV)
+    scr_buf = torch.zeros(lib.dfd_gray256_scratch_bytes(B, H, W) + 4, dtype=torch.uint8, device=DEV)
+    got = ops.gray256_from_rgb(d, True, scratch=scr_buf[4:], out=out_buf[1:].view(B, 256, 256))
+    assert got.data_ptr() % 16 == 4
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
 def test_gray256_full_size_properties():
     """BASELINE batch (512 x 384 x 384): batch-permutation equivariance and range, no oracle at this size."""
     from dfd import ops
