@@ -270,6 +270,47 @@ def test_pipeline_host_helpers_without_a_device():
     assert len(pipeline.DetectionPipeline.MULTICROP_WEIGHTS) == 6 and abs(sum(pipeline.DetectionPipeline.MULTICROP_WEIGHTS) - 1.0) < 1e-12
 
 
+def test_decode_only_loader_and_strong_scaling_unit_plan(tmp_path):
+    """Host-side pieces of the device-preprocess path (no GPU): `decode_only` + `ragged_collate` hand the DataLoader's samples over
+    as a list of u8 HWC tensors of their decoded sizes (inference_ai_human_images.py:155-192 without the host Resize), rows without
+    a file are dropped like the reference does; and bench.py's work-queue plan covers every image exactly once for weak and strong
+    scaling shapes."""
+    import importlib.util
+
+    from PIL import Image
+
+    from dfd import dropin
+
+    rng = np.random.default_rng(0)
+    rows, sizes = [], [(40, 50), (64, 64), (33, 71)]
+    for i, (h, w) in enumerate(sizes):
+        Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).save(tmp_path / f"i{i}.png")
+        rows.append(f"i{i}.png,{i % 2}")
+    rows.append("gone.png,1")
+    (tmp_path / "meta.csv").write_text("file_name,label\n" + "\n".join(rows) + "\n")
+    ds = dropin.AIHumanDataset(tmp_path, tmp_path / "meta.csv", transform=dropin.decode_only)
+    assert len(ds) == 3
+    ld = torch.utils.data.DataLoader(ds, batch_size=2, shuffle=False, collate_fn=dropin.ragged_collate)
+    batches = list(ld)
+    assert [len(b[0]) for b in batches] == [2, 1] and batches[0][1].tolist() == [0, 1] and batches[1][2] == ["i2.png"]
+    got = [tuple(t.shape) for b in batches for t in b[0]]
+    assert got == [(h, w, 3) for h, w in sizes] and all(t.dtype == torch.uint8 for b in batches for t in b[0])
+    with Image.open(tmp_path / "i2.png") as pil:
+        assert np.array_equal(batches[1][0][0].numpy(), np.asarray(pil.convert("RGB")))
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for total, world, B, sub in [(5 * 512, 1, 512, 512), (5 * 4096, 8, 512, 256), (10 * 512, 8, 64, 64), (10 * 512, 2, 256, 256),
+                                 (3 * 96, 4, 24, 12)]:
+        plan = bench.unit_plan(total, world, B, sub)
+        assert plan[0][0] == 0 and sum(n for _, n in plan) == total
+        assert all(plan[i][0] + plan[i][1] == plan[i + 1][0] for i in range(len(plan) - 1))    # contiguous, no overlap
+        assert all(0 < n <= sub for _, n in plan)
+        if world > 1 and sub % 4 == 0:
+            assert plan[-1][1] <= sub // 4          # the queue ends in quarter-size units
+
+
 def test_fused_normalise_rounds_to_the_reference_bf16_for_every_byte():
     """patchify_u8_rows_kernel computes ToTensor + Normalize(.5,.5) as ONE fp32 FMA, fmaf(x, 2/255, -1); the reference chain is
     ((x / 255) - 0.5) / 0.5 with three fp32 roundings (inference_ai_human_images.py:200-204).  The two differ by an ulp for most
