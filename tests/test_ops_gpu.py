@@ -997,3 +997,54 @@ def test_empty_batches_in_the_python_drivers():
     assert train_fusion.extract_siglip_logits(_M(), []).shape == (0,)
     y, p, f = dropin.run_inference(None, [])
     assert y.shape == (0,) and p.shape == (0,) and f == []
+
+
+def test_streaming_kernels_write_only_their_own_bytes():
+    """Guard bands around every output and scratch buffer of the word-wide kernels (gray256, per-channel CLAHE, frequency
+    features, patchify): sentinel bytes before and after each buffer survive the call (compute-sanitizer is not available on the
+    pool; the results themselves are checked bit for bit by the tests above)."""
+    from dfd import _lib, ops, scoring
+
+    lib = _lib.load()
+    G = 4096                                   # guard bytes on either side
+
+    def guarded(nbytes, fill=0xA5):
+        buf = torch.full((nbytes + 2 * G,), fill, dtype=torch.uint8, device=DEV)
+        return buf, buf[G: G + nbytes]
+
+    def intact(buf, nbytes, fill=0xA5):
+        return bool((buf[:G] == fill).all()) and bool((buf[G + nbytes:] == fill).all())
+
+    for (B, H, W) in [(3, 384, 384), (2, 224, 224), (2, 96, 160), (2, 100, 37)]:
+        img = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=DEV)
+        n_scr = lib.dfd_gray256_scratch_bytes(B, H, W)
+        scr_buf, scr = guarded(n_scr)
+        out_buf, out = guarded(B * 256 * 256 * 4)
+        gray = ops.gray256_from_rgb(img, True, scratch=scr, out=out.view(torch.float32).view(B, 256, 256))
+        torch.cuda.synchronize()
+        assert intact(scr_buf, n_scr) and intact(out_buf, B * 256 * 256 * 4), ("gray256", B, H, W)
+        # frequency features: scratch + [B,24] output
+        n_f = lib.dfd_freq_scratch_bytes(B)
+        f_buf, f_scr = guarded(n_f)
+        luts = scoring.build_freq_luts(torch.device(DEV))
+        feats = ops.freq_features(gray, luts, scratch=f_scr)
+        torch.cuda.synchronize()
+        assert intact(f_buf, n_f) and bool(torch.isfinite(feats).all()), ("freq", B)
+        # per-channel CLAHE through the C ABI with guarded LUT scratch and destination
+        n_l = lib.dfd_clahe_scratch_bytes(B, 3)
+        l_buf, l_scr = guarded(n_l)
+        d_buf, dst = guarded(B * H * W * 3)
+        assert lib.dfd_clahe_u8(img.data_ptr(), B, H, W, 3, l_scr.data_ptr(), dst.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        assert intact(l_buf, n_l) and intact(d_buf, B * H * W * 3), ("clahe", B, H, W)
+        assert torch.equal(dst.view(B, H, W, 3), ops.clahe_u8(img))
+    for (S, P, B) in [(384, 14, 3), (224, 16, 2)]:
+        img = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8, device=DEV)
+        Gd = S // P
+        lda = (3 * P * P + 63) // 64 * 64
+        n_a = B * Gd * Gd * lda * 2
+        a_buf, a = guarded(n_a)
+        assert lib.dfd_patchify(img.data_ptr(), 0, B, S, S, S, P, 0, a.data_ptr(), lda, None) == 0
+        torch.cuda.synchronize()
+        assert intact(a_buf, n_a), ("patchify", S, P)
+        assert torch.equal(a.view(torch.bfloat16).view(B * Gd * Gd, lda), ops.patchify(img, S, P))
