@@ -219,6 +219,50 @@ def make_gray():
     print("gray golden:", len(outs), "images")
 
 
+PREPROCESS_CASES = [(97, 64, "noise", 5), (512, 384, "edges", 6), (300, 451, "waves", 4), (224, 224, "waves", 2)]  # gray_ref.synthetic_rgb
+PREPROCESS_TRAIN_CASES = 2      # the training preprocess always emits 384 x 384 x 3 (442 KB each): first two cases only
+PREPROCESS_TTA_SIZE = 96
+
+
+def make_preprocess():
+    """The pixels the backbone sees, through the reference's OWN transform objects on the seeded images of
+    oracle/gray_ref.py: (1) `preprocess` of train_fusion_head_only.py:60-74 (apply_clahe -> Resize((384,384)) -> ToTensor ->
+    Normalize), (2) the "Original" and "H-Flip" entries of create_tta_transforms (inference_ai_human_images.py:195-215) at 96 pixels.
+    Stored as the u8 pixels behind the normalised tensor (the normalisation is inverted exactly and checked): what dfd_clahe_u8 +
+    dfd_resize_u8 (+ the patch kernel's mirrored read) must reproduce bit for bit."""
+    from PIL import Image
+    from torchvision import transforms
+
+    from oracle import gray_ref as G
+
+    ns = base_namespace()
+    ns["transforms"] = transforms
+    tr = extract(f"{REF}/train_fusion_head_only.py", {"IMG_SIZE", "apply_clahe", "preprocess"}, ns)
+    inf = base_namespace()
+    inf["transforms"] = transforms
+    extract(f"{REF}/inference_ai_human_images.py", {"create_tta_transforms"}, inf)
+    tta = inf["create_tta_transforms"](PREPROCESS_TTA_SIZE, 2)
+    assert [n for n, _ in tta] == ["Original", "H-Flip"] and tr["IMG_SIZE"] == 384
+
+    def to_u8(t):
+        u8 = torch.round((t * 0.5 + 0.5) * 255.0).to(torch.uint8)
+        assert torch.equal((u8.float() / 255.0 - 0.5) / 0.5, t)          # ToTensor + Normalize of exactly these bytes
+        return u8.permute(1, 2, 0).contiguous().numpy()                  # HWC
+
+    train, orig = [], []
+    for i, (h, w, kind, seed) in enumerate(PREPROCESS_CASES):
+        pil = Image.fromarray(G.synthetic_rgb(h, w, kind, seed), "RGB")
+        if i < PREPROCESS_TRAIN_CASES:
+            train.append(to_u8(tr["preprocess"](pil)))
+        orig.append(to_u8(tta[0][1](pil)))
+        # the reference's H-Flip transform is the mirror image of its Original one, byte for byte: only the latter is stored
+        assert np.array_equal(to_u8(tta[1][1](pil)), orig[-1][:, ::-1])
+    np.savez_compressed(os.path.join(OUT, "preprocess_golden.npz"), train_u8=np.stack(train), tta_original_u8=np.stack(orig),
+                        tta_size=np.int32(PREPROCESS_TTA_SIZE),
+                        cases=np.array([c[:2] + (c[3],) for c in PREPROCESS_CASES], dtype=np.int32))
+    print("preprocess golden:", len(train), "images")
+
+
 def make_freq_train():
     """Loss and gradients of the reference's OWN FreqMLP class ("FreqMLP trainer.py":218-301) in eval mode (no dropout)
     under autograd, for seeded weights / features — pins oracle.scoring_ref.freq_mlp_g2_loss_and_grads."""
@@ -355,9 +399,11 @@ def make_backbone():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["scoring", "heads", "backbone", "gray", "freq_train", "decoder"]
+    which = sys.argv[1:] or ["scoring", "heads", "backbone", "gray", "freq_train", "decoder", "preprocess"]
     if "gray" in which:
         make_gray()
+    if "preprocess" in which:
+        make_preprocess()
     if "freq_train" in which:
         make_freq_train()
     if "decoder" in which:

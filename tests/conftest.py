@@ -57,6 +57,11 @@ def golden_decoder():
 
 
 @pytest.fixture(scope="session")
+def golden_preprocess():
+    return np.load(os.path.join(GOLDEN, "preprocess_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_gray():
     return np.load(os.path.join(GOLDEN, "gray_golden.npz"))
 

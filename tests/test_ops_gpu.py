@@ -711,6 +711,30 @@ def test_clahe_u8_per_channel_is_bit_exact(B, H, W, C):
             assert np.array_equal(got[b, :, :, c], cl.apply(np.ascontiguousarray(imgs[b, :, :, c])))
 
 
+def test_device_preprocess_matches_reference_golden(golden_preprocess):
+    """dfd_clahe_u8 + dfd_resize_u8 against the pixels of the reference's own `preprocess` object (train_fusion_head_only.py:60-74)
+    and of its TTA transforms (inference_ai_human_images.py:195-215), generated in the build container by oracle/make_golden.py;
+    the H-Flip view is the mirror of the Original one there, and here the patch kernel's DFD_FLIP_H read of the same pixels."""
+    from dfd import ops, train_fusion
+    from oracle import gray_ref as G
+
+    g = golden_preprocess
+    cases = [(97, 64, "noise", 5), (512, 384, "edges", 6), (300, 451, "waves", 4), (224, 224, "waves", 2)]
+    S = int(g["tta_size"])
+    for i, (h, w, kind, seed) in enumerate(cases):
+        rgb = G.synthetic_rgb(h, w, kind, seed)
+        d = torch.from_numpy(rgb).to(DEV)[None]
+        got = ops.resize_u8(d, S, S, "bilinear")[0]
+        assert np.array_equal(got.cpu().numpy(), g["tta_original_u8"][i]), ("tta", h, w)
+        P = 16
+        a_flip = ops.patchify(got[None].contiguous(), S, P, resize_mode=ops.FLIP_H)
+        a_ref = ops.patchify(torch.from_numpy(np.ascontiguousarray(g["tta_original_u8"][i][:, ::-1])).to(DEV)[None], S, P)
+        assert torch.equal(a_flip, a_ref)
+        if i < len(g["train_u8"]):
+            dev = train_fusion.preprocess_on_device(rgb, 384, torch.device(DEV))
+            assert np.array_equal(dev.cpu().numpy(), g["train_u8"][i]), ("train", h, w)
+
+
 def test_clahe_u8_rejects_in_place_and_bad_shapes():
     from dfd import _lib
 

@@ -176,6 +176,28 @@ def test_gray_oracle_matches_reference_golden(golden_gray):
             assert np.array_equal(G.gray256_from_rgb_u8(rgb, clahe), want), (h, w, kind, clahe)
 
 
+def _preprocess_cases():
+    from oracle import gray_ref as G
+
+    return [(97, 64, "noise", 5), (512, 384, "edges", 6), (300, 451, "waves", 4), (224, 224, "waves", 2)], G
+
+
+def test_preprocess_oracle_matches_reference_golden(golden_preprocess):
+    """oracle/gray_ref.py (per-channel CLAHE + Pillow bilinear Resize) against the pixels the reference's OWN transform objects
+    produce: `preprocess` of train_fusion_head_only.py:60-74 and the Original / H-Flip entries of create_tta_transforms
+    (inference_ai_human_images.py:195-215), run by oracle/make_golden.py."""
+    cases, G = _preprocess_cases()
+    g = golden_preprocess
+    assert [tuple(c) for c in g["cases"]] == [(h, w, s) for h, w, _, s in cases]
+    S = int(g["tta_size"])
+    for i, (h, w, kind, seed) in enumerate(cases):
+        rgb = G.synthetic_rgb(h, w, kind, seed)
+        assert np.array_equal(G.resize_u8(rgb, S, S, "bilinear"), g["tta_original_u8"][i]), ("tta", h, w)
+        if i < len(g["train_u8"]):
+            cl = np.stack([G.clahe_u8(np.ascontiguousarray(rgb[..., c])) for c in range(3)], -1)
+            assert np.array_equal(G.resize_u8(cl, 384, 384, "bilinear"), g["train_u8"][i]), ("train", h, w)
+
+
 def test_gray_oracle_matches_installed_libraries():
     """Stage by stage against Pillow / OpenCV as installed (skipped where they are missing)."""
     PIL_Image = pytest.importorskip("PIL.Image")
